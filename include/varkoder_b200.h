@@ -1,0 +1,157 @@
+/*
+ * varkoder_b200.h -- C ABI of the B200-native varKoder image hot path.
+ *
+ * Scope: cleaned FASTQ reads -> (sub-sample ladder) -> canonical k-mer counts -> varKode / CGR pixels,
+ * i.e. steps C-E of run_clean2img in the reference (varKoder/commands/image.py:1005-1125).  The reference
+ * has no FFI for this path: it shells out to reformat.sh, dsk and dsk2ascii and finishes in pandas/numpy.
+ * Each entry point below names the reference code it stands in for.  Plain pointers and sizes only; every
+ * function returns 0 on success or a negative VK_E* code, with a thread-local message in vk_last_error().
+ *
+ * All device work of one context runs on one internal CUDA stream of one GPU.  A context is not
+ * thread-safe; use one per (thread, device).  Host buffers may be pageable or pinned.
+ *
+ * K-mer index convention of every histogram that crosses this boundary ("lex index"): first base most
+ * significant, A=0 C=1 G=2 T=3, so index = sum code(b_i) * 4^(k-1-i).
+ */
+#ifndef VARKODER_B200_H
+#define VARKODER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VK_ABI_VERSION 1
+#define VK_MAX_LEVELS 64 /* ladder levels: 3 per decade, far more than any real sample needs */
+#define VK_MIN_K 5       /* ImageCommand.__init__ accepts k in [5, 9] (image.py:1209) */
+#define VK_MAX_K 9
+#define VK_BREAKLENGTH 500 /* reformat.sh breaklength=500 (image.py:586) */
+
+enum {
+    VK_OK = 0,
+    VK_EINVAL = -1,   /* bad argument */
+    VK_ECUDA = -2,    /* CUDA runtime error (message holds cudaGetErrorString) */
+    VK_ENOMEM = -3,
+    VK_ESTATE = -4,   /* call order violated (e.g. count before parse) */
+    VK_ERANGE = -5    /* input outside supported range (read longer than 2^24-1 bases, buffer >= 2^40 B) */
+};
+
+/* status of the ladder, vk_result.status */
+enum {
+    VK_LADDER_OK = 0,
+    VK_LADDER_LESS_THAN_MIN = 1 /* split_fastq raises Exception("Input file has less than minimum data.") image.py:674-680 */
+};
+
+typedef struct vk_ctx vk_ctx;
+
+/* Options of one sample; mirrors the arguments of split_fastq (image.py:629-640) and count_kmers (:727-734). */
+typedef struct vk_params {
+    int32_t k;             /* kmer_size, 5..9 */
+    int32_t is_query;      /* split_fastq(is_query=...): single level, no min_bp check */
+    int32_t has_max_bp;    /* 0 <=> max_bp is None (cli.py:496-501 maps "--max-bp 0" to None) */
+    int32_t breaklength;   /* reformat.sh breaklength; VK_BREAKLENGTH for parity, 0 disables */
+    uint64_t min_bp;
+    uint64_t max_bp;
+    uint64_t seed;         /* split_fastq(seed=...) reduced mod 2^64 */
+    uint64_t read_index_base; /* global index of this buffer's first record (read-sharded samples) */
+    uint64_t nsites_override; /* 0: ladder from this buffer's own base count; else the sample-wide total */
+} vk_params;
+
+/* What parsing found; mirrors the first loop of split_fastq (image.py:662-667). */
+typedef struct vk_stats {
+    uint64_t n_bytes;
+    uint64_t n_lines;      /* lines as Python's binary line iterator yields them */
+    uint64_t n_reads;      /* sequence lines (line index % 4 == 1) */
+    uint64_t nsites;       /* sum(len(line) - 1) over sequence lines, exactly as the reference counts */
+    uint64_t nsites_true;  /* bases really present (differs by one only for an unterminated last sequence line) */
+} vk_stats;
+
+/* Ladder and realised sub-samples; level 0 is the largest. */
+typedef struct vk_result {
+    vk_stats stats;
+    int32_t status;        /* VK_LADDER_* */
+    int32_t n_levels;
+    uint64_t level_bp[VK_MAX_LEVELS];    /* sites_per_file (image.py:669-695): the target named in the file */
+    uint64_t level_reads[VK_MAX_LEVELS]; /* reads realised in each (nested) level, reads shorter than k excluded */
+    uint64_t level_bases[VK_MAX_LEVELS]; /* bases realised in each level */
+} vk_result;
+
+int vk_abi_version(void);
+const char* vk_last_error(void);
+
+int vk_ctx_create(int device, vk_ctx** out);
+int vk_ctx_destroy(vk_ctx* ctx);
+
+/*
+ * Pixel table of one (k, mapping): replaces get_kmer_mapping / get_cgr (core/utils.py:152-217) and the
+ * join + groupby + scatter of make_image (image.py:900-913).  lut[row * side + col] = lex index of a k-mer
+ * of the canonical class shown at that pixel of the FINAL image (row = H-1-y, col = x), or -1 if unused.
+ * slot: 0..3, lets a context keep several tables (e.g. varKode and cgr) resident.
+ */
+int vk_set_mapping(vk_ctx* ctx, int slot, int k, int side, const int32_t* lut_host);
+
+/*
+ * Input: the uncompressed bytes of <int>/clean_reads/<sample>.fq.gz (image.py:971).
+ * vk_upload copies host bytes into a context-owned device buffer (pinned staging, async chunks);
+ * vk_attach uses caller-owned device memory (16-byte aligned; readable up to the next 16-byte boundary).
+ */
+int vk_upload(vk_ctx* ctx, const void* host_bytes, uint64_t n_bytes);
+int vk_attach(vk_ctx* ctx, const void* dev_bytes, uint64_t n_bytes);
+
+/* FASTQ framing + base count: the gzip line loop of split_fastq (image.py:662-667). Synchronises. */
+int vk_parse(vk_ctx* ctx, vk_stats* out);
+
+/*
+ * Ladder (image.py:669-695), seeded nested sub-sampling (stands in for reformat.sh, image.py:577-627) and
+ * k-mer counting of every level in one pass over the reads (stands in for dsk, image.py:771-796).
+ * seg_hist_dev: nullable caller-owned DEVICE buffer of VK_MAX_LEVELS * 4^k uint64 that receives (is
+ * overwritten with) per-segment forward-strand histograms in the internal index order; segment s holds
+ * the reads that are in levels 0..s but not in s+1, so sums over ranks/shards are meaningful (NCCL
+ * all-reduce between vk_count and vk_render).  NULL uses a context-owned buffer.  Synchronises.
+ */
+int vk_count(vk_ctx* ctx, const vk_params* params, uint64_t* seg_hist_dev, vk_result* out);
+
+/*
+ * Canonical fold + pixel mapping + rank scaling for n_levels levels (stands in for dsk2ascii and
+ * make_image's numpy half, image.py:875-919).
+ * canon_host: nullable, n_levels * 4^k uint64, canon[l][K] = canon[l][rc K] = abundance of the canonical
+ *             class of K in level l (lex index) -- what dsk2ascii would print for min(K, rc K).
+ * pixels_host: nullable, n_levels * side * side uint8, the PNG pixels (mode "L") of each level.
+ * Synchronises.
+ */
+int vk_render(vk_ctx* ctx, int slot, int k, int n_levels, const uint64_t* seg_hist_dev,
+              uint64_t* canon_host, uint8_t* pixels_host);
+
+/*
+ * Pixel mapping + rank scaling from canonical counts that are already on the host (lex index, n * 4^k uint64,
+ * as returned in canon_host above): the part of make_image after the dsk2ascii dump (image.py:897-919).
+ */
+int vk_render_counts(vk_ctx* ctx, int slot, int k, int n, const uint64_t* canon_host, uint8_t* pixels_host);
+
+/*
+ * Whole path without intermediate host synchronisation: parse -> ladder -> count -> render.
+ * text: host bytes (on_device = 0; copied in the timed path) or device bytes (on_device = 1).
+ * Outputs as in vk_count / vk_render; pixels_host must hold VK_MAX_LEVELS * side * side bytes unless
+ * max_levels_out is smaller (then at most that many levels are copied back).
+ */
+int vk_reads_to_images(vk_ctx* ctx, const void* text, uint64_t n_bytes, int on_device, const vk_params* params,
+                       int slot, int max_levels_out, vk_result* result, uint64_t* canon_host, uint8_t* pixels_host);
+
+/* Device time of the last vk_reads_to_images / stage call, per kernel group, in milliseconds (CUDA events on
+ * the context stream): [0] upload, [1] parse, [2] plan+bucket, [3] count, [4] reduce+fold, [5] render, [6] total. */
+int vk_last_timings(vk_ctx* ctx, float* ms7);
+
+/* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
+uint64_t vk_launch_count(vk_ctx* ctx);
+
+/* Deterministic synthetic FASTQ (bench / tests): fills a DEVICE buffer.
+ * Fixed read length L: record r occupies bytes [r*(2L+17), (r+1)*(2L+17)); returns bytes written in *n_out. */
+int vk_synth_fastq(vk_ctx* ctx, void* dev_bytes, uint64_t capacity, uint64_t n_bases, int read_len, uint64_t seed,
+                   uint64_t first_read, uint64_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VARKODER_B200_H */

@@ -1,0 +1,291 @@
+"""GPU suite: the CUDA path (through the C ABI) against the CPU oracle, the committed golden vectors and
+size-independent properties.  Integer work: every comparison is bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import dsk, image as oimg
+from tests.helpers import fastq, oracle_images, oracle_levels, rand_reads
+from varkoder_b200 import synth
+from varkoder_b200.engine import Params
+from varkoder_b200.mapping import get_kmer_mapping
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_counts(engine, buf, params, table=None):
+    engine.upload(buf)
+    st = engine.parse()
+    res = engine.count(params)
+    canon, pixels = engine.render(table, params.k, len(res.levels))
+    return st, res, canon, pixels
+
+
+# ------------------------------------------------------------------------------------------- framing
+EDGE_FASTQ = {
+    "plain": fastq(["ACGTACGTAC", "GGGGGGGGGGGG", "ACGTNACGTACGTACG"]),
+    "no_final_newline": fastq(["ACGTACGTAC", "TTTTGGGGCCCCAAAA"], final_newline=False),
+    "unterminated_seq_line": b"@h\nACGTACGTACGT\n+\nIIIIIIIIIIII\n@h2\nACGTACGTAAAA",
+    "header_only_tail": fastq(["ACGTACGTACGT"]) + b"@h2\n",
+    "empty": b"",
+    "only_newlines": b"\n\n\n\n\n\n\n\n\n",
+    "empty_reads": fastq(["", "ACGTACGTACGTAA", "", "AC", ""]),
+    "quality_starts_with_at_plus": fastq(["ACGTACGTAC", "CCCCGGGGTT"], quals=["@@@@@@@@@@", "++++++++++"]),
+    "lowercase_and_iupac": fastq(["acgtacgtacgtRYKMacgtacgtacgt", "ACGTNNNNACGTACGTACGT.-ACGTACGTACGT"]),
+    "truncated_record": fastq(["ACGTACGTACGT"]) + b"@t\nACGTACGTACGT\n+",
+    "crlf": b"@h\r\nACGTACGTACGT\r\n+\r\nIIIIIIIIIIII\r\n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(EDGE_FASTQ))
+def test_framing_edge_cases(engine, name):
+    buf = EDGE_FASTQ[name]
+    p = dsk.parse_fastq(buf)
+    engine.upload(buf)
+    st = engine.parse()
+    assert st["n_bytes"] == len(buf)
+    assert st["n_lines"] == p["n_lines"]
+    assert st["n_reads"] == p["n_reads"]
+    assert st["nsites"] == p["nsites_ref"]
+    assert st["nsites_true"] == p["nsites_true"]
+    for k in (5, 7):
+        res = engine.count(Params(k=k, min_bp=0, max_bp=None))
+        canon, _ = engine.render(None, k, len(res.levels))
+        if res.levels:
+            assert res.levels[0] == p["nsites_ref"]
+            assert (canon[0] == dsk.canonical_counts(buf, k)).all()
+
+
+def test_framing_across_tile_boundaries(engine):
+    # records straddling the 16 KiB parse tiles and the 64-byte thread spans, with every alignment
+    rng = np.random.default_rng(11)
+    reads = rand_reads(rng, 3000, 0, 300, p_n=0.01)
+    buf = fastq(reads, headers=["@" + "h" * int(rng.integers(1, 40)) for _ in reads])
+    p = dsk.parse_fastq(buf)
+    engine.upload(buf)
+    st = engine.parse()
+    assert (st["n_reads"], st["nsites"], st["n_lines"]) == (p["n_reads"], p["nsites_ref"], p["n_lines"])
+
+
+# ----------------------------------------------------------------------------------- counts (dsk stand-in)
+@pytest.mark.parametrize("k", [5, 6, 7, 8, 9])
+def test_counts_bit_exact_single_level(engine, k):
+    rng = np.random.default_rng(100 + k)
+    reads = rand_reads(rng, 2500, 0, 260, p_n=0.004) + ["G" * 200, "A" * 33, "ACGT" * 40, "N" * 50, ""]
+    buf = fastq(reads)
+    _, res, canon, _ = gpu_counts(engine, buf, Params(k=k, min_bp=0, max_bp=None, is_query=True))
+    assert len(res.levels) == 1
+    expect = dsk.canonical_counts(buf, k)
+    assert (canon[0] == expect).all()
+    # conservation (SURVEY 8c golden 4): sum of canonical counts over classes = number of valid windows
+    assert int(canon[0].sum()) == int(expect.sum())
+
+
+@pytest.mark.parametrize("k", [7, 9])
+def test_counts_long_reads_breaklength(engine, k):
+    rng = np.random.default_rng(5)
+    reads = rand_reads(rng, 40, 400, 2600, p_n=0.002) + ["ACGT" * 300, "G" * 1001, "A" * 500, "C" * 501, "T" * 499]
+    buf = fastq(reads)
+    _, res, canon, _ = gpu_counts(engine, buf, Params(k=k, min_bp=0, max_bp=None, is_query=True))
+    assert (canon[0] == dsk.canonical_counts(buf, k)).all()
+    _, res, canon, _ = gpu_counts(engine, buf, Params(k=k, min_bp=0, max_bp=None, is_query=True, breaklength=0))
+    assert (canon[0] == dsk.canonical_counts(buf, k, breaklen=0)).all()
+
+
+@pytest.mark.parametrize("k,seed", [(7, 1), (7, "1234567890123"), (5, 42), (8, 7)])
+def test_ladder_levels_bit_exact(engine, k, seed):
+    """every ladder level = oracle counts over exactly the reads the seeded rule selects."""
+    buf = synth.variable(9000, seed=3, k=k).tobytes()
+    p = dsk.parse_fastq(buf)
+    params = Params(k=k, min_bp=20000, max_bp=1_000_000, seed=seed)
+    _, res, canon, _ = gpu_counts(engine, buf, params)
+    expect_levels = oimg.ladder(p["nsites_ref"], 20000, 1_000_000)
+    assert res.levels == expect_levels and len(res.levels) >= 4
+    from varkoder_b200.ladder import parse_seed
+    expect = oracle_levels(buf, k, parse_seed(seed), res.levels, p["nsites_ref"])
+    assert (canon == expect).all()
+    # nested levels: counts are monotone down the ladder; realised bases are near the target
+    assert (canon[:-1] >= canon[1:]).all()
+    for lvl, bp in enumerate(res.levels):
+        sel = dsk.select_reads(p["n_reads"], parse_seed(seed), bp, p["nsites_ref"])
+        keep = sel.astype(bool) & (p["lens"] >= k)
+        assert res.level_reads[lvl] == int(keep.sum())
+        assert res.level_bases[lvl] == int(p["lens"][keep].sum())
+
+
+def test_ladder_golden_on_device(engine, golden_dir):
+    """plan_kernel's integer ladder == the reference's split_fastq ladders (golden, made by the reference)."""
+    with open(os.path.join(golden_dir, "ladder.json")) as f:
+        cases = json.load(f)
+    buf = fastq(["ACGTACGTACGTACGT"] * 4)
+    engine.upload(buf)
+    engine.parse()
+    for c in cases:
+        res = engine.count(Params(k=5, min_bp=c["min_bp"], max_bp=c["max_bp"], is_query=c["is_query"],
+                                  nsites_override=c["nsites"]))
+        if "raises" in c:
+            assert res.status == 1 and res.levels == []
+        else:
+            assert res.status == 0 and res.levels == c["sites"]
+
+
+def test_read_sharding_sums_to_whole(engine):
+    """read-sharded sample: per-shard segment counts with global read indices and the sample-wide nsites add up
+    to the unsharded result (what the NCCL all-reduce computes)."""
+    k = 7
+    buf = synth.variable(6000, seed=8, k=k).tobytes()
+    p = dsk.parse_fastq(buf)
+    params = Params(k=k, min_bp=20000, max_bp=None, seed=77)
+    _, res, whole, _ = gpu_counts(engine, buf, params)
+    cut_read = 2500
+    cut = int(p["starts"][cut_read]) - 1
+    while buf[cut - 1:cut] != b"\n" or buf[cut:cut + 1] != b"@":       # back to the start of that record's header
+        cut -= 1
+    # record boundary = header start: find via the oracle's own table (header precedes the sequence line)
+    shards = [(buf[:cut], 0), (buf[cut:], cut_read)]
+    assert dsk.parse_fastq(shards[0][0])["n_reads"] == cut_read
+    total = np.zeros_like(whole)
+    for sb, base in shards:
+        ps = Params(k=k, min_bp=20000, max_bp=None, seed=77, read_index_base=base, nsites_override=p["nsites_ref"])
+        _, r2, c2, _ = gpu_counts(engine, sb, ps)
+        assert r2.levels == res.levels
+        total += c2
+    assert (total == whole).all()
+
+
+# --------------------------------------------------------------------------------- images (make_image stand-in)
+@pytest.mark.parametrize("k", [5, 6, 7, 8, 9])
+@pytest.mark.parametrize("mapping", ["varKode", "cgr"])
+def test_images_match_reference_golden(engine, golden_dir, k, mapping):
+    """pixels == the PNG the unmodified reference make_image wrote for the same counts (0 differing pixels)."""
+    z = np.load(os.path.join(golden_dir, f"make_image_k{k}_{mapping}.npz"))
+    table = get_kmer_mapping(k, mapping)
+    names = sorted({n.split("__")[0] for n in z.files})
+    canon = np.stack([z[n + "__counts"].astype(np.uint64) for n in names])
+    px = engine.render_counts(table, canon)
+    for i, n in enumerate(names):
+        assert (px[i] == z[n + "__pixels"]).all(), n
+
+
+def test_images_huge_counts(engine):
+    # counts beyond 2^32 (30 Gbp skims): exact integer path has no float to lose bits in
+    k = 6
+    table = get_kmer_mapping(k, "cgr")
+    rng = np.random.default_rng(2)
+    n = 4 ** k
+    rc = np.array([oimg.revcomp_index(i, k) for i in range(n)])
+    canon = (rng.integers(0, 2 ** 44, n).astype(np.uint64))[np.minimum(np.arange(n), rc)]
+    assert (engine.render_counts(table, canon)[0] == oimg.image_exact(canon, table.lut)).all()
+
+
+@pytest.mark.parametrize("k,mapping", [(7, "varKode"), (7, "cgr"), (5, "cgr"), (9, "varKode")])
+def test_fused_path_end_to_end(engine, k, mapping):
+    """vk_reads_to_images == oracle counts + oracle image, level by level, from host bytes."""
+    buf = synth.fixed(600_000, 150, seed=5).tobytes()
+    p = dsk.parse_fastq(buf)
+    table = get_kmer_mapping(k, mapping)
+    params = Params(k=k, min_bp=50_000, max_bp=500_000, seed=9)
+    res = engine.reads_to_images(buf, params, table, want_canon=True)
+    assert res.nsites == 600_000 and res.levels == [500_000, 200_000, 100_000, 50_000]
+    expect = oracle_levels(buf, k, 9, res.levels, p["nsites_ref"])
+    assert (res.canon == expect).all()
+    assert (res.pixels == oracle_images(expect, table.lut)).all()
+    assert engine.timings()["total"] > 0 and engine.launch_count() > 0
+
+
+def test_stage_functions_write_reference_named_pngs(engine, tmp_path):
+    """split_fastq / count_kmers / make_image mirror: file names, stats keys, PNG metadata, skip/raise behaviour."""
+    import gzip
+    from PIL import Image
+    from varkoder_b200 import stages
+    buf = synth.fixed(300_000, 150, seed=21).tobytes()
+    clean = tmp_path / "clean_reads"
+    clean.mkdir()
+    fq = clean / "sampleA.fq.gz"
+    with gzip.open(fq, "wb", compresslevel=1) as f:
+        f.write(buf)
+    table = get_kmer_mapping(7, "cgr")
+    st = stages.split_fastq(fq, "sampleA", tmp_path / "split_fastqs", min_bp=50_000, max_bp=200_000, seed="31415",
+                            engine=engine)
+    assert st["splitting_bp_per_file"] == "200000,100000,50000" and "splitting_time" in st
+    assert stages.split_fastq(fq, "sampleA", tmp_path / "split_fastqs", min_bp=50_000, max_bp=200_000, seed="31415",
+                              engine=engine) == {}
+    with pytest.raises(Exception, match="Input file has less than minimum data."):
+        stages.split_fastq(fq, "sampleA", tmp_path / "x", min_bp=300_000, max_bp=200_000_000, engine=engine)
+    for f in sorted((tmp_path / "split_fastqs").glob("sampleA@*")):
+        cs = stages.count_kmers(f, tmp_path / "7mer_counts", k=7, engine=engine)
+        assert "7mer_counting_time" in cs
+    outs = []
+    for f in sorted((tmp_path / "7mer_counts").glob("sampleA@*")):
+        ms = stages.make_image(f, tmp_path / "images", table, labels=["genus:X", "sp:y"], base_sd=0.02,
+                               mapping_code="cgr", engine=engine)
+        assert "k7_img_time" in ms
+        outs.append(f)
+    names = sorted(p.name for p in (tmp_path / "images").glob("*.png"))
+    assert names == ["sampleA@00000050K+cgr+k7.png", "sampleA@00000100K+cgr+k7.png", "sampleA@00000200K+cgr+k7.png"]
+    p = dsk.parse_fastq(buf)
+    expect = oracle_levels(buf, 7, 31415, [200_000, 100_000, 50_000], p["nsites_ref"])
+    for name, canon in zip(reversed(names), expect):
+        img = Image.open(tmp_path / "images" / name)
+        assert img.mode == "L" and list(img.info) == ["varkoderKeywords", "varkoderBaseFreqSd",
+                                                      "varkoderLowQualityFlag", "varkoderMapping"]
+        assert img.info["varkoderKeywords"] == "genus:X;sp:y" and img.info["varkoderLowQualityFlag"] == "True"
+        assert (np.array(img) == oimg.image_exact(canon, table.lut)).all()
+    # fused form writes the same files
+    fs = stages.reads_to_images(fq, "sampleA", tmp_path / "images2", table, k=7, mapping_code="cgr", min_bp=50_000,
+                                max_bp=200_000, seed="31415", labels=["genus:X", "sp:y"], base_sd=0.02, engine=engine)
+    assert set(fs) == {"splitting_time", "splitting_bp_per_file", "7mer_counting_time", "k7_img_time"}
+    for name in names:
+        assert (np.array(Image.open(tmp_path / "images2" / name)) == np.array(Image.open(tmp_path / "images" / name))).all()
+
+
+# ------------------------------------------------------------------------------------ synthetic generator, scale
+def test_device_generator_equals_host_generator(engine):
+    import torch
+    n_bases, L = 123_457, 150
+    host = synth.fixed(n_bases, L, seed=20260118)
+    dev = torch.empty(len(host) + 64, dtype=torch.uint8, device="cuda")
+    n = engine.synth_fastq(dev.data_ptr(), dev.numel(), n_bases, L, seed=20260118)
+    assert n == len(host) == synth.fixed_total_bytes(n_bases, L)
+    assert (dev[:n].cpu().numpy() == host).all()
+    p = dsk.parse_fastq(host)
+    assert p["nsites_ref"] == n_bases
+
+
+def test_full_size_properties_config2(engine):
+    """BASELINE config 2 shape (200 Mbp, k=7, cgr, 9 levels) on device-resident synthetic reads, checked through
+    size-independent properties: conservation, nesting, ladder, rank-transform invariants, linearity in shards."""
+    import torch
+    k, L, n_bases = 7, 150, 200_000_000
+    table = get_kmer_mapping(k, "cgr")
+    total = synth.fixed_total_bytes(n_bases, L)
+    dev = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+    assert engine.synth_fastq(dev.data_ptr(), dev.numel(), n_bases, L, seed=2026) == total
+    params = Params(k=k, min_bp=500_000, max_bp=200_000_000, seed=1)
+    res = engine.reads_to_images(dev.data_ptr(), params, table, on_device=True, n_bytes=total, want_canon=True)
+    assert res.nsites == n_bases and res.n_reads == (n_bases + L - 1) // L
+    assert res.levels == [200_000_000, 100_000_000, 50_000_000, 20_000_000, 10_000_000, 5_000_000, 2_000_000,
+                          1_000_000, 500_000]
+    canon = res.canon
+    assert (canon[:-1] >= canon[1:]).all()
+    rc = np.array([oimg.revcomp_index(i, k) for i in range(4 ** k)])
+    assert (canon[:, rc] == canon).all()                       # canon[K] == canon[rc K]
+    pal = rc == np.arange(4 ** k)
+    windows = (canon.sum(axis=1) + canon[:, pal].sum(axis=1)) // 2      # forward windows counted
+    # every read of length L without N gives L-k+1 windows; N and read ends only remove some
+    for lvl in range(len(res.levels)):
+        assert windows[lvl] <= res.level_bases[lvl] - (k - 1) * res.level_reads[lvl]
+        assert windows[lvl] >= 0.97 * (res.level_bases[lvl] - (k - 1) * res.level_reads[lvl])
+        assert abs(res.level_bases[lvl] - res.levels[lvl]) <= 0.05 * res.levels[lvl]
+    assert res.level_bases[0] == n_bases
+    # images: rank transform invariants + agreement with the oracle image of the GPU counts
+    assert (res.pixels.max(axis=(1, 2)) == 255).all()
+    for lvl in (0, 4, 8):
+        assert (res.pixels[lvl] == oimg.image_exact(canon[lvl], table.lut)).all()
+    # a 1 Mbp prefix of the same reads, counted by the CPU oracle, must match the GPU on that prefix
+    nb = synth.fixed_total_bytes(1_000_050, L)
+    head = dev[:nb].cpu().numpy().tobytes()
+    r2 = engine.reads_to_images(head, Params(k=k, min_bp=0, max_bp=None, is_query=True), table, want_canon=True)
+    assert (r2.canon[0] == dsk.canonical_counts(head, k, threads=0)).all()

@@ -1,0 +1,140 @@
+"""CPU suite, part 1: the oracle itself -- pinned against the reference's golden vectors.
+
+These tests never touch the product; they establish that ``oracle/`` restates the reference so that the
+GPU parity tests have something trustworthy to be compared with.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import dsk, image as oimg, ref_shim
+from tests.helpers import fastq, rand_reads
+
+K_ALL = [5, 6, 7]
+
+
+def test_oracle_c_matches_bruteforce():
+    rng = np.random.default_rng(7)
+    reads = rand_reads(rng, 60, 0, 90, p_n=0.03) + ["", "ACG", "N" * 20, "acgtacgtacgtNNacgtacgtacgt", "A" * 40]
+    buf = fastq(reads)
+    for k in (5, 7, 9):
+        c = dsk.canonical_counts(buf, k)
+        b = dsk.brute_canonical_counts(buf, k)
+        assert (c == b).all()
+        # conservation: every window of k valid bases inside a piece is counted once per strand
+        assert int(c.sum()) == int(b.sum())
+
+
+def test_oracle_breaklength_and_selection():
+    rng = np.random.default_rng(3)
+    reads = rand_reads(rng, 8, 900, 1700, p_n=0.002)
+    buf = fastq(reads)
+    sel = np.array([1, 0, 1, 1, 0, 0, 1, 1], dtype=np.uint8)
+    for k in (6, 7):
+        assert (dsk.canonical_counts(buf, k, select=sel) == dsk.brute_canonical_counts(buf, k, select=sel)).all()
+        # with breaklength off there are strictly more k-mers (those spanning a cut)
+        assert dsk.canonical_counts(buf, k, breaklen=0).sum() > dsk.canonical_counts(buf, k).sum()
+
+
+def test_oracle_framing_matches_python_line_loop():
+    # the reference counts bases with `for nlines, l in enumerate(f): if nlines % 4 == 1: len(l) - 1`
+    cases = [
+        fastq(["ACGT", "GG", ""]),
+        fastq(["ACGT", "GGA"], final_newline=False),
+        b"@h\nACGT",                      # unterminated sequence line: reference counts 3
+        b"@h\n",                          # header only
+        b"",
+        b"@h\nAC\n+\n@@\n@h2\nGT\n+\n++\n",   # qualities starting with '@' and '+'
+        fastq(["ACGT"]) + b"@trunc\nACG\n+",
+    ]
+    for buf in cases:
+        expect = 0
+        for i, l in enumerate(buf.splitlines(keepends=True)):
+            if i % 4 == 1:
+                expect += len(l) - 1
+        p = dsk.parse_fastq(buf)
+        assert p["nsites_ref"] == expect, buf
+        assert p["n_lines"] == len(buf.splitlines())
+
+
+def test_prio_hash_c_equals_python():
+    for seed, r in [(0, 0), (1, 2), (2**64 - 1, 2**40), (12345678901234567890, 77)]:
+        assert dsk.prio(seed, r) == dsk.prio_py(seed, r)
+
+
+def test_ladder_golden(golden_dir):
+    with open(os.path.join(golden_dir, "ladder.json")) as f:
+        cases = json.load(f)
+    assert len(cases) >= 15
+    for c in cases:
+        if "raises" in c:
+            with pytest.raises(Exception, match="less than minimum data"):
+                oimg.ladder(c["nsites"], c["min_bp"], c["max_bp"], c["is_query"])
+        else:
+            sites = oimg.ladder(c["nsites"], c["min_bp"], c["max_bp"], c["is_query"])
+            assert sites == c["sites"]
+            assert ["x@" + oimg.level_tag(b) + ".fq.gz" for b in sites] == c["names"]
+
+
+@pytest.mark.parametrize("k", [5, 6, 7, 8, 9])
+@pytest.mark.parametrize("mapping", ["varKode", "cgr"])
+def test_make_image_golden(golden_dir, k, mapping):
+    """pixels written by the UNMODIFIED reference make_image == exact-integer restatement."""
+    z = np.load(os.path.join(golden_dir, f"make_image_k{k}_{mapping}.npz"))
+    from varkoder_b200.mapping import get_kmer_mapping
+    lut = get_kmer_mapping(k, mapping).lut
+    if k <= 7:
+        assert (np.load(os.path.join(golden_dir, f"lut_k{k}_{mapping}.npy")) == lut).all() or mapping == "cgr"
+    names = sorted({n.split("__")[0] for n in z.files})
+    assert names
+    for name in names:
+        canon = z[name + "__counts"].astype(np.uint64)
+        px = z[name + "__pixels"]
+        assert (oimg.image_exact(canon, lut) == px).all(), name
+        if k <= 6:
+            assert (oimg.image_float(canon, lut) == px).all(), name
+
+
+def test_docs_png_properties(golden_dir):
+    """the reference's own shipped example images: histogram shape of the rank transform and
+    the varKode <-> cgr geometry (remap identity)."""
+    from PIL import Image
+    from varkoder_b200.mapping import get_kmer_mapping
+    d = os.path.join(golden_dir, "docs_png")
+    vk = get_kmer_mapping(7, "varKode").lut
+    cg = get_kmer_mapping(7, "cgr").lut
+    samples = sorted({f.split("+")[0] for f in os.listdir(d)})
+    assert len(samples) == 3
+    rc = np.array([oimg.revcomp_index(i, 7) for i in range(4 ** 7)])
+    canon_of = np.minimum(np.arange(4 ** 7), rc)
+    for s in samples:
+        a = np.array(Image.open(os.path.join(d, s + "+varKode+k7.png")))
+        b = np.array(Image.open(os.path.join(d, s + "+cgr+k7.png")))
+        assert a.shape == (91, 91) and b.shape == (128, 128)
+        h = np.bincount(a.ravel(), minlength=256)
+        assert h[0] == 0 and h[1] == 0 and h[2] >= 89           # 89 unused pixels share the lowest used level
+        assert 28 <= np.median(h[3:]) <= 36 and a.max() == 255  # 8281 / 256 = 32.3 pixels per grey level
+        # the shipped cgr image is the varKode image re-scattered by convert.remap (convert.py:34-77): pixels of
+        # the same canonical class carry the same grey level => pins both tables' geometry incl. the y flip
+        val = np.zeros(4 ** 7, dtype=np.int64)
+        used = vk >= 0
+        val[canon_of[vk[used]]] = a[used]
+        assert (val[canon_of[cg]] == b).all()
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference not mounted (GPU box)")
+def test_restatement_against_live_reference(tmp_path):
+    """re-run the unmodified reference on fresh random counts (not the committed goldens)."""
+    from PIL import Image
+    _, utils, _ = ref_shim.load()
+    rng = np.random.default_rng(99)
+    for k, mapping in [(5, "varKode"), (6, "cgr")]:
+        table = utils.get_kmer_mapping(k, mapping)
+        lut = oimg.lut_from_table(table)
+        n = 4 ** k
+        rcs = np.array([oimg.revcomp_index(i, k) for i in range(n)])
+        canon = rng.integers(0, 50, n).astype(np.uint64)[np.minimum(np.arange(n), rcs)]
+        png, _ = ref_shim.reference_make_image(dsk.dsk2ascii_text(canon, k), tmp_path, table, k=k, mapping_code=mapping)
+        assert (np.array(Image.open(png)) == oimg.image_exact(canon, lut)).all()

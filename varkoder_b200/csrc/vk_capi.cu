@@ -1,0 +1,651 @@
+// vk_capi.cu -- C ABI (include/varkoder_b200.h) over the sm_100a kernels of the varKoder image hot path.
+// Host side of one context: device buffers, one stream, kernel sequencing, timing events.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "vk_bucket.cuh"
+#include "vk_common.cuh"
+#include "vk_count.cuh"
+#include "vk_image.cuh"
+#include "vk_parse.cuh"
+#include "vk_synth.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+struct CudaError {
+    cudaError_t e;
+    const char* what;
+    int line;
+};
+#define CU(x)                                                 \
+    do {                                                      \
+        cudaError_t e_ = (x);                                 \
+        if (e_ != cudaSuccess) throw CudaError{e_, #x, __LINE__}; \
+    } while (0)
+
+struct ApiError {
+    int code;
+    std::string msg;
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;      // elements
+    void ensure(size_t n)
+    {
+        if (n <= cap) return;
+        if (p) CU(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 256;
+        CU(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Mapping {
+    int k = 0, side = 0;
+    DevBuf<int32_t> lut;
+};
+
+enum { EV_START = 0, EV_UPLOAD, EV_PARSE, EV_BUCKET, EV_COUNT, EV_FOLD, EV_RENDER, EV_N };
+
+}  // namespace
+
+struct vk_ctx {
+    int device = 0;
+    int n_sms = vk::kNumSMs;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_N] = {};
+    bool ev_valid[EV_N] = {};
+    uint64_t launches = 0;
+
+    vk::Plan* plan_d = nullptr;
+    vk::Plan* plan_h = nullptr;     // pinned
+
+    DevBuf<uint8_t> text_own;
+    const uint8_t* text = nullptr;  // device
+    uint64_t n_bytes = 0;
+    bool have_text = false, parsed = false, counted = false;
+    int counted_k = 0;
+
+    DevBuf<uint64_t> tile_status, starts, ends, sorted;
+    DevBuf<uint32_t> slabs;
+    DevBuf<unsigned long long> seg_hist, canon, vals, bins;
+    DevBuf<uint8_t> pixels;
+    uint8_t* pix_h = nullptr;       // pinned staging for pixel read-back
+    size_t pix_h_cap = 0;
+    Mapping maps[4];
+
+    void mark(int e)
+    {
+        CU(cudaEventRecord(ev[e], stream));
+        ev_valid[e] = true;
+    }
+};
+
+namespace {
+
+void set_device(vk_ctx* c) { CU(cudaSetDevice(c->device)); }
+
+// ---- K1: framing -------------------------------------------------------------------------------------
+void enqueue_parse(vk_ctx* c, const vk_params* params, bool rescan = true)
+{
+    using namespace vk;
+    const uint64_t n = c->n_bytes;
+    const uint32_t n_tiles = (uint32_t)((n + kParseTileBytes - 1) / kParseTileBytes);
+    c->tile_status.ensure(n_tiles + 1);
+    const size_t cap = c->starts.cap;
+    if (rescan) CU(cudaMemsetAsync(c->plan_d, 0, offsetof(Plan, n_lines), c->stream));      // parse fields: counters, sums, ticket
+    if (n_tiles && rescan) {
+        CU(cudaMemsetAsync(c->tile_status.p, 0, sizeof(uint64_t) * n_tiles, c->stream));
+        int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)c->n_sms * 8);
+        parse_kernel<<<grid, kParseThreads, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->text), n, 0, n_tiles,
+                                                           c->tile_status.p, c->starts.p, c->ends.p, cap, c->plan_d);
+        CU(cudaGetLastError());
+        ++c->launches;
+    }
+    PlanArgs a;
+    memset(&a, 0, sizeof(a));
+    if (params) a.p = *params;
+    a.n_bytes = n;
+    a.cap_reads = cap;
+    plan_kernel<<<1, 32, 0, c->stream>>>(c->text, c->starts.p, c->ends.p, a, c->plan_d);
+    CU(cudaGetLastError());
+    ++c->launches;
+}
+
+void ensure_tables_for(vk_ctx* c, uint64_t n_reads_hint)
+{
+    c->starts.ensure(n_reads_hint);
+    c->ends.ensure(n_reads_hint);
+}
+
+// ---- K1b + K2 + K3 -----------------------------------------------------------------------------------
+template <int K>
+void launch_count(vk_ctx* c, unsigned long long* seg_hist, int breaklen)
+{
+    using namespace vk;
+    constexpr uint32_t NK = 1u << (2 * K);
+    if (K <= 7) {
+        const size_t smem = (size_t)(NK + 32) * sizeof(uint32_t);
+        CU(cudaFuncSetAttribute(count_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        count_kernel<K, true><<<c->n_sms, kCountThreads, smem, c->stream>>>(
+            reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d, c->slabs.p, seg_hist, breaklen);
+        CU(cudaGetLastError());
+        ++c->launches;
+        const uint64_t total = (uint64_t)kMaxLevels * NK;
+        reduce_slabs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->slabs.p, c->plan_d, NK, seg_hist);
+        CU(cudaGetLastError());
+        ++c->launches;
+    } else {
+        const uint64_t total = (uint64_t)kMaxLevels * NK;
+        zero_u64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(seg_hist, total);
+        CU(cudaGetLastError());
+        ++c->launches;
+        count_kernel<K, false><<<c->n_sms, kCountThreads, 0, c->stream>>>(
+            reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d, c->slabs.p, seg_hist, breaklen);
+        CU(cudaGetLastError());
+        ++c->launches;
+    }
+}
+
+void enqueue_count(vk_ctx* c, const vk_params* p, unsigned long long* seg_hist, uint64_t n_reads_bound)
+{
+    using namespace vk;
+    const int k = p->k;
+    const uint32_t nk = 1u << (2 * k);
+    c->sorted.ensure(n_reads_bound + (uint64_t)kMaxLevels * kUnitReads);
+    if (k <= 7) c->slabs.ensure((size_t)c->n_sms * nk);
+    const int bgrid = (int)std::min<uint64_t>((n_reads_bound + kBucketThreads - 1) / kBucketThreads + 1, (uint64_t)c->n_sms * 8);
+    bucket_count_kernel<<<bgrid, kBucketThreads, 0, c->stream>>>(c->starts.p, c->ends.p, k, p->seed, p->read_index_base, c->plan_d);
+    CU(cudaGetLastError());
+    bucket_layout_kernel<<<1, 32, 0, c->stream>>>(c->plan_d, (uint32_t)c->n_sms);
+    CU(cudaGetLastError());
+    bucket_scatter_kernel<<<bgrid, kBucketThreads, 0, c->stream>>>(c->starts.p, c->ends.p, k, p->seed, p->read_index_base, 0,
+                                                                  c->sorted.p, c->plan_d);
+    CU(cudaGetLastError());
+    c->launches += 3;
+    c->mark(EV_BUCKET);
+    switch (k) {
+    case 5: launch_count<5>(c, seg_hist, p->breaklength); break;
+    case 6: launch_count<6>(c, seg_hist, p->breaklength); break;
+    case 7: launch_count<7>(c, seg_hist, p->breaklength); break;
+    case 8: launch_count<8>(c, seg_hist, p->breaklength); break;
+    case 9: launch_count<9>(c, seg_hist, p->breaklength); break;
+    default: throw ApiError{VK_EINVAL, "k must be 5..9"};
+    }
+    c->mark(EV_COUNT);
+}
+
+// ---- K4 ----------------------------------------------------------------------------------------------
+uint32_t next_pow2(uint32_t v)
+{
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// levels: number of levels to render (grid size); canon must hold levels * 4^k
+void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsigned long long* seg_hist)
+{
+    using namespace vk;
+    const uint32_t nk = 1u << (2 * k);
+    const uint32_t n_pix = (uint32_t)m.side * (uint32_t)m.side;
+    const uint32_t n_pad = next_pow2(n_pix);
+    c->canon.ensure((size_t)levels * nk);
+    c->pixels.ensure((size_t)levels * n_pix);
+    if (seg_hist) {
+        fold_kernel<<<(nk + 255) / 256, 256, 0, c->stream>>>(seg_hist, k, levels, c->canon.p);
+        CU(cudaGetLastError());
+        ++c->launches;
+    }
+    c->mark(EV_FOLD);
+    const size_t smem = ((size_t)n_pad + 256) * sizeof(unsigned long long);
+    if (smem <= 200 * 1024) {
+        CU(cudaFuncSetAttribute(image_kernel_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        image_kernel_smem<<<levels, kImageThreads, smem, c->stream>>>(c->canon.p, m.lut.p, nk, n_pix, n_pad, c->pixels.p);
+        CU(cudaGetLastError());
+        ++c->launches;
+    } else {
+        c->vals.ensure((size_t)levels * n_pad);
+        c->bins.ensure((size_t)levels * 256);
+        dim3 g1((n_pad + 255) / 256, levels);
+        image_gather_kernel<<<g1, 256, 0, c->stream>>>(c->canon.p, m.lut.p, nk, n_pix, n_pad, c->vals.p);
+        CU(cudaGetLastError());
+        ++c->launches;
+        dim3 gt(n_pad / kSortTile, levels);
+        bitonic_tile_kernel<<<gt, 1024, 0, c->stream>>>(c->vals.p, n_pad, 2, kSortTile, kSortTile / 2);
+        CU(cudaGetLastError());
+        ++c->launches;
+        for (uint32_t size = 2 * kSortTile; size <= n_pad; size <<= 1) {
+            for (uint32_t stride = size >> 1; stride >= kSortTile; stride >>= 1) {
+                dim3 gs((n_pad / 2 + 255) / 256, levels);
+                bitonic_global_step<<<gs, 256, 0, c->stream>>>(c->vals.p, n_pad, size, stride);
+                CU(cudaGetLastError());
+                ++c->launches;
+            }
+            bitonic_tile_kernel<<<gt, 1024, 0, c->stream>>>(c->vals.p, n_pad, size, size, kSortTile / 2);
+            CU(cudaGetLastError());
+            ++c->launches;
+        }
+        image_bins_kernel<<<levels, 256, 0, c->stream>>>(c->vals.p, n_pix, n_pad, c->bins.p);
+        CU(cudaGetLastError());
+        dim3 gd((n_pix + 255) / 256, levels);
+        image_digitize_kernel<<<gd, 256, 0, c->stream>>>(c->canon.p, m.lut.p, nk, n_pix, c->bins.p, c->pixels.p);
+        CU(cudaGetLastError());
+        c->launches += 2;
+    }
+    c->mark(EV_RENDER);
+}
+
+void fill_stats(const vk::Plan& p, vk_stats* s)
+{
+    s->n_bytes = p.n_bytes;
+    s->n_lines = p.n_lines;
+    s->n_reads = p.n_reads;
+    s->nsites = p.nsites_ref;
+    s->nsites_true = p.nsites_true;
+}
+
+void fill_result(const vk::Plan& p, vk_result* r)
+{
+    memset(r, 0, sizeof(*r));
+    fill_stats(p, &r->stats);
+    r->status = p.status;
+    r->n_levels = p.n_levels;
+    uint64_t reads = 0, bases = 0;
+    for (int l = p.n_levels - 1; l >= 0; --l) {
+        reads += p.seg_reads[l];
+        bases += p.seg_bases[l];
+        r->level_bp[l] = p.level_bp[l];
+        r->level_reads[l] = reads;
+        r->level_bases[l] = bases;
+    }
+}
+
+void fetch_plan(vk_ctx* c)
+{
+    CU(cudaMemcpyAsync(c->plan_h, c->plan_d, sizeof(vk::Plan), cudaMemcpyDeviceToHost, c->stream));
+}
+
+void ensure_pix_h(vk_ctx* c, size_t n)
+{
+    if (n <= c->pix_h_cap) return;
+    if (c->pix_h) CU(cudaFreeHost(c->pix_h));
+    c->pix_h = nullptr;
+    CU(cudaMallocHost(&c->pix_h, n));
+    c->pix_h_cap = n;
+}
+
+const Mapping& get_mapping(vk_ctx* c, int slot, int k)
+{
+    if (slot < 0 || slot >= 4) throw ApiError{VK_EINVAL, "mapping slot must be 0..3"};
+    const Mapping& m = c->maps[slot];
+    if (m.k != k || m.side <= 0) throw ApiError{VK_ESTATE, "no pixel table of this k in the mapping slot (vk_set_mapping)"};
+    return m;
+}
+
+void check_params(const vk_params* p)
+{
+    if (!p) throw ApiError{VK_EINVAL, "params is NULL"};
+    if (p->k < VK_MIN_K || p->k > VK_MAX_K) throw ApiError{VK_EINVAL, "k must be 5..9"};
+    if (p->breaklength != 0 && p->breaklength < 32) throw ApiError{VK_EINVAL, "breaklength must be 0 or >= 32"};
+}
+
+uint64_t reads_bound(uint64_t n_bytes) { return n_bytes / 24 + 1024; }
+
+template <typename F>
+int guarded(F&& f)
+{
+    try {
+        f();
+        return VK_OK;
+    } catch (const CudaError& e) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "CUDA error %d (%s) in %s at vk_capi.cu:%d", (int)e.e, cudaGetErrorString(e.e), e.what, e.line);
+        g_err = buf;
+        cudaGetLastError();
+        return e.e == cudaErrorMemoryAllocation ? VK_ENOMEM : VK_ECUDA;
+    } catch (const ApiError& e) {
+        g_err = e.msg;
+        return e.code;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return VK_EINVAL;
+    }
+}
+
+// run parse (+ optional later stages via `rest`) and redo everything once if the read table was too small
+template <typename F>
+void with_table_retry(vk_ctx* c, F&& body)
+{
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        body();
+        CU(cudaStreamSynchronize(c->stream));
+        if (!c->plan_h->table_overflow) return;
+        if (attempt == 1) throw ApiError{VK_ERANGE, "read table overflow after resize"};
+        ensure_tables_for(c, c->plan_h->n_reads + 16);          // exact size is known now
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int vk_abi_version(void) { return VK_ABI_VERSION; }
+const char* vk_last_error(void) { return g_err.c_str(); }
+
+int vk_ctx_create(int device, vk_ctx** out)
+{
+    return guarded([&] {
+        if (!out) throw ApiError{VK_EINVAL, "out is NULL"};
+        int n = 0;
+        CU(cudaGetDeviceCount(&n));
+        if (device < 0 || device >= n) throw ApiError{VK_EINVAL, "no such CUDA device"};
+        CU(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) throw ApiError{VK_ECUDA, "this library is built for sm_100a (B200) only"};
+        vk_ctx* c = new vk_ctx();
+        c->device = device;
+        c->n_sms = prop.multiProcessorCount;
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (int i = 0; i < EV_N; ++i) CU(cudaEventCreate(&c->ev[i]));
+        CU(cudaMalloc(&c->plan_d, sizeof(vk::Plan)));
+        CU(cudaMemset(c->plan_d, 0, sizeof(vk::Plan)));
+        CU(cudaMallocHost(&c->plan_h, sizeof(vk::Plan)));
+        memset(c->plan_h, 0, sizeof(vk::Plan));
+        *out = c;
+    });
+}
+
+int vk_ctx_destroy(vk_ctx* c)
+{
+    if (!c) return VK_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->text_own.release();
+    c->tile_status.release();
+    c->starts.release();
+    c->ends.release();
+    c->sorted.release();
+    c->slabs.release();
+    c->seg_hist.release();
+    c->canon.release();
+    c->vals.release();
+    c->bins.release();
+    c->pixels.release();
+    for (auto& m : c->maps) m.lut.release();
+    if (c->pix_h) cudaFreeHost(c->pix_h);
+    if (c->plan_h) cudaFreeHost(c->plan_h);
+    if (c->plan_d) cudaFree(c->plan_d);
+    for (int i = 0; i < EV_N; ++i)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return VK_OK;
+}
+
+int vk_set_mapping(vk_ctx* c, int slot, int k, int side, const int32_t* lut_host)
+{
+    return guarded([&] {
+        if (!c || !lut_host) throw ApiError{VK_EINVAL, "NULL argument"};
+        if (slot < 0 || slot >= 4) throw ApiError{VK_EINVAL, "mapping slot must be 0..3"};
+        if (k < VK_MIN_K || k > VK_MAX_K || side <= 0 || side > 1024) throw ApiError{VK_EINVAL, "bad k or side"};
+        const int32_t nk = 1 << (2 * k);
+        const size_t n = (size_t)side * side;
+        for (size_t i = 0; i < n; ++i)
+            if (lut_host[i] < -1 || lut_host[i] >= nk) throw ApiError{VK_EINVAL, "pixel table entry outside [-1, 4^k)"};
+        set_device(c);
+        Mapping& m = c->maps[slot];
+        m.lut.ensure(n);
+        CU(cudaMemcpyAsync(m.lut.p, lut_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        m.k = k;
+        m.side = side;
+    });
+}
+
+int vk_upload(vk_ctx* c, const void* host_bytes, uint64_t n_bytes)
+{
+    return guarded([&] {
+        if (!c || (!host_bytes && n_bytes)) throw ApiError{VK_EINVAL, "NULL argument"};
+        if (n_bytes >> 40) throw ApiError{VK_ERANGE, "buffers of 2^40 bytes or more are not supported"};
+        set_device(c);
+        c->mark(EV_START);
+        c->text_own.ensure(n_bytes + 64);
+        if (n_bytes) CU(cudaMemcpyAsync(c->text_own.p, host_bytes, n_bytes, cudaMemcpyHostToDevice, c->stream));
+        c->mark(EV_UPLOAD);
+        c->text = c->text_own.p;
+        c->n_bytes = n_bytes;
+        c->have_text = true;
+        c->parsed = c->counted = false;
+    });
+}
+
+int vk_attach(vk_ctx* c, const void* dev_bytes, uint64_t n_bytes)
+{
+    return guarded([&] {
+        if (!c || (!dev_bytes && n_bytes)) throw ApiError{VK_EINVAL, "NULL argument"};
+        if (n_bytes >> 40) throw ApiError{VK_ERANGE, "buffers of 2^40 bytes or more are not supported"};
+        if ((uintptr_t)dev_bytes & 15) throw ApiError{VK_EINVAL, "device text must be 16-byte aligned"};
+        c->text = static_cast<const uint8_t*>(dev_bytes);
+        c->n_bytes = n_bytes;
+        c->have_text = true;
+        c->parsed = c->counted = false;
+        c->ev_valid[EV_UPLOAD] = false;
+    });
+}
+
+int vk_parse(vk_ctx* c, vk_stats* out)
+{
+    return guarded([&] {
+        if (!c || !out) throw ApiError{VK_EINVAL, "NULL argument"};
+        if (!c->have_text) throw ApiError{VK_ESTATE, "vk_parse before vk_upload / vk_attach"};
+        set_device(c);
+        ensure_tables_for(c, reads_bound(c->n_bytes));
+        with_table_retry(c, [&] {
+            if (!c->ev_valid[EV_UPLOAD]) { c->mark(EV_START); c->mark(EV_UPLOAD); }
+            enqueue_parse(c, nullptr);
+            c->mark(EV_PARSE);
+            fetch_plan(c);
+        });
+        c->parsed = true;
+        fill_stats(*c->plan_h, out);
+    });
+}
+
+int vk_count(vk_ctx* c, const vk_params* p, uint64_t* seg_hist_dev, vk_result* out)
+{
+    return guarded([&] {
+        if (!c || !out) throw ApiError{VK_EINVAL, "NULL argument"};
+        check_params(p);
+        if (!c->have_text) throw ApiError{VK_ESTATE, "vk_count before vk_upload / vk_attach"};
+        set_device(c);
+        const uint32_t nk = 1u << (2 * p->k);
+        unsigned long long* sh = reinterpret_cast<unsigned long long*>(seg_hist_dev);
+        if (!sh) {
+            c->seg_hist.ensure((size_t)vk::kMaxLevels * nk);
+            sh = c->seg_hist.p;
+        }
+        ensure_tables_for(c, reads_bound(c->n_bytes));
+        with_table_retry(c, [&] {
+            if (!c->ev_valid[EV_UPLOAD]) { c->mark(EV_START); c->mark(EV_UPLOAD); }
+            enqueue_parse(c, p, !c->parsed);      // framing found by vk_parse is kept; the ladder needs the parameters
+            c->mark(EV_PARSE);
+            enqueue_count(c, p, sh, std::max<uint64_t>(c->starts.cap, 1));
+            fetch_plan(c);
+            c->parsed = false;                     // a retry (table overflow) must rescan
+        });
+        if (c->plan_h->long_reads) throw ApiError{VK_ERANGE, "a read is longer than 2^24-1 bases"};
+        c->parsed = true;
+        c->counted = true;
+        c->counted_k = p->k;
+        fill_result(*c->plan_h, out);
+    });
+}
+
+int vk_render(vk_ctx* c, int slot, int k, int n_levels, const uint64_t* seg_hist_dev, uint64_t* canon_host, uint8_t* pixels_host)
+{
+    return guarded([&] {
+        if (!c) throw ApiError{VK_EINVAL, "NULL argument"};
+        if (n_levels < 0 || n_levels > VK_MAX_LEVELS) throw ApiError{VK_EINVAL, "n_levels out of range"};
+        if (k < VK_MIN_K || k > VK_MAX_K) throw ApiError{VK_EINVAL, "k must be 5..9"};
+        set_device(c);
+        const unsigned long long* sh = reinterpret_cast<const unsigned long long*>(seg_hist_dev);
+        if (!sh) {
+            if (!c->counted || c->counted_k != k) throw ApiError{VK_ESTATE, "vk_render without histograms: call vk_count first"};
+            sh = c->seg_hist.p;
+        }
+        if (n_levels == 0) return;
+        const uint32_t nk = 1u << (2 * k);
+        const Mapping* m = pixels_host ? &get_mapping(c, slot, k) : nullptr;
+        if (m) {
+            enqueue_render(c, *m, k, n_levels, sh);
+        } else {
+            c->canon.ensure((size_t)n_levels * nk);
+            vk::fold_kernel<<<(nk + 255) / 256, 256, 0, c->stream>>>(sh, k, n_levels, c->canon.p);
+            CU(cudaGetLastError());
+            ++c->launches;
+        }
+        if (canon_host)
+            CU(cudaMemcpyAsync(canon_host, c->canon.p, (size_t)n_levels * nk * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        if (pixels_host)
+            CU(cudaMemcpyAsync(pixels_host, c->pixels.p, (size_t)n_levels * m->side * m->side, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int vk_render_counts(vk_ctx* c, int slot, int k, int n, const uint64_t* canon_host, uint8_t* pixels_host)
+{
+    return guarded([&] {
+        if (!c || !canon_host || !pixels_host) throw ApiError{VK_EINVAL, "NULL argument"};
+        if (n < 1 || n > VK_MAX_LEVELS) throw ApiError{VK_EINVAL, "n out of range"};
+        if (k < VK_MIN_K || k > VK_MAX_K) throw ApiError{VK_EINVAL, "k must be 5..9"};
+        set_device(c);
+        const Mapping& m = get_mapping(c, slot, k);
+        const uint32_t nk = 1u << (2 * k);
+        c->canon.ensure((size_t)n * nk);
+        CU(cudaMemcpyAsync(c->canon.p, canon_host, (size_t)n * nk * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        enqueue_render(c, m, k, n, nullptr);      // canon is already in place: no fold
+        CU(cudaMemcpyAsync(pixels_host, c->pixels.p, (size_t)n * m.side * m.side, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int vk_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, int on_device, const vk_params* p, int slot,
+                       int max_levels_out, vk_result* result, uint64_t* canon_host, uint8_t* pixels_host)
+{
+    int rc = on_device ? vk_attach(c, text, n_bytes) : VK_OK;
+    if (rc != VK_OK) return rc;
+    return guarded([&] {
+        if (!c || !result) throw ApiError{VK_EINVAL, "NULL argument"};
+        check_params(p);
+        if (max_levels_out < 1 || max_levels_out > VK_MAX_LEVELS) throw ApiError{VK_EINVAL, "max_levels_out out of range"};
+        set_device(c);
+        const int k = p->k;
+        const uint32_t nk = 1u << (2 * k);
+        const Mapping& m = get_mapping(c, slot, k);
+        const size_t n_pix = (size_t)m.side * m.side;
+        c->seg_hist.ensure((size_t)vk::kMaxLevels * nk);
+        ensure_tables_for(c, reads_bound(n_bytes));
+        ensure_pix_h(c, (size_t)max_levels_out * n_pix);
+        if (!on_device) {
+            if (n_bytes >> 40) throw ApiError{VK_ERANGE, "buffers of 2^40 bytes or more are not supported"};
+            c->text_own.ensure(n_bytes + 64);
+        }
+        with_table_retry(c, [&] {
+            c->mark(EV_START);
+            if (!on_device) {
+                if (n_bytes) CU(cudaMemcpyAsync(c->text_own.p, text, n_bytes, cudaMemcpyHostToDevice, c->stream));
+                c->text = c->text_own.p;
+                c->n_bytes = n_bytes;
+                c->have_text = true;
+            }
+            c->mark(EV_UPLOAD);
+            enqueue_parse(c, p);
+            c->mark(EV_PARSE);
+            enqueue_count(c, p, c->seg_hist.p, std::max<uint64_t>(c->starts.cap, 1));
+            // the number of levels is only known on the device: render max_levels_out, rows beyond the ladder
+            // come from all-zero segments and are ignored by the caller
+            enqueue_render(c, m, k, max_levels_out, c->seg_hist.p);
+            CU(cudaMemcpyAsync(c->pix_h, c->pixels.p, (size_t)max_levels_out * n_pix, cudaMemcpyDeviceToHost, c->stream));
+            fetch_plan(c);
+        });
+        if (c->plan_h->long_reads) throw ApiError{VK_ERANGE, "a read is longer than 2^24-1 bases"};
+        c->parsed = c->counted = true;
+        c->counted_k = k;
+        fill_result(*c->plan_h, result);
+        int nl = result->n_levels;
+        if (nl > max_levels_out) {
+            // rare: more levels than the caller guessed; render the rest with a second pass
+            enqueue_render(c, m, k, nl, c->seg_hist.p);
+            ensure_pix_h(c, (size_t)nl * n_pix);
+            CU(cudaMemcpyAsync(c->pix_h, c->pixels.p, (size_t)nl * n_pix, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+        if (pixels_host && nl > 0) memcpy(pixels_host, c->pix_h, (size_t)nl * n_pix);
+        if (canon_host && nl > 0) {
+            CU(cudaMemcpyAsync(canon_host, c->canon.p, (size_t)nl * nk * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+    });
+}
+
+int vk_last_timings(vk_ctx* c, float* ms7)
+{
+    return guarded([&] {
+        if (!c || !ms7) throw ApiError{VK_EINVAL, "NULL argument"};
+        for (int i = 0; i < 7; ++i) ms7[i] = 0.f;
+        for (int i = 1; i < EV_N; ++i) {
+            if (c->ev_valid[i] && c->ev_valid[i - 1]) {
+                float t = 0.f;
+                if (cudaEventElapsedTime(&t, c->ev[i - 1], c->ev[i]) == cudaSuccess) ms7[i - 1] = t;
+            }
+        }
+        if (c->ev_valid[EV_START] && c->ev_valid[EV_RENDER]) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, c->ev[EV_START], c->ev[EV_RENDER]) == cudaSuccess) ms7[6] = t;
+        }
+        cudaGetLastError();
+    });
+}
+
+uint64_t vk_launch_count(vk_ctx* c) { return c ? c->launches : 0; }
+
+int vk_synth_fastq(vk_ctx* c, void* dev_bytes, uint64_t capacity, uint64_t n_bases, int read_len, uint64_t seed,
+                   uint64_t first_read, uint64_t* n_out)
+{
+    return guarded([&] {
+        if (!c || !dev_bytes || !n_out) throw ApiError{VK_EINVAL, "NULL argument"};
+        if (read_len < 1 || read_len > 100000 || n_bases == 0) throw ApiError{VK_EINVAL, "bad read_len / n_bases"};
+        set_device(c);
+        const uint64_t L = (uint64_t)read_len;
+        const uint64_t n_reads = (n_bases + L - 1) / L;
+        const uint64_t last_len = n_bases - (n_reads - 1) * L;
+        const uint64_t total = (n_reads - 1) * (2 * L + 17) + 2 * last_len + 17;
+        if (total > capacity) throw ApiError{VK_EINVAL, "synthetic FASTQ does not fit the buffer"};
+        const int grid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->n_sms * 16);
+        vk::synth_fixed_kernel<<<grid, 256, 0, c->stream>>>(static_cast<uint8_t*>(dev_bytes), total, n_reads, (uint32_t)L,
+                                                            (uint32_t)last_len, seed, first_read);
+        CU(cudaGetLastError());
+        ++c->launches;
+        CU(cudaStreamSynchronize(c->stream));
+        *n_out = total;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// vk_common.cuh -- shared definitions of the sm_100a kernels of the varKoder image hot path.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/varkoder_b200.h"
+
+namespace vk {
+
+constexpr int kMaxLevels = VK_MAX_LEVELS;
+constexpr int kNumSMs = 148;              // B200
+constexpr uint32_t kUnitReads = 256;      // reads a warp takes from its segment at a time (count kernel)
+constexpr int kEntryLenBits = 24;         // sorted read entry = start << 24 | len
+constexpr uint64_t kEntryLenMask = (1ull << kEntryLenBits) - 1;
+constexpr uint64_t kThrAll = ~0ull;
+
+// Device-resident plan: written by the parse / plan / bucket kernels, read by the count / render kernels,
+// copied to the host once at the end.  One per context.
+struct Plan {
+    // ---- parse (K1)
+    uint64_t n_bytes;
+    uint64_t n_newlines;      // running total over all chunks parsed so far (look-back carry)
+    uint64_t sum_starts;      // sum over header-line newlines of (pos + 1), mod 2^64
+    uint64_t sum_ends;        // sum over sequence-line newlines of pos, mod 2^64
+    uint32_t parse_ticket;    // dynamic tile counter of the current parse launch
+    uint32_t table_overflow;  // 1 if a read index exceeded the table capacity
+    // ---- plan (K1L)
+    uint64_t n_lines, n_reads, nsites_ref, nsites_true, nsites_ladder;
+    int32_t status;
+    int32_t n_levels;
+    uint64_t level_bp[kMaxLevels];
+    uint64_t level_thr[kMaxLevels];   // read is in level l iff prio < thr[l]; kThrAll + level_all => every read
+    uint32_t level_all[kMaxLevels];
+    // ---- bucket (K1b): segment s = reads in levels 0..s and not in s+1
+    unsigned long long seg_reads[kMaxLevels];
+    unsigned long long seg_bases[kMaxLevels];
+    unsigned long long seg_cursor[kMaxLevels];   // scatter cursors
+    unsigned long long seg_next[kMaxLevels];     // dynamic unit counters of the count kernel
+    uint64_t seg_begin[kMaxLevels + 1];          // offsets into the sorted entry array
+    uint32_t seg_cta_begin[kMaxLevels + 1];      // CTA ranges of the count kernel
+    uint32_t long_reads;                         // reads longer than 2^24-1 bases (unsupported)
+    uint32_t pad_;
+};
+
+// splitmix64 finaliser over (seed, global read index): the seeded per-read priority (DESIGN.md "Sub-sampling").
+__host__ __device__ __forceinline__ uint64_t prio64(uint64_t seed, uint64_t read_index)
+{
+    uint64_t z = seed + (read_index + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// number of (nested) levels a read with priority h belongs to; 0 = in no level
+__device__ __forceinline__ int levels_of(const Plan* __restrict__ p, int n_levels, uint64_t h)
+{
+    int c = 0;
+    while (c < n_levels && (p->level_all[c] || h < p->level_thr[c])) ++c;
+    return c;
+}
+
+// ---- index conventions ------------------------------------------------------------------------------
+// internal index: base j of the k-mer at bits [2j, 2j+2), 2-bit code (ascii >> 1) & 3  (A0 C1 T2 G3)
+// lex index:      base j of the k-mer at bits [2(k-1-j), ...), code A0 C1 G2 T3
+__host__ __device__ __forceinline__ uint32_t lex_to_internal(uint32_t x, int k)
+{
+    uint32_t r = 0;
+    for (int j = 0; j < k; ++j) {
+        uint32_t d = (x >> (2 * (k - 1 - j))) & 3u;
+        r |= (d ^ (d >> 1)) << (2 * j);      // 0,1,2,3 -> 0,1,3,2
+    }
+    return r;
+}
+__host__ __device__ __forceinline__ uint32_t internal_revcomp(uint32_t i, int k)
+{
+    uint32_t r = 0;
+    for (int j = 0; j < k; ++j) {
+        uint32_t c = (i >> (2 * (k - 1 - j))) & 3u;
+        r |= (c ^ 2u) << (2 * j);            // complement under the dsk code is XOR 2
+    }
+    return r;
+}
+
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+}  // namespace vk

@@ -1,0 +1,234 @@
+"""Host-side mirror of the reference's stage functions for the image hot path.
+
+Same names, argument meaning, file-name contract, stats keys and error behaviour as
+``split_fastq`` / ``count_kmers`` / ``make_image`` in the reference (varKoder/commands/image.py:629-936), so
+``run_clean2img`` (image.py:938-1128) can call these instead; plus :func:`reads_to_images`, the fused form of
+steps C-E that does one upload, one pass over the reads and one synchronisation per sample.
+
+What differs, by design (DESIGN.md "Boundary"):
+  * no sub-sampled FASTQ files and no dsk HDF5 are produced.  ``split_fastq`` writes one small JSON
+    *level descriptor* per ladder level under the same name stem (``<sample>@NNNNNNNNK.fq.vk``) and
+    ``count_kmers`` writes the canonical counts of that level as ``<sample>@NNNNNNNNK+k7.fq.npy``; the
+    globs of run_clean2img (image.py:1060, 1092) find them exactly as they find the reference's files.
+  * all levels of a sample are counted in ONE pass on the GPU the first time ``count_kmers`` sees the
+    sample; the other levels are served from that result.
+  * the sub-sample of each level is the seeded nested rule of this project, not BBTools' RNG.
+All compute is in the CUDA library; nothing here falls back to a CPU implementation of it.
+"""
+import gzip
+import hashlib
+import json
+import os
+import sys
+import time
+from collections import OrderedDict
+from pathlib import Path
+
+import numpy as np
+
+from .engine import Engine, Params
+from .ladder import (BP_KMER_SEP, LABELS_SEP, QUAL_THRESH, SAMPLE_BP_SEP, LessThanMinimumData, image_name,
+                     ladder, level_tag)
+from .mapping import as_pixel_table
+
+_ENGINES = {}
+
+
+def eprint(*args, **kwargs):
+    print(*args, file=sys.stderr, **kwargs)
+
+
+def default_engine(device=None):
+    """one Engine per (process, device): CUDA contexts do not survive fork (image.py:1281 uses a fork pool),
+    so the engine is created lazily inside whichever process first needs it."""
+    if device is None:
+        device = int(os.environ.get("VARKODER_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    key = (os.getpid(), device)
+    if key not in _ENGINES:
+        _ENGINES[key] = Engine(device)
+    return _ENGINES[key]
+
+
+def read_clean_fastq(path):
+    """bytes of a cleaned FASTQ (``.fq.gz`` as written by clean_reads, image.py:529-540, or plain text)."""
+    path = str(path)
+    with open(path, "rb") as f:
+        magic = f.read(2)
+    if magic == b"\x1f\x8b":
+        with gzip.open(path, "rb") as f:
+            return f.read()
+    with open(path, "rb") as f:
+        return f.read()
+
+
+def _strip_suffixes(p):
+    p = Path(p)
+    return str(p.name.removesuffix("".join(p.suffixes)))           # image.py:753, 840
+
+
+def write_png(pixels, path, labels=(), base_sd=0, base_sd_thresh=QUAL_THRESH, mapping_code="varKode"):
+    """image.py:920-930: mode L, tEXt keys in the reference's order, optimize=True."""
+    from PIL import Image
+    from PIL.PngImagePlugin import PngInfo
+    img = Image.fromarray(np.ascontiguousarray(pixels, dtype=np.uint8), mode="L")
+    meta = PngInfo()
+    meta.add_text("varkoderKeywords", LABELS_SEP.join(labels))
+    meta.add_text("varkoderBaseFreqSd", str(base_sd))
+    meta.add_text("varkoderLowQualityFlag", str(base_sd > base_sd_thresh))
+    meta.add_text("varkoderMapping", mapping_code)
+    img.save(Path(path), optimize=True, pnginfo=meta)
+
+
+def _image_folder(outfolder, outfile, subfolder_levels):
+    outfolder = Path(outfolder)
+    if subfolder_levels:
+        hsh = list(hashlib.md5(outfile.encode("UTF-8")).hexdigest())      # image.py:850-853
+        for _ in range(subfolder_levels):
+            outfolder = outfolder / hsh.pop()
+    outfolder.mkdir(exist_ok=True, parents=True)
+    return outfolder
+
+
+# --------------------------------------------------------------------------------------------- fused
+def reads_to_images(infile, sample, outfolder, kmer_mapping, k=7, mapping_code="varKode", min_bp=50000,
+                    max_bp=None, is_query=False, seed=None, labels=(), base_sd=0, base_sd_thresh=QUAL_THRESH,
+                    subfolder_levels=0, overwrite=False, verbose=False, engine=None, fastq_bytes=None):
+    """Steps C-E of run_clean2img for one sample (image.py:1005-1125) in one GPU pass.
+
+    Returns the stats dict of the three stages merged (same keys as the reference) and writes
+    ``<outfolder>[/h/...]/<sample>@NNNNNNNNK+<mapping>+k<k>.png`` for every ladder level.
+    Raises ``Exception("Input file has less than minimum data.")`` exactly when split_fastq does.
+    """
+    eng = engine or default_engine()
+    table = as_pixel_table(kmer_mapping, mapping_code)
+    if table.k != int(k):
+        raise ValueError(f"pixel table is for k={table.k}, asked for k={k}")
+    t0 = time.perf_counter()
+    data = fastq_bytes if fastq_bytes is not None else read_clean_fastq(infile)
+    params = Params(k=int(k), min_bp=int(min_bp), max_bp=None if max_bp is None else int(max_bp),
+                    is_query=bool(is_query), seed=seed)
+    res = eng.reads_to_images(data, params, table)
+    if res.status != 0:
+        eprint("Post-cleaning input file " + str(infile) + " has less than " + str(min_bp)
+               + "bp, decrease --min_bp if you want to produce an image.")
+        raise LessThanMinimumData()
+    t1 = time.perf_counter()
+    written = []
+    for lvl, bp in enumerate(res.levels):
+        outfile = image_name(sample, bp, mapping_code, k)
+        folder = _image_folder(outfolder, outfile, subfolder_levels)
+        if not overwrite and (folder / outfile).is_file():
+            eprint("File exists. Skipping image for file:", outfile)
+            continue
+        write_png(res.pixels[lvl], folder / outfile, labels, base_sd, base_sd_thresh, mapping_code)
+        written.append(folder / outfile)
+    t2 = time.perf_counter()
+    tm = eng.timings()
+    stats = OrderedDict()
+    stats["splitting_time"] = (tm["upload"] + tm["parse"] + tm["plan_bucket"]) / 1e3
+    stats["splitting_bp_per_file"] = ",".join(str(x) for x in res.levels)
+    stats[str(k) + "mer_counting_time"] = (tm["count"] + tm["reduce_fold"]) / 1e3
+    stats["k" + str(k) + "_img_time"] = tm["render"] / 1e3 + (t2 - t1)
+    if verbose:
+        eprint(f"varkoder_b200: {sample}: {res.nsites} bp, levels {res.levels}, "
+               f"read+gpu {t1 - t0:.3f}s, png {t2 - t1:.3f}s")
+    return stats
+
+
+# --------------------------------------------------------------------------------- stage-by-stage mirror
+_SAMPLE = {}      # the sample currently resident on the GPU of this process: source path -> state
+
+
+def _resident(source, eng):
+    st = _SAMPLE.get("state")
+    key = (str(source), os.path.getmtime(source), id(eng))
+    if st is None or st["key"] != key:
+        data = read_clean_fastq(source)
+        eng.upload(data)
+        st = dict(key=key, stats=eng.parse(), counts={})
+        _SAMPLE["state"] = st
+    return st
+
+
+def split_fastq(infile, outprefix, outfolder, min_bp=50000, max_bp=None, is_query=False, seed=None,
+                overwrite=False, verbose=False, n_threads=1, engine=None):
+    """image.py:629-725.  Counts the bases on the GPU, builds the ladder, writes one level descriptor per level."""
+    start = time.perf_counter()
+    eng = engine or default_engine()
+    st = _resident(infile, eng)
+    nsites = st["stats"]["nsites"]
+    try:
+        sites_per_file = ladder(nsites, min_bp, max_bp, is_query)
+    except LessThanMinimumData:
+        eprint("Post-cleaning input file " + str(infile) + " has less than " + str(min_bp)
+               + "bp, decrease --min_bp if you want to produce an image.")
+        raise
+    outfs = [Path(outfolder) / (outprefix + SAMPLE_BP_SEP + level_tag(bp) + ".fq.vk") for bp in sites_per_file]
+    if all(f.is_file() for f in outfs):
+        if not overwrite:
+            eprint("Files exist. Skipping subsampling for file:", str(infile))
+            return OrderedDict()
+    Path(outfolder).mkdir(exist_ok=True, parents=True)
+    for lvl, (bp, f) in enumerate(zip(sites_per_file, outfs)):
+        desc = dict(source=str(infile), level=lvl, level_bp=int(bp), sites_per_file=[int(x) for x in sites_per_file],
+                    nsites=int(nsites), min_bp=int(min_bp), max_bp=None if max_bp is None else int(max_bp),
+                    is_query=bool(is_query), seed=str(seed) if seed is not None else None)
+        with open(f, "w") as fh:
+            json.dump(desc, fh)
+    stats = OrderedDict()
+    stats["splitting_time"] = time.perf_counter() - start
+    stats["splitting_bp_per_file"] = ",".join(str(x) for x in sites_per_file)
+    return stats
+
+
+def count_kmers(infile, outfolder, threads=1, k=7, overwrite=False, verbose=False, engine=None):
+    """image.py:727-806.  ``infile`` is a level descriptor written by :func:`split_fastq`."""
+    start = time.perf_counter()
+    outfolder = Path(outfolder)
+    outfolder.mkdir(exist_ok=True)
+    outpath = outfolder / (_strip_suffixes(infile) + BP_KMER_SEP + "k" + str(k) + ".fq.npy")
+    if not overwrite and outpath.is_file():
+        eprint("File exists. Skipping kmer counting for file:", str(infile))
+        return OrderedDict()
+    with open(infile) as fh:
+        desc = json.load(fh)
+    eng = engine or default_engine()
+    st = _resident(desc["source"], eng)
+    ckey = (int(k), desc["min_bp"], desc["max_bp"], desc["is_query"], desc["seed"])
+    if ckey not in st["counts"]:
+        params = Params(k=int(k), min_bp=desc["min_bp"], max_bp=desc["max_bp"], is_query=desc["is_query"],
+                        seed=desc["seed"])
+        res = eng.count(params)
+        res.raise_if_less_than_min()
+        canon, _ = eng.render(None, int(k), len(res.levels))
+        st["counts"][ckey] = (res.levels, canon)
+    levels, canon = st["counts"][ckey]
+    if levels != desc["sites_per_file"]:
+        raise RuntimeError("level descriptor does not match the ladder of its source file")
+    np.save(outpath, canon[desc["level"]])
+    stats = OrderedDict()
+    stats[str(k) + "mer_counting_time"] = time.perf_counter() - start
+    return stats
+
+
+def make_image(infile, outfolder, kmer_mapping, threads=1, overwrite=False, verbose=False, labels=[], base_sd=0,
+               base_sd_thresh=QUAL_THRESH, subfolder_levels=0, mapping_code="varKode", engine=None):
+    """image.py:808-936.  ``infile`` holds the canonical counts written by :func:`count_kmers`."""
+    in_basename = _strip_suffixes(infile)
+    in_base1, in_k = in_basename.split(BP_KMER_SEP)                     # image.py:841 (ValueError if malformed)
+    outfile = in_base1 + BP_KMER_SEP + mapping_code + BP_KMER_SEP + in_k + ".png"
+    outfolder = _image_folder(outfolder, outfile, subfolder_levels)
+    if not overwrite and (outfolder / outfile).is_file():
+        eprint("File exists. Skipping image for file:", str(infile))
+        return OrderedDict()
+    start = time.perf_counter()
+    table = as_pixel_table(kmer_mapping, mapping_code)
+    canon = np.load(infile)
+    if canon.shape != (4 ** table.k,):
+        raise IndexError("k-mer counts do not match the k-mer size of the mapping")      # caller catches IndexError
+    eng = engine or default_engine()
+    pixels = eng.render_counts(table, canon)[0]
+    write_png(pixels, outfolder / outfile, labels, base_sd, base_sd_thresh, mapping_code)
+    stats = OrderedDict()
+    stats["k" + str(table.k) + "_img_time"] = time.perf_counter() - start
+    return stats
