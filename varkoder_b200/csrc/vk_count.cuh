@@ -135,13 +135,15 @@ count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sort
         const uint32_t V = (acgt4(w.x) | (acgt4(w.y) << 4) | (acgt4(w.z) << 8) | (acgt4(w.w) << 12)) & range;
         const uint32_t P = pack4(w.x) | (pack4(w.y) << 8) | (pack4(w.z) << 16) | (pack4(w.w) << 24);
         const uint64_t W = (uint64_t)Cc | ((uint64_t)P << (2 * KM1));
-        const uint32_t VW = Vc | (V << KM1);
+        uint32_t VW = Vc | (V << KM1);
         uint32_t E;
         if (nbrk < cur + 16) {
             // a break point falls in this word: no window may span it (windows wholly before or wholly after)
             const uint32_t b = (uint32_t)(nbrk - cur);         // 0..15: first base of the new piece
             const uint32_t below = (1u << (b + KM1)) - 1u;
-            E = runs_of_k<K>(VW & below) | runs_of_k<K>(VW & ~below);
+            E = runs_of_k<K>(VW & below);
+            VW &= ~below;                                      // bases before the cut are dead for later windows too
+            E |= runs_of_k<K>(VW);
             nbrk += (uint64_t)breaklen;
             if (nbrk >= end) nbrk = ~0ull;
         } else {
