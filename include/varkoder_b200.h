@@ -140,8 +140,9 @@ int vk_reads_to_images(vk_ctx* ctx, const void* text, uint64_t n_bytes, int on_d
                        int slot, int max_levels_out, vk_result* result, uint64_t* canon_host, uint8_t* pixels_host);
 
 /* Device time of the last vk_reads_to_images / stage call, per kernel group, in milliseconds (CUDA events on
- * the context stream): [0] upload, [1] parse, [2] plan+bucket, [3] count, [4] reduce+fold, [5] render, [6] total. */
-int vk_last_timings(vk_ctx* ctx, float* ms7);
+ * the context stream): [0] upload (H2D), [1] parse, [2] plan+bucket, [3] count kernel, [4] slab reduce+fold,
+ * [5] render, [6] read-back (D2H), [7] total. */
+int vk_last_timings(vk_ctx* ctx, float* ms8);
 
 /* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
 uint64_t vk_launch_count(vk_ctx* ctx);

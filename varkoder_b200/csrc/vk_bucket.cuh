@@ -15,9 +15,12 @@
 namespace vk {
 
 constexpr int kBucketThreads = 256;
+constexpr int kBucketCountThreads = 1024;
 
-// pass A: reads and bases per segment
-__global__ void __launch_bounds__(kBucketThreads)
+// pass A: reads and bases per segment.  One CTA per SM; a warp tallies its 32 reads per segment with a ballot and
+// a redux, lane (s mod 32) keeps the running totals of segment s in registers, so the only atomics are a few
+// per warp at the very end (64-bit shared-memory atomics are CAS loops on sm_100 and must stay off the hot loop).
+__global__ void __launch_bounds__(kBucketCountThreads)
 bucket_count_kernel(const uint64_t* __restrict__ starts, const uint64_t* __restrict__ ends, int k, uint64_t seed,
                     uint64_t read_index_base, Plan* __restrict__ plan)
 {
@@ -25,18 +28,45 @@ bucket_count_kernel(const uint64_t* __restrict__ starts, const uint64_t* __restr
     __shared__ uint32_t s_long;
     const int nl = plan->n_levels;
     const uint64_t n_reads = plan->n_reads;
+    const uint32_t lane = threadIdx.x & 31;
     if (threadIdx.x < kMaxLevels) { s_reads[threadIdx.x] = 0; s_bases[threadIdx.x] = 0; }
     if (threadIdx.x == 0) s_long = 0;
     __syncthreads();
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t len = ends[r] - starts[r];
-        if (len < (uint64_t)k) continue;
-        if (len > kEntryLenMask) { atomicAdd(&s_long, 1u); continue; }
-        const int c = levels_of(plan, nl, prio64(seed, read_index_base + r));
-        if (c == 0) continue;
-        atomicAdd(&s_reads[c - 1], 1ull);
-        atomicAdd(&s_bases[c - 1], (unsigned long long)len);
+    unsigned long long my_reads[2] = {0, 0}, my_bases[2] = {0, 0};
+    uint32_t my_long = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_iter = (n_reads + stride - 1) / stride;
+    for (uint64_t it = 0; it < n_iter; ++it) {
+        const uint64_t r = it * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        int seg = -1;
+        uint32_t len32 = 0;
+        if (r < n_reads) {
+            const uint64_t len = ends[r] - starts[r];
+            if (len > kEntryLenMask) ++my_long;
+            else if (len >= (uint64_t)k) {
+                seg = levels_of(plan, nl, prio64(seed, read_index_base + r)) - 1;
+                len32 = (uint32_t)len;
+            }
+        }
+        if (__ballot_sync(0xffffffffu, seg >= 0) == 0) continue;
+        for (int s = 0; s < nl; ++s) {
+            const uint32_t m = __ballot_sync(0xffffffffu, seg == s);
+            if (m == 0) continue;
+            const uint32_t sum = __reduce_add_sync(0xffffffffu, seg == s ? len32 : 0u);    // 32 x 2^24 fits
+            if (lane == (uint32_t)(s & 31)) {
+                my_reads[s >> 5] += __popc(m);
+                my_bases[s >> 5] += sum;
+            }
+        }
     }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (my_reads[h]) {
+            atomicAdd(&s_reads[lane + 32 * h], my_reads[h]);
+            atomicAdd(&s_bases[lane + 32 * h], my_bases[h]);
+        }
+    }
+    if (my_long) atomicAdd(&s_long, my_long);
     __syncthreads();
     if (threadIdx.x < kMaxLevels && s_reads[threadIdx.x]) {
         atomicAdd(&plan->seg_reads[threadIdx.x], s_reads[threadIdx.x]);
@@ -45,44 +75,93 @@ bucket_count_kernel(const uint64_t* __restrict__ starts, const uint64_t* __restr
     if (threadIdx.x == 0 && s_long) atomicAdd(&plan->long_reads, s_long);
 }
 
-// single thread: segment offsets (padded to whole units) and the CTA allocation of the count kernel
-__global__ void bucket_layout_kernel(Plan* __restrict__ plan, uint32_t n_count_ctas)
+// one warp: segment offsets (padded to whole units) and the CTA allocation of the count kernel.
+// lane l owns segments l and l + 32.
+__global__ void __launch_bounds__(32)
+bucket_layout_kernel(Plan* __restrict__ plan, uint32_t n_count_ctas)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint32_t lane = threadIdx.x;
     const int nl = plan->n_levels;
-    uint64_t off = 0;
-    int nonempty = 0;
-    for (int s = 0; s < kMaxLevels; ++s) {
-        plan->seg_begin[s] = off;
-        if (s < nl) {
-            off += (plan->seg_reads[s] + kUnitReads - 1) / kUnitReads * kUnitReads;
-            nonempty += plan->seg_reads[s] != 0;
+    uint64_t reads[2], bases[2], padded[2];
+    uint32_t n_cta[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int s = lane + 32 * h;
+        reads[h] = s < nl ? plan->seg_reads[s] : 0;
+        bases[h] = s < nl ? plan->seg_bases[s] : 0;
+        padded[h] = (reads[h] + kUnitReads - 1) / kUnitReads * kUnitReads;
+        n_cta[h] = reads[h] ? 1u : 0u;
+    }
+    // exclusive scan of the padded sizes over the 64 segments
+    uint64_t run = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint64_t incl = padded[h];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += t;
+        }
+        plan->seg_begin[lane + 32 * h] = run + incl - padded[h];
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) plan->seg_begin[kMaxLevels] = run;
+
+    // CTAs: one per non-empty segment, the rest in proportion to the bases, leftovers one by one to the segment
+    // with the most bases per CTA (minimises the slowest segment)
+    uint64_t total_bases = bases[0] + bases[1];
+    uint32_t used = n_cta[0] + n_cta[1];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        total_bases += __shfl_xor_sync(0xffffffffu, total_bases, d);
+        used += __shfl_xor_sync(0xffffffffu, used, d);
+    }
+    if (used > 0 && used < n_count_ctas && total_bases > 0) {
+        const uint64_t spare = n_count_ctas - used;
+        uint32_t extra = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t e = (uint32_t)(spare * bases[h] / total_bases);      // exact floor: spare < 2^16, bases < 2^47
+            n_cta[h] += reads[h] ? e : 0;
+            extra += reads[h] ? e : 0;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) extra += __shfl_xor_sync(0xffffffffu, extra, d);
+        uint32_t left = (uint32_t)spare - extra;               // fewer than the number of non-empty segments
+        while (left > 0) {
+            double best = -1.0;
+            int best_s = -1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (n_cta[h]) {
+                    const double load = (double)bases[h] / (double)n_cta[h];
+                    if (load > best) { best = load; best_s = lane + 32 * h; }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, d);
+                const int os = __shfl_xor_sync(0xffffffffu, best_s, d);
+                if (ob > best || (ob == best && os >= 0 && (best_s < 0 || os < best_s))) { best = ob; best_s = os; }
+            }
+            if (best_s < 0) break;
+            if ((uint32_t)(best_s & 31) == lane) ++n_cta[best_s >> 5];
+            --left;
         }
     }
-    plan->seg_begin[kMaxLevels] = off;
-    // CTAs per segment: start with one per non-empty segment, then hand out the rest one at a time to the
-    // segment with the most bases per CTA (minimises the maximum load; <= 296 x 64 steps)
-    uint32_t n_cta[kMaxLevels];
-    uint32_t used = 0;
-    for (int s = 0; s < kMaxLevels; ++s) { n_cta[s] = (s < nl && plan->seg_reads[s]) ? 1u : 0u; used += n_cta[s]; }
-    while (used < n_count_ctas && nonempty > 0) {
-        int best = -1;
-        double best_load = -1.0;
-        for (int s = 0; s < nl; ++s) {
-            if (!n_cta[s]) continue;
-            // a segment cannot use more CTAs than it has units
-            const uint64_t units = (plan->seg_reads[s] + kUnitReads - 1) / kUnitReads;
-            if (n_cta[s] >= units) continue;
-            const double load = (double)plan->seg_bases[s] / (double)n_cta[s];
-            if (load > best_load) { best_load = load; best = s; }
+    uint32_t crun = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t incl = n_cta[h];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += t;
         }
-        if (best < 0) break;
-        ++n_cta[best];
-        ++used;
+        plan->seg_cta_begin[lane + 32 * h] = crun + incl - n_cta[h];
+        crun += __shfl_sync(0xffffffffu, incl, 31);
     }
-    uint32_t c = 0;
-    for (int s = 0; s < kMaxLevels; ++s) { plan->seg_cta_begin[s] = c; c += n_cta[s]; }
-    plan->seg_cta_begin[kMaxLevels] = c;
+    if (lane == 0) plan->seg_cta_begin[kMaxLevels] = crun;
 }
 
 // pass B: scatter (start, len) entries into their segment's range

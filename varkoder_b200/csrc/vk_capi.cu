@@ -60,7 +60,7 @@ struct Mapping {
     DevBuf<int32_t> lut;
 };
 
-enum { EV_START = 0, EV_UPLOAD, EV_PARSE, EV_BUCKET, EV_COUNT, EV_FOLD, EV_RENDER, EV_N };
+enum { EV_START = 0, EV_UPLOAD, EV_PARSE, EV_BUCKET, EV_COUNT, EV_FOLD, EV_RENDER, EV_DONE, EV_N };
 
 }  // namespace
 
@@ -81,7 +81,8 @@ struct vk_ctx {
     bool have_text = false, parsed = false, counted = false;
     int counted_k = 0;
 
-    DevBuf<uint64_t> tile_status, starts, ends, sorted;
+    DevBuf<uint64_t> tile_status, masks, starts, ends, sorted;      // tile_status = exclusive newline prefix per tile
+    DevBuf<uint32_t> tile_count, warp_count;
     DevBuf<uint32_t> slabs;
     DevBuf<unsigned long long> seg_hist, canon, vals, bins;
     DevBuf<uint8_t> pixels;
@@ -110,19 +111,28 @@ void enqueue_parse(vk_ctx* c, const vk_params* params, bool rescan = true)
     const size_t cap = c->starts.cap;
     if (rescan) CU(cudaMemsetAsync(c->plan_d, 0, offsetof(Plan, n_lines), c->stream));      // parse fields: counters, sums, ticket
     if (n_tiles && rescan) {
-        CU(cudaMemsetAsync(c->tile_status.p, 0, sizeof(uint64_t) * n_tiles, c->stream));
-        int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)c->n_sms * 8);
-        parse_kernel<<<grid, kParseThreads, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->text), n, 0, n_tiles,
-                                                           c->tile_status.p, c->starts.p, c->ends.p, cap, c->plan_d);
+        c->masks.ensure((size_t)n_tiles * kParseThreads);
+        c->tile_count.ensure(n_tiles);
+        c->warp_count.ensure((size_t)n_tiles * kParseWarps);
+        CU(cudaMemsetAsync(c->tile_count.p, 0, sizeof(uint32_t) * n_tiles, c->stream));
+        const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)c->n_sms * 16);
+        parse_mask_kernel<<<grid, kParseThreads, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->text), n, n_tiles,
+                                                                 c->masks.p, c->tile_count.p, c->warp_count.p);
         CU(cudaGetLastError());
-        ++c->launches;
+        parse_scan_kernel<<<1, 1024, 0, c->stream>>>(c->tile_count.p, n_tiles, c->tile_status.p, c->plan_d);
+        CU(cudaGetLastError());
+        const int egrid = (int)std::min<uint64_t>(((uint64_t)n_tiles * kParseWarps + 7) / 8, (uint64_t)c->n_sms * 32);
+        parse_emit_kernel<<<egrid, 256, 0, c->stream>>>(c->masks.p, c->tile_status.p, c->warp_count.p, n_tiles, 0,
+                                                        c->starts.p, c->ends.p, cap, c->plan_d);
+        CU(cudaGetLastError());
+        c->launches += 3;
     }
     PlanArgs a;
     memset(&a, 0, sizeof(a));
     if (params) a.p = *params;
     a.n_bytes = n;
     a.cap_reads = cap;
-    plan_kernel<<<1, 32, 0, c->stream>>>(c->text, c->starts.p, c->ends.p, a, c->plan_d);
+    plan_kernel<<<1, 64, 0, c->stream>>>(c->text, c->starts.p, c->ends.p, a, c->plan_d);
     CU(cudaGetLastError());
     ++c->launches;
 }
@@ -146,6 +156,7 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist, int breaklen)
             reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d, c->slabs.p, seg_hist, breaklen);
         CU(cudaGetLastError());
         ++c->launches;
+        c->mark(EV_COUNT);
         const uint64_t total = (uint64_t)kMaxLevels * NK;
         reduce_slabs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->slabs.p, c->plan_d, NK, seg_hist);
         CU(cudaGetLastError());
@@ -155,10 +166,12 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist, int breaklen)
         zero_u64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(seg_hist, total);
         CU(cudaGetLastError());
         ++c->launches;
+        c->mark(EV_BUCKET);
         count_kernel<K, false><<<c->n_sms, kCountThreads, 0, c->stream>>>(
             reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d, c->slabs.p, seg_hist, breaklen);
         CU(cudaGetLastError());
         ++c->launches;
+        c->mark(EV_COUNT);
     }
 }
 
@@ -170,7 +183,7 @@ void enqueue_count(vk_ctx* c, const vk_params* p, unsigned long long* seg_hist, 
     c->sorted.ensure(n_reads_bound + (uint64_t)kMaxLevels * kUnitReads);
     if (k <= 7) c->slabs.ensure((size_t)c->n_sms * nk);
     const int bgrid = (int)std::min<uint64_t>((n_reads_bound + kBucketThreads - 1) / kBucketThreads + 1, (uint64_t)c->n_sms * 8);
-    bucket_count_kernel<<<bgrid, kBucketThreads, 0, c->stream>>>(c->starts.p, c->ends.p, k, p->seed, p->read_index_base, c->plan_d);
+    bucket_count_kernel<<<c->n_sms, kBucketCountThreads, 0, c->stream>>>(c->starts.p, c->ends.p, k, p->seed, p->read_index_base, c->plan_d);
     CU(cudaGetLastError());
     bucket_layout_kernel<<<1, 32, 0, c->stream>>>(c->plan_d, (uint32_t)c->n_sms);
     CU(cudaGetLastError());
@@ -187,7 +200,6 @@ void enqueue_count(vk_ctx* c, const vk_params* p, unsigned long long* seg_hist, 
     case 9: launch_count<9>(c, seg_hist, p->breaklength); break;
     default: throw ApiError{VK_EINVAL, "k must be 5..9"};
     }
-    c->mark(EV_COUNT);
 }
 
 // ---- K4 ----------------------------------------------------------------------------------------------
@@ -213,10 +225,11 @@ void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsign
         ++c->launches;
     }
     c->mark(EV_FOLD);
-    const size_t smem = ((size_t)n_pad + 256) * sizeof(unsigned long long);
-    if (smem <= 200 * 1024) {
+    const uint32_t n_pad16 = n_pad < 512 ? 512 : n_pad;                 // at least one warp of 16-value threads
+    const size_t smem = (size_t)(n_pad16 + n_pad16 / 16) * sizeof(unsigned long long);     // one pad word per 16 (bank spread)
+    if (n_pad16 <= 16384) {
         CU(cudaFuncSetAttribute(image_kernel_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        image_kernel_smem<<<levels, kImageThreads, smem, c->stream>>>(c->canon.p, m.lut.p, nk, n_pix, n_pad, c->pixels.p);
+        image_kernel_smem<<<levels, n_pad16 / kImageItems, smem, c->stream>>>(c->canon.p, m.lut.p, nk, n_pix, n_pad16, c->pixels.p);
         CU(cudaGetLastError());
         ++c->launches;
     } else {
@@ -379,6 +392,9 @@ int vk_ctx_destroy(vk_ctx* c)
     cudaStreamSynchronize(c->stream);
     c->text_own.release();
     c->tile_status.release();
+    c->masks.release();
+    c->tile_count.release();
+    c->warp_count.release();
     c->starts.release();
     c->ends.release();
     c->sorted.release();
@@ -426,6 +442,7 @@ int vk_upload(vk_ctx* c, const void* host_bytes, uint64_t n_bytes)
         if (n_bytes >> 40) throw ApiError{VK_ERANGE, "buffers of 2^40 bytes or more are not supported"};
         set_device(c);
         c->mark(EV_START);
+        c->ev_valid[EV_DONE] = false;
         c->text_own.ensure(n_bytes + 64);
         if (n_bytes) CU(cudaMemcpyAsync(c->text_own.p, host_bytes, n_bytes, cudaMemcpyHostToDevice, c->stream));
         c->mark(EV_UPLOAD);
@@ -584,6 +601,7 @@ int vk_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, int on_dev
             enqueue_render(c, m, k, max_levels_out, c->seg_hist.p);
             CU(cudaMemcpyAsync(c->pix_h, c->pixels.p, (size_t)max_levels_out * n_pix, cudaMemcpyDeviceToHost, c->stream));
             fetch_plan(c);
+            c->mark(EV_DONE);
         });
         if (c->plan_h->long_reads) throw ApiError{VK_ERANGE, "a read is longer than 2^24-1 bases"};
         c->parsed = c->counted = true;
@@ -605,20 +623,21 @@ int vk_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, int on_dev
     });
 }
 
-int vk_last_timings(vk_ctx* c, float* ms7)
+int vk_last_timings(vk_ctx* c, float* ms8)
 {
     return guarded([&] {
-        if (!c || !ms7) throw ApiError{VK_EINVAL, "NULL argument"};
-        for (int i = 0; i < 7; ++i) ms7[i] = 0.f;
+        if (!c || !ms8) throw ApiError{VK_EINVAL, "NULL argument"};
+        for (int i = 0; i < 8; ++i) ms8[i] = 0.f;
         for (int i = 1; i < EV_N; ++i) {
             if (c->ev_valid[i] && c->ev_valid[i - 1]) {
                 float t = 0.f;
-                if (cudaEventElapsedTime(&t, c->ev[i - 1], c->ev[i]) == cudaSuccess) ms7[i - 1] = t;
+                if (cudaEventElapsedTime(&t, c->ev[i - 1], c->ev[i]) == cudaSuccess) ms8[i - 1] = t;
             }
         }
-        if (c->ev_valid[EV_START] && c->ev_valid[EV_RENDER]) {
+        const int last = c->ev_valid[EV_DONE] ? EV_DONE : EV_RENDER;
+        if (c->ev_valid[EV_START] && c->ev_valid[last]) {
             float t = 0.f;
-            if (cudaEventElapsedTime(&t, c->ev[EV_START], c->ev[EV_RENDER]) == cudaSuccess) ms7[6] = t;
+            if (cudaEventElapsedTime(&t, c->ev[EV_START], c->ev[last]) == cudaSuccess) ms8[7] = t;
         }
         cudaGetLastError();
     });

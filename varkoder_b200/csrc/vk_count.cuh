@@ -80,7 +80,13 @@ count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sort
     }
     const uint32_t trash = NK + lane;
 
-    // ---- warp-level dynamic read distribution
+    // ---- read distribution: the warps serving a segment take its sorted reads in units of 32 (one per lane,
+    // neighbouring lanes = neighbouring records), unit u going to warp (u mod number-of-warps); inside a warp a
+    // lane that finishes its read takes the next one of the warp's current unit, so lanes stay busy whatever
+    // the read lengths are and no global atomic is needed.
+    const uint32_t seg_ctas = plan->seg_cta_begin[seg + 1] - plan->seg_cta_begin[seg];
+    const uint64_t unit_stride = (uint64_t)seg_ctas * (kCountThreads / 32) * 32;                 // in reads
+    uint64_t unit_at = seg_b + ((uint64_t)(blockIdx.x - plan->seg_cta_begin[seg]) * (kCountThreads / 32) + (tid >> 5)) * 32;
     uint64_t wnext = 0, wend = 0;     // warp-uniform: range of sorted entries the warp still owns
     bool exhausted = false;
     // per-lane read state
@@ -96,11 +102,9 @@ count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sort
         const uint32_t need = __ballot_sync(0xffffffffu, !active);
         if (need) {
             if (wnext >= wend && !exhausted) {
-                unsigned long long ub = 0;
-                if (lane == 0) ub = atomicAdd(&plan->seg_next[seg], (unsigned long long)kUnitReads);
-                ub = __shfl_sync(0xffffffffu, ub, 0);
-                wnext = seg_b + ub;
-                wend = wnext + kUnitReads < seg_e ? wnext + kUnitReads : seg_e;
+                wnext = unit_at;
+                wend = wnext + 32 < seg_e ? wnext + 32 : seg_e;
+                unit_at += unit_stride;
                 if (wnext >= seg_e) { exhausted = true; wnext = wend = seg_e; }
             }
             if (!active) {

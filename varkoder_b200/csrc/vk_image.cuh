@@ -40,54 +40,93 @@ __device__ __forceinline__ unsigned long long pixel_value(const unsigned long lo
     return x < 0 ? 0ull : canon_l[x] + 1ull;
 }
 
-// One CTA per level; the n = side^2 values (<= NPAD, a power of two) are sorted in shared memory (bitonic).
-constexpr int kImageThreads = 1024;
+// Rank scaling without bins.  For a pixel value v that occurs in the image, with c(v) = #{pixels <= v} and
+// n pixels, the digitize-against-quantiles of image.py:916-919 collapses to
+//     out(v) = min(255, floor(256 * (c(v) - 1) / (n - 1)))
+// (bins[i] <= v  <=>  (n-1) * i <= 256 * (c(v) - 1), because v itself is one of the sorted values; derivation in
+// DESIGN.md "K4", checked against the reference's PNGs in tests/golden).  So the kernel only needs c(v): sort the
+// n values once, then an upper bound per pixel.
+//
+// One CTA per level, 16 values per thread: in-register bitonic network for the 16, then log2(n/16) merge-path
+// levels through shared memory (each thread finds its diagonal by binary search and merges 16 outputs serially).
+constexpr int kImageItems = 16;
+// shared-memory index of logical element i: one pad word per 16, so that threads owning consecutive 16-element
+// blocks (stride 17 x 8 B) do not all land on one bank (the unpadded layout was a 32-way conflict: 177 us -> see profiles)
+__device__ __forceinline__ uint32_t sidx(uint32_t i) { return i + (i >> 4); }
 
-__global__ void __launch_bounds__(kImageThreads, 1)
+__device__ __forceinline__ void cex(unsigned long long& a, unsigned long long& b, bool up)
+{
+    const bool sw = (a > b) == up;
+    const unsigned long long lo = sw ? b : a, hi = sw ? a : b;
+    a = lo;
+    b = hi;
+}
+
+__global__ void __launch_bounds__(1024, 1)
 image_kernel_smem(const unsigned long long* __restrict__ canon, const int32_t* __restrict__ lut, uint32_t nk,
                   uint32_t n_pix, uint32_t n_pad, uint8_t* __restrict__ pixels)
 {
-    extern __shared__ unsigned long long s_val[];        // n_pad sorted values, then 256 bins
-    unsigned long long* s_bins = s_val + n_pad;
+    extern __shared__ unsigned long long s_val[];        // n_pad values
     const unsigned long long* canon_l = canon + (size_t)blockIdx.x * nk;
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x;                     // blockDim.x == n_pad / 16
+    const uint32_t base = tid * kImageItems;
 
-    for (uint32_t p = tid; p < n_pad; p += kImageThreads)
-        s_val[p] = p < n_pix ? pixel_value(canon_l, lut, p) : ~0ull;
-    __syncthreads();
+    unsigned long long v[kImageItems];
+#pragma unroll
+    for (int i = 0; i < kImageItems; ++i) v[i] = base + i < n_pix ? pixel_value(canon_l, lut, base + i) : ~0ull;
 
-    // bitonic sort, ascending
-    for (uint32_t size = 2; size <= n_pad; size <<= 1) {
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t t = tid; t < (n_pad >> 1); t += kImageThreads) {
-                const uint32_t lo = 2 * t - (t & (stride - 1));      // index with the stride bit cleared
-                const uint32_t hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const unsigned long long a = s_val[lo], b = s_val[hi];
-                if ((a > b) == up) { s_val[lo] = b; s_val[hi] = a; }
+    // ---- 16 values in registers: bitonic sorting network, ascending
+#pragma unroll
+    for (int size = 2; size <= kImageItems; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int i = 0; i < kImageItems; ++i) {
+                const int l = i ^ stride;
+                if (l > i) cex(v[i], v[l], (i & size) == 0);
             }
-            __syncthreads();
         }
     }
+#pragma unroll
+    for (int i = 0; i < kImageItems; ++i) s_val[sidx(base) + i] = v[i];
 
-    if (tid < 256) {
-        const uint64_t t = (uint64_t)(n_pix - 1) * tid;
-        const uint32_t p = (uint32_t)(t >> 8), g = (uint32_t)(t & 255u);
-        const uint32_t q = p + 1 < n_pix ? p + 1 : n_pix - 1;
-        s_bins[tid] = 256ull * s_val[p] + (s_val[q] - s_val[p]) * g;
+    // ---- merge sorted runs pairwise: run = 16, 32, ..., n_pad / 2
+    for (uint32_t run = kImageItems; run < n_pad; run <<= 1) {
+        __syncthreads();
+        const uint32_t pair_base = base & ~(2 * run - 1);
+        const uint32_t A = pair_base, B = pair_base + run;      // logical offsets of the two runs
+        const uint32_t diag = base - pair_base;           // this thread emits merged outputs diag .. diag+15
+        uint32_t lo = diag > run ? diag - run : 0, hi = diag < run ? diag : run;
+        while (lo < hi) {                                 // merge path: first a with A[a] > B[diag-1-a]
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_val[sidx(A + mid)] <= s_val[sidx(B + diag - 1 - mid)]) lo = mid + 1; else hi = mid;
+        }
+        uint32_t a = lo, b = diag - lo;
+        unsigned long long ka = a < run ? s_val[sidx(A + a)] : ~0ull, kb = b < run ? s_val[sidx(B + b)] : ~0ull;
+#pragma unroll
+        for (int i = 0; i < kImageItems; ++i) {
+            const bool take_a = b >= run || (a < run && ka <= kb);
+            v[i] = take_a ? ka : kb;
+            if (take_a) { ++a; ka = a < run ? s_val[sidx(A + a)] : ~0ull; }
+            else { ++b; kb = b < run ? s_val[sidx(B + b)] : ~0ull; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kImageItems; ++i) s_val[sidx(base) + i] = v[i];
     }
     __syncthreads();
 
+    // ---- c(v) = upper bound over the n_pix real values (the padding sorts last), then the closed form
     uint8_t* out = pixels + (size_t)blockIdx.x * n_pix;
-    for (uint32_t p = tid; p < n_pix; p += kImageThreads) {
-        const unsigned long long v = 256ull * pixel_value(canon_l, lut, p);
-        // number of bins <= v (bins are non-decreasing, bins[0] <= v always)
-        uint32_t lo = 0, hi = 256;
+    for (uint32_t p = tid; p < n_pix; p += blockDim.x) {
+        const unsigned long long val = pixel_value(canon_l, lut, p);
+        uint32_t lo = 0, hi = n_pix;
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (s_bins[mid] <= v) lo = mid + 1; else hi = mid;
+            if (s_val[sidx(mid)] <= val) lo = mid + 1; else hi = mid;
         }
-        out[p] = (uint8_t)(lo - 1);
+        const uint32_t g = n_pix > 1 ? (256u * (lo - 1)) / (n_pix - 1) : 0u;        // lo <= 2^14: fits 32 bits
+        out[p] = (uint8_t)(g > 255u ? 255u : g);
     }
 }
 

@@ -4,23 +4,26 @@
 // '\n', line index % 4 == 1 is a sequence line, nsites = sum(len(line) - 1)) and for the ladder that follows
 // it (image.py:669-695).
 //
-// K1 is HBM-bound: every byte is read exactly once with 16-byte loads.  A tile of 16 KiB is owned by one
-// CTA; the line index of a tile's first byte (which decides what each newline in the tile terminates) is
-// the exclusive prefix sum of newline counts over all earlier tiles, obtained with a single-pass
-// decoupled look-back (one 64-bit status word per tile: 2 flag bits + 62 value bits), so there is no
-// second pass over the text.  Output: for read r, starts[r] = offset of its sequence line and ends[r] =
-// offset of the newline closing it; nsites falls out as sum(ends) - sum(starts) in modular arithmetic.
+// K1 is HBM-bound: every byte of the text is read exactly once with 16-byte loads.  Deciding what a newline
+// terminates needs the number of newlines before it, a prefix sum over the whole file.  A single-pass
+// decoupled look-back was tried first and measured at 1.8 TB/s (16 KiB tiles, 32-wide window) and 1.0 TB/s
+// (32 KiB, 128-wide, static tiles): its throughput is tile bytes x window / L2 round trip and the tiles of a
+// wave all wait at the same time (profiles/r01_notes.md).  The shipped form has no waiting at all:
+//   K1a parse_mask_kernel   streams the text once, writes one 64-bit newline mask per 64 bytes (1/8 of the
+//                           text) and a newline count per 32 KiB tile;
+//   K1s parse_scan_kernel   one CTA: exclusive prefix of the tile counts (13 k tiles for 423 MB);
+//   K1b parse_emit_kernel   reads the masks (not the text) + the tile prefix and writes, for read r,
+//                           starts[r] = offset of its sequence line, ends[r] = offset of the closing newline;
+// nsites falls out as sum(ends) - sum(starts) in modular arithmetic.
 #pragma once
 #include "vk_common.cuh"
 
 namespace vk {
 
-constexpr int kParseThreads = 256;
+constexpr int kParseThreads = 512;
+constexpr int kParseWarps = kParseThreads / 32;
 constexpr int kParseWordsPerThread = 4;                                   // 4 x 16 B = 64 contiguous bytes per thread
-constexpr uint32_t kParseTileBytes = kParseThreads * kParseWordsPerThread * 16;   // 16 KiB
-constexpr uint64_t kFlagAgg = 1ull << 62;
-constexpr uint64_t kFlagIncl = 2ull << 62;
-constexpr uint64_t kValMask = (1ull << 62) - 1;
+constexpr uint32_t kParseTileBytes = kParseThreads * kParseWordsPerThread * 16;   // 32 KiB
 
 // 4-bit mask of the bytes of x equal to '\n'
 __device__ __forceinline__ uint32_t nl4(uint32_t x)
@@ -35,27 +38,14 @@ __device__ __forceinline__ uint32_t nl16(uint4 w)
     return nl4(w.x) | (nl4(w.y) << 4) | (nl4(w.z) << 8) | (nl4(w.w) << 12);
 }
 
+// K1a: thread t of tile T owns bytes [T*32Ki + 64t, +64): mask bit j = byte j is '\n'.
 __global__ void __launch_bounds__(kParseThreads)
-parse_kernel(const uint4* __restrict__ text16, uint64_t n_bytes, uint64_t byte_base, uint32_t n_tiles,
-             uint64_t* __restrict__ tile_status, uint64_t* __restrict__ starts, uint64_t* __restrict__ ends,
-             uint64_t cap_reads, Plan* __restrict__ plan)
+parse_mask_kernel(const uint4* __restrict__ text16, uint64_t n_bytes, uint32_t n_tiles,
+                  uint64_t* __restrict__ masks, uint32_t* __restrict__ tile_count, uint32_t* __restrict__ warp_count)
 {
-    __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_prefix;
-    __shared__ uint32_t s_warp[kParseThreads / 32];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t carry_in = plan->n_newlines;       // read once, before any tile of this launch can finish
-    uint64_t sum_s = 0, sum_e = 0;
-    uint32_t overflow = 0;
-
-    for (;;) {
-        if (tid == 0) s_tile = atomicAdd(&plan->parse_ticket, 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= n_tiles) break;
-
-        // ---- load 64 contiguous bytes, build the newline mask
-        const uint64_t tbyte = (uint64_t)tile * kParseTileBytes + (uint64_t)tid * (kParseWordsPerThread * 16);
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t tbyte = (uint64_t)tile * kParseTileBytes + (uint64_t)tid * 64;
         uint64_t m = 0;
         if (tbyte < n_bytes) {
             uint4 w[kParseWordsPerThread];
@@ -66,69 +56,94 @@ parse_kernel(const uint4* __restrict__ text16, uint64_t n_bytes, uint64_t byte_b
             }
 #pragma unroll
             for (int i = 0; i < kParseWordsPerThread; ++i) m |= (uint64_t)nl16(w[i]) << (16 * i);
-            const uint64_t left = n_bytes - tbyte;             // bytes of this thread's span inside the buffer
-            if (left < 64) m &= (1ull << left) - 1;
+            if (n_bytes - tbyte < 64) m &= (1ull << (n_bytes - tbyte)) - 1;
         }
-        const uint32_t cnt = __popcll(m);
+        masks[(uint64_t)tile * kParseThreads + tid] = m;
+        const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popcll(m));
+        if (lane == 0) {
+            warp_count[(uint64_t)tile * kParseWarps + (tid >> 5)] = c;       // newlines in this warp's 2 KiB
+            if (c) atomicAdd(tile_count + tile, c);
+        }
+    }
+}
 
-        // ---- block exclusive scan of the counts
-        uint32_t incl = cnt;
+// K1s: one CTA; tile_prefix[T] = carry + newlines in tiles < T; plan->n_newlines = carry + all.
+// Counts are staged through shared memory in chunks (coalesced loads/stores), each thread scans a contiguous slice.
+constexpr uint32_t kScanChunk = 8192;            // 32 KiB of static shared memory
+__global__ void __launch_bounds__(1024)
+parse_scan_kernel(const uint32_t* __restrict__ tile_count, uint32_t n_tiles, uint64_t* __restrict__ tile_prefix,
+                  Plan* __restrict__ plan)
+{
+    __shared__ uint32_t s_cnt[kScanChunk];
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint64_t carry = plan->n_newlines;
+    constexpr uint32_t PER = kScanChunk / 1024;
+    for (uint32_t c0 = 0; c0 < n_tiles; c0 += kScanChunk) {
+        const uint32_t n = n_tiles - c0 < kScanChunk ? n_tiles - c0 : kScanChunk;
+        for (uint32_t i = tid; i < kScanChunk; i += 1024) s_cnt[i] = i < n ? tile_count[c0 + i] : 0u;
+        __syncthreads();
+        uint32_t loc[PER], sum = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < PER; ++i) { loc[i] = sum; sum += s_cnt[tid * PER + i]; }
+        uint32_t incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += t;
         }
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-
         if (warp == 0) {
-            uint32_t wv = (lane < kParseThreads / 32) ? s_warp[lane] : 0;
+            const uint32_t wv = s_warp[lane];
             uint32_t wi = wv;
 #pragma unroll
-            for (int d = 1; d < 8; d <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
-                if (lane >= d) wi += t;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= (uint32_t)d) wi += t;
             }
-            const uint32_t total = __shfl_sync(0xffffffffu, wi, kParseThreads / 32 - 1);
-            if (lane < kParseThreads / 32) s_warp[lane] = wi - wv;      // exclusive warp offsets
-            // ---- decoupled look-back
-            uint64_t excl = carry_in;
-            if (tile == 0) {
-                if (lane == 0) st_volatile_u64(tile_status + 0, kFlagIncl | (carry_in + total));
-            } else {
-                if (lane == 0) st_volatile_u64(tile_status + tile, kFlagAgg | (uint64_t)total);
-                int64_t j = (int64_t)tile - 1;
-                excl = 0;
-                for (;;) {
-                    const int64_t idx = j - (int64_t)lane;
-                    uint64_t v = (idx >= 0) ? ld_volatile_u64(tile_status + idx) : (kFlagIncl | carry_in);
-                    // before tile 0 sits a virtual inclusive prefix; only the first lane past it counts
-                    if (idx < -1) v = kFlagIncl;
-                    if (__any_sync(0xffffffffu, (v >> 62) == 0)) continue;     // a predecessor has not published yet
-                    const uint32_t inc = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-                    uint64_t c = v & kValMask;
-                    if (inc) {
-                        const int first = __ffs(inc) - 1;                       // nearest predecessor with a full prefix
-                        if ((int)lane > first) c = 0;
-                    }
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-                    excl += c;
-                    if (inc) break;
-                    j -= 32;
-                }
-                if (lane == 0) st_volatile_u64(tile_status + tile, kFlagIncl | (excl + total));
-            }
-            if (lane == 0) {
-                s_prefix = excl;
-                if (tile == n_tiles - 1) plan->n_newlines = excl + total;       // carry for the next chunk / final total
-            }
+            s_warp[lane] = wi - wv;
+            if (lane == 31) s_total = wi;
         }
         __syncthreads();
+        const uint32_t base = s_warp[warp] + incl - sum;
+#pragma unroll
+        for (uint32_t i = 0; i < PER; ++i) s_cnt[tid * PER + i] = base + loc[i];      // exclusive prefix inside the chunk
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += 1024) tile_prefix[c0 + i] = carry + s_cnt[i];
+        carry += s_total;
+        __syncthreads();
+    }
+    if (tid == 0) plan->n_newlines = carry;
+}
 
-        // ---- what does each newline terminate?  line index = number of newlines before it
-        uint64_t line = s_prefix + s_warp[warp] + (incl - cnt);
-        const uint64_t pos0 = byte_base + tbyte;
+// K1b: one WARP per 2 KiB of text (32 masks); no block-level synchronisation.
+// line index of a newline = tile prefix + newlines in earlier warps of the tile + newlines in earlier lanes + rank.
+__global__ void __launch_bounds__(256)
+parse_emit_kernel(const uint64_t* __restrict__ masks, const uint64_t* __restrict__ tile_prefix,
+                  const uint32_t* __restrict__ warp_count, uint32_t n_tiles, uint64_t byte_base,
+                  uint64_t* __restrict__ starts, uint64_t* __restrict__ ends, uint64_t cap_reads, Plan* __restrict__ plan)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n_wt = (uint64_t)n_tiles * kParseWarps;                 // warp-tiles
+    const uint64_t wstride = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    uint64_t sum_s = 0, sum_e = 0;
+    uint32_t overflow = 0;
+    for (uint64_t g = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < n_wt; g += wstride) {
+        const uint32_t tile = (uint32_t)(g / kParseWarps), wit = (uint32_t)(g % kParseWarps);
+        uint64_t m = masks[g * 32 + lane];
+        const uint32_t wc = lane < wit ? warp_count[(uint64_t)tile * kParseWarps + lane] : 0u;
+        const uint32_t woff = __reduce_add_sync(0xffffffffu, wc);
+        const uint32_t cnt = __popcll(m);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += t;
+        }
+        uint64_t line = tile_prefix[tile] + woff + (incl - cnt);
+        const uint64_t pos0 = byte_base + g * 2048 + (uint64_t)lane * 64;
         while (m) {
             const int j = __ffsll((long long)m) - 1;
             m &= m - 1;
@@ -144,9 +159,7 @@ parse_kernel(const uint4* __restrict__ text16, uint64_t n_bytes, uint64_t byte_b
             }
             ++line;
         }
-        // s_tile / s_prefix / s_warp are rewritten only after the next iteration's barriers
     }
-
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         sum_s += __shfl_xor_sync(0xffffffffu, sum_s, d);
@@ -180,69 +193,82 @@ __device__ inline uint64_t div_2p64(uint64_t num, uint64_t den)
     return q;
 }
 
-__global__ void plan_kernel(const uint8_t* __restrict__ text, uint64_t* __restrict__ starts,
-                            uint64_t* __restrict__ ends, PlanArgs a, Plan* __restrict__ plan)
+__global__ void __launch_bounds__(64)
+plan_kernel(const uint8_t* __restrict__ text, uint64_t* __restrict__ starts, uint64_t* __restrict__ ends, PlanArgs a,
+            Plan* __restrict__ plan)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const uint64_t n = a.n_bytes;
-    const uint64_t T = plan->n_newlines;
-    const bool last_nl = n > 0 && text[n - 1] == '\n';
-    const uint64_t n_lines = T + ((n > 0 && !last_nl) ? 1 : 0);      // Python yields an unterminated last line too
-    const uint64_t n_reads = (n_lines + 2) >> 2;                      // line indices 1 mod 4
-    uint64_t S = plan->sum_starts, E = plan->sum_ends;
-    uint64_t ref_adjust = 0;
-    if ((T & 3) == 1) {
-        // a header newline opened a sequence line that no newline closed
-        if (!last_nl) {                    // unterminated, non-empty sequence line: closes at EOF
-            if (n_reads >= 1 && n_reads - 1 < a.cap_reads) ends[n_reads - 1] = n;
-            E += n;
-            ref_adjust = 1;                // len(line) - 1 drops a real base here (image.py:666)
-        } else {
-            S -= n;                        // header newline was the last byte: no such line for Python
+    // one CTA of 64 threads: thread 0 finishes the framing and walks the ladder (sequential by nature, ~10 levels),
+    // then thread l computes level l's priority threshold (a 64-step long division each) and clears its segment slots
+    __shared__ uint64_t s_lv[kMaxLevels];
+    __shared__ uint64_t s_nsites;
+    __shared__ int s_nl;
+    const int l = threadIdx.x;
+    if (l == 0) {
+        const uint64_t n = a.n_bytes;
+        const uint64_t T = plan->n_newlines;
+        const bool last_nl = n > 0 && text[n - 1] == '\n';
+        const uint64_t n_lines = T + ((n > 0 && !last_nl) ? 1 : 0);      // Python yields an unterminated last line too
+        const uint64_t n_reads = (n_lines + 2) >> 2;                      // line indices 1 mod 4
+        uint64_t S = plan->sum_starts, E = plan->sum_ends;
+        uint64_t ref_adjust = 0;
+        if ((T & 3) == 1) {
+            // a header newline opened a sequence line that no newline closed
+            if (!last_nl) {                    // unterminated, non-empty sequence line: closes at EOF
+                if (n_reads >= 1 && n_reads - 1 < a.cap_reads) ends[n_reads - 1] = n;
+                E += n;
+                ref_adjust = 1;                // len(line) - 1 drops a real base here (image.py:666)
+            } else {
+                S -= n;                        // header newline was the last byte: no such line for Python
+            }
         }
-    }
-    plan->n_bytes = n;
-    plan->n_lines = n_lines;
-    plan->n_reads = n_reads;
-    plan->nsites_true = E - S;
-    plan->nsites_ref = E - S - ref_adjust;
-    if (n_reads > a.cap_reads) plan->table_overflow = 1;
+        plan->n_bytes = n;
+        plan->n_lines = n_lines;
+        plan->n_reads = n_reads;
+        plan->nsites_true = E - S;
+        plan->nsites_ref = E - S - ref_adjust;
+        if (n_reads > a.cap_reads) plan->table_overflow = 1;
 
-    // ---- ladder, image.py:669-695 in integers
-    const uint64_t nsites = a.p.nsites_override ? a.p.nsites_override : plan->nsites_ref;
-    plan->nsites_ladder = nsites;
-    int nl = 0;
-    int status = VK_LADDER_OK;
-    uint64_t lv[kMaxLevels];
-    if (!a.p.has_max_bp) lv[nl++] = nsites;
-    else if (a.p.is_query || nsites > a.p.min_bp) lv[nl++] = nsites < a.p.max_bp ? nsites : a.p.max_bp;
-    else status = VK_LADDER_LESS_THAN_MIN;
-    if (status == VK_LADDER_OK && !a.p.is_query) {
-        while (lv[nl - 1] > a.p.min_bp && nl < kMaxLevels) {
-            const uint64_t oneless = lv[nl - 1] - 1;
-            if (oneless == 0) break;                      // the reference would raise in log10(0); min_bp = 0 only
-            uint64_t p10 = 1;
-            while (oneless / p10 >= 10) p10 *= 10;        // 10^floor(log10(oneless))
-            const uint64_t fd = oneless / p10;
-            const uint64_t mult = fd >= 5 ? 5 : (fd >= 2 ? 2 : 1);   // largest of {1,2,5} <= first digit
-            lv[nl++] = mult * p10;
+        // ---- ladder, image.py:669-695 in integers
+        const uint64_t nsites = a.p.nsites_override ? a.p.nsites_override : (E - S - ref_adjust);
+        plan->nsites_ladder = nsites;
+        int nl = 0;
+        int status = VK_LADDER_OK;
+        if (!a.p.has_max_bp) s_lv[nl++] = nsites;
+        else if (a.p.is_query || nsites > a.p.min_bp) s_lv[nl++] = nsites < a.p.max_bp ? nsites : a.p.max_bp;
+        else status = VK_LADDER_LESS_THAN_MIN;
+        if (status == VK_LADDER_OK && !a.p.is_query) {
+            while (s_lv[nl - 1] > a.p.min_bp && nl < kMaxLevels) {
+                const uint64_t oneless = s_lv[nl - 1] - 1;
+                if (oneless == 0) break;                      // the reference would raise in log10(0); min_bp = 0 only
+                uint64_t p10 = 1;
+                while (oneless / p10 >= 10) p10 *= 10;        // 10^floor(log10(oneless))
+                const uint64_t fd = oneless / p10;
+                const uint64_t mult = fd >= 5 ? 5 : (fd >= 2 ? 2 : 1);   // largest of {1,2,5} <= first digit
+                s_lv[nl++] = mult * p10;
+            }
+            if (s_lv[nl - 1] < a.p.min_bp) --nl;
         }
-        if (lv[nl - 1] < a.p.min_bp) --nl;
+        if (status != VK_LADDER_OK) nl = 0;
+        plan->status = status;
+        plan->n_levels = nl;
+        plan->long_reads = 0;
+        s_nl = nl;
+        s_nsites = nsites;
     }
-    if (status != VK_LADDER_OK) nl = 0;
-    plan->status = status;
-    plan->n_levels = nl;
-    for (int l = 0; l < kMaxLevels; ++l) {
-        plan->level_bp[l] = l < nl ? lv[l] : 0;
-        const bool all = l < nl && (lv[l] >= nsites || nsites == 0);
+    __syncthreads();
+    if (l < kMaxLevels) {
+        const int nl = s_nl;
+        const uint64_t nsites = s_nsites;
+        const uint64_t bp = l < nl ? s_lv[l] : 0;
+        const bool all = l < nl && (bp >= nsites || nsites == 0);
+        plan->level_bp[l] = bp;
         plan->level_all[l] = all ? 1u : 0u;
-        plan->level_thr[l] = l < nl ? (all ? kThrAll : div_2p64(lv[l], nsites)) : 0;
+        plan->level_thr[l] = l < nl ? (all ? kThrAll : div_2p64(bp, nsites)) : 0;
         plan->seg_reads[l] = 0;
         plan->seg_bases[l] = 0;
         plan->seg_cursor[l] = 0;
         plan->seg_next[l] = 0;
     }
-    plan->long_reads = 0;
 }
 
 }  // namespace vk

@@ -8,7 +8,7 @@ from . import _lib
 from .ladder import LessThanMinimumData, parse_seed
 from .mapping import PixelTable
 
-TIMING_KEYS = ("upload", "parse", "plan_bucket", "count", "reduce_fold", "render", "total")
+TIMING_KEYS = ("upload", "parse", "plan_bucket", "count", "reduce_fold", "render", "readback", "total")
 
 
 class VkError(RuntimeError):
@@ -192,7 +192,7 @@ class Engine:
 
     # ------------------------------------------------------------------ misc
     def timings(self):
-        ms = (C.c_float * 7)()
+        ms = (C.c_float * 8)()
         self._check(self._L.vk_last_timings(self._ctx, ms))
         return dict(zip(TIMING_KEYS, [float(x) for x in ms]))
 
