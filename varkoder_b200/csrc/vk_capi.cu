@@ -71,6 +71,7 @@ struct vk_ctx {
     cudaEvent_t ev[EV_N] = {};
     bool ev_valid[EV_N] = {};
     uint64_t launches = 0;
+    int count_threads = 1024, count_ctas_per_sm = 1;      // count-kernel launch shape (VK_COUNT_THREADS / VK_COUNT_CTAS)
 
     vk::Plan* plan_d = nullptr;
     vk::Plan* plan_h = nullptr;     // pinned
@@ -150,9 +151,10 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist, int breaklen)
     using namespace vk;
     constexpr uint32_t NK = 1u << (2 * K);
     if (K <= 7) {
-        const size_t smem = (size_t)(NK + 32) * sizeof(uint32_t);
+        // the histogram sits at a 64 KiB-aligned shared address (vk_count.cuh step16): up to 64 KiB of padding in front
+        const size_t smem = 0x10000 + (size_t)(NK + 32) * sizeof(uint32_t);
         CU(cudaFuncSetAttribute(count_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        count_kernel<K, true><<<c->n_sms, kCountThreads, smem, c->stream>>>(
+        count_kernel<K, true><<<c->n_sms * c->count_ctas_per_sm, c->count_threads, smem, c->stream>>>(
             reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d, c->slabs.p, seg_hist, breaklen);
         CU(cudaGetLastError());
         ++c->launches;
@@ -167,7 +169,7 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist, int breaklen)
         CU(cudaGetLastError());
         ++c->launches;
         c->mark(EV_BUCKET);
-        count_kernel<K, false><<<c->n_sms, kCountThreads, 0, c->stream>>>(
+        count_kernel<K, false><<<c->n_sms * c->count_ctas_per_sm, c->count_threads, 0, c->stream>>>(
             reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d, c->slabs.p, seg_hist, breaklen);
         CU(cudaGetLastError());
         ++c->launches;
@@ -181,11 +183,11 @@ void enqueue_count(vk_ctx* c, const vk_params* p, unsigned long long* seg_hist, 
     const int k = p->k;
     const uint32_t nk = 1u << (2 * k);
     c->sorted.ensure(n_reads_bound + (uint64_t)kMaxLevels * kUnitReads);
-    if (k <= 7) c->slabs.ensure((size_t)c->n_sms * nk);
+    if (k <= 7) c->slabs.ensure((size_t)c->n_sms * c->count_ctas_per_sm * nk);
     const int bgrid = (int)std::min<uint64_t>((n_reads_bound + kBucketThreads - 1) / kBucketThreads + 1, (uint64_t)c->n_sms * 8);
     bucket_count_kernel<<<c->n_sms, kBucketCountThreads, 0, c->stream>>>(c->starts.p, c->ends.p, k, p->seed, p->read_index_base, c->plan_d);
     CU(cudaGetLastError());
-    bucket_layout_kernel<<<1, 32, 0, c->stream>>>(c->plan_d, (uint32_t)c->n_sms);
+    bucket_layout_kernel<<<1, 32, 0, c->stream>>>(c->plan_d, (uint32_t)(c->n_sms * c->count_ctas_per_sm));
     CU(cudaGetLastError());
     bucket_scatter_kernel<<<bgrid, kBucketThreads, 0, c->stream>>>(c->starts.p, c->ends.p, k, p->seed, p->read_index_base, 0,
                                                                   c->sorted.p, c->plan_d);
@@ -375,6 +377,10 @@ int vk_ctx_create(int device, vk_ctx** out)
         vk_ctx* c = new vk_ctx();
         c->device = device;
         c->n_sms = prop.multiProcessorCount;
+        if (const char* e = getenv("VK_COUNT_THREADS")) c->count_threads = atoi(e);
+        if (const char* e = getenv("VK_COUNT_CTAS")) c->count_ctas_per_sm = atoi(e);
+        if (c->count_threads < 32 || c->count_threads > 1024 || c->count_threads % 32 || c->count_ctas_per_sm < 1 || c->count_ctas_per_sm > 3)
+            throw ApiError{VK_EINVAL, "bad VK_COUNT_THREADS / VK_COUNT_CTAS"};
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (int i = 0; i < EV_N; ++i) CU(cudaEventCreate(&c->ev[i]));
         CU(cudaMalloc(&c->plan_d, sizeof(vk::Plan)));
