@@ -181,47 +181,71 @@ def best_thread_count(buf):
         dt, _, _ = cpu_path_once(buf, th)
         if best_dt is None or dt < best_dt:
             best_t, best_dt = th, dt
-    return best_t
+    return best_t, best_dt
 
 
-def run_cpu_baseline(sample_bases=20_000_000, reps=2):
-    buf = cpu_sample(sample_bases)
-    threads = best_thread_count(buf)
-    best = None
-    for _ in range(reps):
-        dt, nsites, nl = cpu_path_once(buf, threads)
-        best = dt if best is None else min(best, dt)
-    return {"value": sample_bases / best / 1e9, "unit": "Gbases/s", "cores": threads, "kind": "port",
-            "sample": f"{sample_bases} bases of the same synthetic shape (L=150), k=7 cgr, {nl}-level ladder "
-                      f"{sample_bases}..{MIN_BP}, oracle port (C/OpenMP dsk restatement + exact make_image arithmetic), "
-                      f"uncompressed FASTQ bytes in host memory, {best:.2f} s"}
+SAMPLE_SIZES = (200_000_000, 100_000_000, 50_000_000, 20_000_000, 10_000_000, 5_000_000)
+
+
+def cpu_sample_desc(sample_bases, nl, secs):
+    return (f"{sample_bases} bases of the workload's synthetic shape (L=150), k=7 cgr, {nl}-level ladder "
+            f"{sample_bases}..{MIN_BP}; oracle port of the reference CPU path (framing + seeded sub-sampling + dsk restated "
+            f"in C/OpenMP + exact make_image arithmetic), uncompressed FASTQ bytes in host memory, {secs:.2f} s per pass; "
+            "the reference's own dsk / dsk2ascii / reformat.sh binaries cannot be installed offline")
+
+
+def run_cpu_baseline(host_bytes, budget_s=20.0):
+    """GPU arm, rank 0, N=1: the CPU path on the SAME 200 Mbp bytes the GPU just processed, repeated for about
+    budget_s seconds (at least one pass, at most five)."""
+    probe = host_bytes[:synth_total(5_000_000)]
+    threads, _ = best_thread_count(probe)
+    times = []
+    nl = 0
+    while not times or (sum(times) < budget_s and len(times) < 5):
+        dt, nsites, nl = cpu_path_once(host_bytes, threads)
+        times.append(dt)
+    best = min(times)
+    return {"value": N_BASES / best / 1e9, "unit": "Gbases/s", "cores": threads, "kind": "port",
+            "sample": cpu_sample_desc(N_BASES, nl, best) + f"; best of {len(times)} passes"}
+
+
+def synth_total(n_bases):
+    from varkoder_b200 import synth
+    return synth.fixed_total_bytes(n_bases, READ_LEN)
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_bases = 20_000_000
-    buf = cpu_sample(sample_bases)
-    threads = best_thread_count(buf)
-    for _ in range(max(0, min(args.warmup, 1))):
+    # size each step's sample so that the whole run ends within a few minutes whatever K is
+    probe = cpu_sample(5_000_000)
+    threads, probe_dt = best_thread_count(probe)
+    speed = 5_000_000 / probe_dt
+    steps = max(1, args.steps)
+    warm = min(max(args.warmup, 0), 1)
+    sample_bases = SAMPLE_SIZES[-1]
+    for sz in SAMPLE_SIZES:
+        if (steps + warm) * sz / speed <= 100.0 and sz * 0.11e-6 <= 60.0:       # second term: host generator time
+            sample_bases = sz
+            break
+    buf = probe if sample_bases == 5_000_000 else cpu_sample(sample_bases)
+    for _ in range(warm):
         cpu_path_once(buf, threads)
     times = []
     nl = 0
-    for _ in range(max(1, args.steps)):
+    for _ in range(steps):
         dt, nsites, nl = cpu_path_once(buf, threads)
         times.append(dt)
     total = sum(times)
     val = sample_bases * len(times) / total / 1e9
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Gbases/s", "n_gpus": args.gpus,
-        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / len(times),
+        "steps": len(times), "warmup": warm, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": workload_config(),
         "cpu_baseline": {"value": val, "unit": "Gbases/s", "cores": threads, "kind": "port",
-                         "sample": f"each step = {sample_bases} bases of the workload's shape, {nl}-level ladder, "
-                                   "oracle port of the reference CPU path (dsk/reformat restated in C + make_image arithmetic); "
-                                   "the reference's own dsk/dsk2ascii/reformat.sh binaries are not installable offline"},
+                         "sample": "each step = " + cpu_sample_desc(sample_bases, nl, total / len(times))},
         "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -322,6 +346,30 @@ def main():
     assert (r2.pixels == res.pixels).all()
     d2h = int(res.pixels.size) + 4096
 
+    # ---- N > 1 only: ONE sample of N x 200 Mbp read-sharded over the ranks (BASELINE configs[4] shape): every rank
+    # frames and counts its shard, one NCCL all-reduce sums the per-segment histograms, every rank renders.
+    sharded = None
+    if world > 1:
+        from varkoder_b200 import sharding
+        seg = torch.zeros(64 * 4 ** K, dtype=torch.int64, device="cuda")
+        sp = Params(k=K, min_bp=MIN_BP, max_bp=None, seed=7)
+        eng.attach(dev.data_ptr(), total)
+        for _ in range(2):
+            rs = sharding.sharded_reads_to_images(eng, None, sp, table, seg_hist=seg)
+        assert rs.nsites == world * n_bases and rs.levels[0] == world * n_bases
+        s_steps = max(1, min(args.steps, 50))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(s_steps):
+            eng.attach(dev.data_ptr(), total)
+            rs = sharding.sharded_reads_to_images(eng, None, sp, table, seg_hist=seg)
+        barrier()
+        sh_ms = 1e3 * (time.perf_counter() - t0) / s_steps
+        sharded = {"workload": f"one sample of {world}x{n_bases} bases read-sharded over {world} GPUs, k={K} {MAPPING}, "
+                               f"{len(rs.levels)} levels, all_gather(2 scalars) + NCCL all_reduce(int64 x {seg.numel()})",
+                   "steps": s_steps, "ms_per_step_wall": sh_ms, "value": world * n_bases / (sh_ms * 1e-3) / 1e9,
+                   "unit": "Gbases/s"}
+
     t = torch.tensor([dev_ms, wall_ms, e2e_ms, per_kernel["count"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -358,8 +406,10 @@ def main():
             "kernel_ms_per_step": {k2: v / steps for k2, v in per_kernel.items()},
             "level_bases": res.level_bases,
         }
+        if sharded is not None:
+            out["read_sharded"] = sharded
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = run_cpu_baseline()
+            out["cpu_baseline"] = run_cpu_baseline(host.numpy())
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

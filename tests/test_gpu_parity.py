@@ -289,3 +289,28 @@ def test_full_size_properties_config2(engine):
     head = dev[:nb].cpu().numpy().tobytes()
     r2 = engine.reads_to_images(head, Params(k=k, min_bp=0, max_bp=None, is_query=True), table, want_canon=True)
     assert (r2.canon[0] == dsk.canonical_counts(head, k, threads=0)).all()
+
+
+def test_sharded_driver_with_real_engine_nccl(engine):
+    """the read-sharded driver (varkoder_b200/sharding.py) with the CUDA engine and an NCCL group of one rank:
+    all_gather + all_reduce run on the device and the result equals the unsharded path and the oracle."""
+    import torch
+    import torch.distributed as dist
+    from varkoder_b200 import sharding
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29631")
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        buf = synth.fixed(400_000, 150, seed=5).tobytes()
+        table = get_kmer_mapping(7, "cgr")
+        params = Params(k=7, min_bp=50_000, max_bp=None, seed=99)
+        res = sharding.sharded_reads_to_images(engine, buf, params, table, want_canon=True)
+        ref = engine.reads_to_images(buf, params, table, want_canon=True)
+        assert res.levels == ref.levels == [400_000, 200_000, 100_000, 50_000]
+        assert res.level_bases == ref.level_bases and res.level_reads == ref.level_reads
+        assert (res.canon == ref.canon).all() and (res.pixels == ref.pixels).all()
+        expect = oracle_levels(buf, 7, 99, res.levels, res.nsites)
+        assert (res.canon == expect).all()
+    finally:
+        dist.destroy_process_group()

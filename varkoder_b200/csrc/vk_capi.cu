@@ -227,11 +227,14 @@ void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsign
         ++c->launches;
     }
     c->mark(EV_FOLD);
-    const uint32_t n_pad16 = n_pad < 512 ? 512 : n_pad;                 // at least one warp of 16-value threads
-    const size_t smem = (size_t)(n_pad16 + n_pad16 / 16) * sizeof(unsigned long long);     // one pad word per 16 (bank spread)
-    if (n_pad16 <= 16384) {
-        CU(cudaFuncSetAttribute(image_kernel_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        image_kernel_smem<<<levels, n_pad16 / kImageItems, smem, c->stream>>>(c->canon.p, m.lut.p, nk, n_pix, n_pad16, c->pixels.p);
+    if (n_pix <= 16384) {
+        // one cluster of 8 CTAs per level; slice = next power of two of a eighth of the pixels
+        uint32_t S = next_pow2((n_pix + vk::kImgCluster - 1) / vk::kImgCluster);
+        if (S < 64) S = 64;
+        const size_t smem = (size_t)vk::kImgCluster * S * sizeof(unsigned long long);
+        const unsigned threads = S / 2 > 1024 ? 1024 : S / 2;
+        CU(cudaFuncSetAttribute(image_kernel_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        image_kernel_cluster<<<dim3(vk::kImgCluster, levels), threads, smem, c->stream>>>(c->canon.p, m.lut.p, nk, n_pix, S, c->pixels.p);
         CU(cudaGetLastError());
         ++c->launches;
     } else {

@@ -11,9 +11,11 @@
 // The float64 route of the reference is exact for these dyadic rationals (values < 2^45), so the integer
 // restatement is bit-identical (tests/golden, oracle/image.py); no +-1 tolerance is needed.
 #pragma once
+#include <cooperative_groups.h>
 #include "vk_common.cuh"
 
 namespace vk {
+namespace cg = cooperative_groups;
 
 // canon[l][x] (lex index x) = sum over segments s >= l of fwd[s][i] + fwd[s][rc i], i = internal index of x.
 __global__ void __launch_bounds__(256)
@@ -44,89 +46,74 @@ __device__ __forceinline__ unsigned long long pixel_value(const unsigned long lo
 // n pixels, the digitize-against-quantiles of image.py:916-919 collapses to
 //     out(v) = min(255, floor(256 * (c(v) - 1) / (n - 1)))
 // (bins[i] <= v  <=>  (n-1) * i <= 256 * (c(v) - 1), because v itself is one of the sorted values; derivation in
-// DESIGN.md "K4", checked against the reference's PNGs in tests/golden).  So the kernel only needs c(v): sort the
-// n values once, then an upper bound per pixel.
+// DESIGN.md "K4", checked against the reference's PNGs in tests/golden).  So the kernel only needs c(v).
 //
-// One CTA per level, 16 values per thread: in-register bitonic network for the 16, then log2(n/16) merge-path
-// levels through shared memory (each thread finds its diagonal by binary search and merges 16 outputs serially).
-constexpr int kImageItems = 16;
-// shared-memory index of logical element i: one pad word per 16, so that threads owning consecutive 16-element
-// blocks (stride 17 x 8 B) do not all land on one bank (the unpadded layout was a 32-way conflict: 177 us -> see profiles)
-__device__ __forceinline__ uint32_t sidx(uint32_t i) { return i + (i >> 4); }
+// One thread-block CLUSTER of 8 CTAs per level (images up to 128 x 128): every CTA gathers and sorts one eighth of
+// the pixels in its own shared memory (keys = value << 16 | pixel index, bitonic network), the eight sorted slices
+// are exchanged through distributed shared memory, and each CTA ranks its own pixels with one upper-bound search
+// per slice: c(v) = sum of the eight positions.  9 levels x 8 CTAs keep 72 SMs busy instead of 9.
+constexpr int kImgCluster = 8;
+constexpr uint32_t kImgIdxBits = 16;
 
-__device__ __forceinline__ void cex(unsigned long long& a, unsigned long long& b, bool up)
+__global__ void __cluster_dims__(kImgCluster, 1, 1) __launch_bounds__(1024, 1)
+image_kernel_cluster(const unsigned long long* __restrict__ canon, const int32_t* __restrict__ lut, uint32_t nk,
+                     uint32_t n_pix, uint32_t S, uint8_t* __restrict__ pixels)
 {
-    const bool sw = (a > b) == up;
-    const unsigned long long lo = sw ? b : a, hi = sw ? a : b;
-    a = lo;
-    b = hi;
-}
+    extern __shared__ unsigned long long s_keys[];        // [kImgCluster][S]: slice r at offset r * S, in every CTA
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t rank = cluster.block_rank();
+    const uint32_t level = blockIdx.y;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    const unsigned long long* canon_l = canon + (size_t)level * nk;
+    unsigned long long* const own = s_keys + (size_t)rank * S;
 
-__global__ void __launch_bounds__(1024, 1)
-image_kernel_smem(const unsigned long long* __restrict__ canon, const int32_t* __restrict__ lut, uint32_t nk,
-                  uint32_t n_pix, uint32_t n_pad, uint8_t* __restrict__ pixels)
-{
-    extern __shared__ unsigned long long s_val[];        // n_pad values
-    const unsigned long long* canon_l = canon + (size_t)blockIdx.x * nk;
-    const uint32_t tid = threadIdx.x;                     // blockDim.x == n_pad / 16
-    const uint32_t base = tid * kImageItems;
-
-    unsigned long long v[kImageItems];
-#pragma unroll
-    for (int i = 0; i < kImageItems; ++i) v[i] = base + i < n_pix ? pixel_value(canon_l, lut, base + i) : ~0ull;
-
-    // ---- 16 values in registers: bitonic sorting network, ascending
-#pragma unroll
-    for (int size = 2; size <= kImageItems; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-            for (int i = 0; i < kImageItems; ++i) {
-                const int l = i ^ stride;
-                if (l > i) cex(v[i], v[l], (i & size) == 0);
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < kImageItems; ++i) s_val[sidx(base) + i] = v[i];
-
-    // ---- merge sorted runs pairwise: run = 16, 32, ..., n_pad / 2
-    for (uint32_t run = kImageItems; run < n_pad; run <<= 1) {
-        __syncthreads();
-        const uint32_t pair_base = base & ~(2 * run - 1);
-        const uint32_t A = pair_base, B = pair_base + run;      // logical offsets of the two runs
-        const uint32_t diag = base - pair_base;           // this thread emits merged outputs diag .. diag+15
-        uint32_t lo = diag > run ? diag - run : 0, hi = diag < run ? diag : run;
-        while (lo < hi) {                                 // merge path: first a with A[a] > B[diag-1-a]
-            const uint32_t mid = (lo + hi) >> 1;
-            if (s_val[sidx(A + mid)] <= s_val[sidx(B + diag - 1 - mid)]) lo = mid + 1; else hi = mid;
-        }
-        uint32_t a = lo, b = diag - lo;
-        unsigned long long ka = a < run ? s_val[sidx(A + a)] : ~0ull, kb = b < run ? s_val[sidx(B + b)] : ~0ull;
-#pragma unroll
-        for (int i = 0; i < kImageItems; ++i) {
-            const bool take_a = b >= run || (a < run && ka <= kb);
-            v[i] = take_a ? ka : kb;
-            if (take_a) { ++a; ka = a < run ? s_val[sidx(A + a)] : ~0ull; }
-            else { ++b; kb = b < run ? s_val[sidx(B + b)] : ~0ull; }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < kImageItems; ++i) s_val[sidx(base) + i] = v[i];
+    for (uint32_t i = tid; i < S; i += nthr) {
+        const uint32_t p = rank * S + i;
+        own[i] = p < n_pix ? (pixel_value(canon_l, lut, p) << kImgIdxBits) | p : ~0ull;
     }
     __syncthreads();
-
-    // ---- c(v) = upper bound over the n_pix real values (the padding sorts last), then the closed form
-    uint8_t* out = pixels + (size_t)blockIdx.x * n_pix;
-    for (uint32_t p = tid; p < n_pix; p += blockDim.x) {
-        const unsigned long long val = pixel_value(canon_l, lut, p);
-        uint32_t lo = 0, hi = n_pix;
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (s_val[sidx(mid)] <= val) lo = mid + 1; else hi = mid;
+    // ---- bitonic sort of the slice, ascending; comparators of stride < 32 stay inside one warp's 64 elements
+    for (uint32_t size = 2; size <= S; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = tid; t < (S >> 1); t += nthr) {
+                const uint32_t lo = 2 * t - (t & (stride - 1));
+                const uint32_t hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = own[lo], b = own[hi];
+                if ((a > b) == up) { own[lo] = b; own[hi] = a; }
+            }
+            if (stride > 16) __syncthreads(); else __syncwarp();
         }
-        const uint32_t g = n_pix > 1 ? (256u * (lo - 1)) / (n_pix - 1) : 0u;        // lo <= 2^14: fits 32 bits
-        out[p] = (uint8_t)(g > 255u ? 255u : g);
+        __syncthreads();
+    }
+    // ---- all-gather of the sorted slices over distributed shared memory
+    cluster.sync();
+    for (uint32_t r = 0; r < kImgCluster; ++r) {
+        if (r == rank) continue;
+        const unsigned long long* src = cluster.map_shared_rank(s_keys + (size_t)r * S, r);
+        unsigned long long* dst = s_keys + (size_t)r * S;
+        for (uint32_t i = tid; i < S; i += nthr) dst[i] = src[i];
+    }
+    cluster.sync();                                       // nobody leaves (or is overwritten) while peers still read
+    // ---- c(v) = sum over slices of the upper bound of v, then the closed form
+    uint8_t* out = pixels + (size_t)level * n_pix;
+    for (uint32_t e = tid; e < S; e += nthr) {
+        const unsigned long long key = own[e];
+        if (key == ~0ull) continue;
+        const unsigned long long vmax = key | ((1ull << kImgIdxBits) - 1);      // every key of the same value is <= this
+        uint32_t c = 0;
+#pragma unroll 1
+        for (uint32_t r = 0; r < kImgCluster; ++r) {
+            const unsigned long long* sl = s_keys + (size_t)r * S;
+            uint32_t lo = 0, hi = S;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (sl[mid] <= vmax) lo = mid + 1; else hi = mid;
+            }
+            c += lo;
+        }
+        const uint32_t g = n_pix > 1 ? (256u * (c - 1)) / (n_pix - 1) : 0u;     // c <= 2^14: fits 32 bits
+        out[(uint32_t)key & ((1u << kImgIdxBits) - 1)] = (uint8_t)(g > 255u ? 255u : g);
     }
 }
 
