@@ -147,6 +147,10 @@ int vk_last_timings(vk_ctx* ctx, float* ms8);
 /* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
 uint64_t vk_launch_count(vk_ctx* ctx);
 
+/* How often a step had to be repeated because a ladder segment received more reads than the region sized from its
+ * expected share (8 sigma + slack): always 0 in practice; tests force it with VK_TEST_TIGHT_BUCKETS=1. */
+uint64_t vk_bucket_retries(vk_ctx* ctx);
+
 /* Deterministic synthetic FASTQ (bench / tests): fills a DEVICE buffer.
  * Fixed read length L: record r occupies bytes [r*(2L+17), (r+1)*(2L+17)); returns bytes written in *n_out. */
 int vk_synth_fastq(vk_ctx* ctx, void* dev_bytes, uint64_t capacity, uint64_t n_bases, int read_len, uint64_t seed,

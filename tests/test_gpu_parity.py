@@ -314,3 +314,28 @@ def test_sharded_driver_with_real_engine_nccl(engine):
         assert (res.canon == expect).all()
     finally:
         dist.destroy_process_group()
+
+
+def test_bucket_overflow_retry_is_exact(monkeypatch):
+    """segment regions of the read table are sized from EXPECTED shares; when one overflows the step is repeated with
+    exact regions.  Forced here with undersized regions: same counts, same pixels, and the retry really happened."""
+    from varkoder_b200.engine import Engine
+    monkeypatch.setenv("VK_TEST_TIGHT_BUCKETS", "1")
+    eng = Engine(0)
+    try:
+        buf = synth.fixed(600_000, 150, seed=21).tobytes()
+        table = get_kmer_mapping(7, "varKode")
+        params = Params(k=7, min_bp=50_000, max_bp=None, seed=5)
+        res = eng.reads_to_images(buf, params, table, want_canon=True)
+        assert eng.bucket_retries() >= 1
+        expect = oracle_levels(buf, 7, 5, res.levels, res.nsites)
+        assert len(res.levels) == 5 and (res.canon == expect).all()
+        assert (res.pixels == oracle_images(expect, table.lut)).all()
+        # staged calls take the same path
+        eng.upload(buf)
+        eng.parse()
+        r2 = eng.count(params)
+        canon2, _ = eng.render(None, 7, len(r2.levels))
+        assert (canon2 == expect).all() and eng.bucket_retries() >= 2
+    finally:
+        eng.close()

@@ -60,6 +60,9 @@ struct Mapping {
     DevBuf<int32_t> lut;
 };
 
+constexpr size_t kPlanPad = 8192;
+static_assert(sizeof(vk::Plan) <= kPlanPad, "Plan must fit its slot of the outbox");
+
 enum { EV_START = 0, EV_UPLOAD, EV_PARSE, EV_BUCKET, EV_COUNT, EV_FOLD, EV_RENDER, EV_DONE, EV_N };
 
 }  // namespace
@@ -73,22 +76,29 @@ struct vk_ctx {
     uint64_t launches = 0;
     int count_threads = 1024, count_ctas_per_sm = 1;      // count-kernel launch shape (VK_COUNT_THREADS / VK_COUNT_CTAS)
 
-    vk::Plan* plan_d = nullptr;
-    vk::Plan* plan_h = nullptr;     // pinned
+    // "outbox": [Plan, padded to kPlanPad bytes][pixels of every level] contiguous on the device and mirrored in pinned
+    // host memory, so that the fused path reads everything back with ONE device-to-host copy
+    uint8_t* out_d = nullptr;
+    uint8_t* out_h = nullptr;       // pinned
+    size_t out_cap = 0;             // pixel bytes the outbox holds
+    vk::Plan* plan_d = nullptr;     // = out_d
+    vk::Plan* plan_h = nullptr;     // = out_h
+    uint8_t* pix_d() const { return out_d + kPlanPad; }
+    uint8_t* pix_h() const { return out_h + kPlanPad; }
 
     DevBuf<uint8_t> text_own;
     const uint8_t* text = nullptr;  // device
     uint64_t n_bytes = 0;
     bool have_text = false, parsed = false, counted = false;
+    bool exact_layout = false;      // segment regions sized for every read (set after a bucket overflow)
+    bool test_tight = false;        // VK_TEST_TIGHT_BUCKETS=1: undersized regions, exercises the retry (tests only)
+    uint64_t bucket_retries = 0;
     int counted_k = 0;
 
     DevBuf<uint64_t> tile_status, masks, starts, ends, sorted;      // tile_status = exclusive newline prefix per tile
     DevBuf<uint32_t> tile_count, warp_count;
     DevBuf<uint32_t> slabs;
     DevBuf<unsigned long long> seg_hist, canon, vals, bins;
-    DevBuf<uint8_t> pixels;
-    uint8_t* pix_h = nullptr;       // pinned staging for pixel read-back
-    size_t pix_h_cap = 0;
     Mapping maps[4];
 
     void mark(int e)
@@ -133,15 +143,30 @@ void enqueue_parse(vk_ctx* c, const vk_params* params, bool rescan = true)
     if (params) a.p = *params;
     a.n_bytes = n;
     a.cap_reads = cap;
+    a.cap_sorted = c->sorted.cap;
+    a.n_count_ctas = (uint32_t)(c->n_sms * c->count_ctas_per_sm);
+    a.exact_layout = c->exact_layout ? 1u : 0u;
+    a.test_tight = c->test_tight ? 1u : 0u;
     plan_kernel<<<1, 64, 0, c->stream>>>(c->text, c->starts.p, c->ends.p, a, c->plan_d);
     CU(cudaGetLastError());
     ++c->launches;
+}
+
+// entries the segment-sorted read table needs for n reads in n_levels segments (plan_kernel's layout rule)
+uint64_t sorted_need(uint64_t n_reads, uint64_t n_levels, bool exact)
+{
+    const uint64_t stride = (n_reads + vk::kUnitReads - 1) / vk::kUnitReads * vk::kUnitReads + vk::kUnitReads;
+    if (exact) return n_levels * stride;
+    uint64_t root = 1;
+    while (root * root < n_reads) root += root < 1024 ? 1 : root / 64 + 1;       // >= sqrt(n_reads)
+    return n_reads + n_levels * (8 * root + 1024 + 2 * vk::kUnitReads);
 }
 
 void ensure_tables_for(vk_ctx* c, uint64_t n_reads_hint)
 {
     c->starts.ensure(n_reads_hint);
     c->ends.ensure(n_reads_hint);
+    if (!c->exact_layout) c->sorted.ensure(sorted_need(n_reads_hint, vk::kMaxLevels, false));
 }
 
 // ---- K1b + K2 + K3 -----------------------------------------------------------------------------------
@@ -182,17 +207,12 @@ void enqueue_count(vk_ctx* c, const vk_params* p, unsigned long long* seg_hist, 
     using namespace vk;
     const int k = p->k;
     const uint32_t nk = 1u << (2 * k);
-    c->sorted.ensure(n_reads_bound + (uint64_t)kMaxLevels * kUnitReads);
     if (k <= 7) c->slabs.ensure((size_t)c->n_sms * c->count_ctas_per_sm * nk);
     const int bgrid = (int)std::min<uint64_t>((n_reads_bound + kBucketThreads - 1) / kBucketThreads + 1, (uint64_t)c->n_sms * 8);
-    bucket_count_kernel<<<c->n_sms, kBucketCountThreads, 0, c->stream>>>(c->starts.p, c->ends.p, k, p->seed, p->read_index_base, c->plan_d);
-    CU(cudaGetLastError());
-    bucket_layout_kernel<<<1, 32, 0, c->stream>>>(c->plan_d, (uint32_t)(c->n_sms * c->count_ctas_per_sm));
-    CU(cudaGetLastError());
     bucket_scatter_kernel<<<bgrid, kBucketThreads, 0, c->stream>>>(c->starts.p, c->ends.p, k, p->seed, p->read_index_base, 0,
                                                                   c->sorted.p, c->plan_d);
     CU(cudaGetLastError());
-    c->launches += 3;
+    ++c->launches;
     c->mark(EV_BUCKET);
     switch (k) {
     case 5: launch_count<5>(c, seg_hist, p->breaklength); break;
@@ -212,6 +232,8 @@ uint32_t next_pow2(uint32_t v)
     return p;
 }
 
+void ensure_outbox(vk_ctx* c, size_t n);
+
 // levels: number of levels to render (grid size); canon must hold levels * 4^k
 void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsigned long long* seg_hist)
 {
@@ -220,7 +242,7 @@ void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsign
     const uint32_t n_pix = (uint32_t)m.side * (uint32_t)m.side;
     const uint32_t n_pad = next_pow2(n_pix);
     c->canon.ensure((size_t)levels * nk);
-    c->pixels.ensure((size_t)levels * n_pix);
+    ensure_outbox(c, (size_t)levels * n_pix);
     if (seg_hist) {
         fold_kernel<<<(nk + 255) / 256, 256, 0, c->stream>>>(seg_hist, k, levels, c->canon.p);
         CU(cudaGetLastError());
@@ -234,7 +256,7 @@ void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsign
         const size_t smem = (size_t)vk::kImgCluster * S * sizeof(unsigned long long);
         const unsigned threads = S / 2 > 1024 ? 1024 : S / 2;
         CU(cudaFuncSetAttribute(image_kernel_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        image_kernel_cluster<<<dim3(vk::kImgCluster, levels), threads, smem, c->stream>>>(c->canon.p, m.lut.p, nk, n_pix, S, c->pixels.p);
+        image_kernel_cluster<<<dim3(vk::kImgCluster, levels), threads, smem, c->stream>>>(c->canon.p, m.lut.p, nk, n_pix, S, c->pix_d());
         CU(cudaGetLastError());
         ++c->launches;
     } else {
@@ -262,7 +284,7 @@ void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsign
         image_bins_kernel<<<levels, 256, 0, c->stream>>>(c->vals.p, n_pix, n_pad, c->bins.p);
         CU(cudaGetLastError());
         dim3 gd((n_pix + 255) / 256, levels);
-        image_digitize_kernel<<<gd, 256, 0, c->stream>>>(c->canon.p, m.lut.p, nk, n_pix, c->bins.p, c->pixels.p);
+        image_digitize_kernel<<<gd, 256, 0, c->stream>>>(c->canon.p, m.lut.p, nk, n_pix, c->bins.p, c->pix_d());
         CU(cudaGetLastError());
         c->launches += 2;
     }
@@ -299,13 +321,30 @@ void fetch_plan(vk_ctx* c)
     CU(cudaMemcpyAsync(c->plan_h, c->plan_d, sizeof(vk::Plan), cudaMemcpyDeviceToHost, c->stream));
 }
 
-void ensure_pix_h(vk_ctx* c, size_t n)
+// grow the outbox to hold n pixel bytes; the Plan travels with it (stream is idle or the copy is stream-ordered)
+void ensure_outbox(vk_ctx* c, size_t n)
 {
-    if (n <= c->pix_h_cap) return;
-    if (c->pix_h) CU(cudaFreeHost(c->pix_h));
-    c->pix_h = nullptr;
-    CU(cudaMallocHost(&c->pix_h, n));
-    c->pix_h_cap = n;
+    if (c->out_d && n <= c->out_cap) return;
+    const size_t want = n + n / 4 + (1u << 20);
+    uint8_t* nd = nullptr;
+    uint8_t* nh = nullptr;
+    CU(cudaMalloc(&nd, kPlanPad + want));
+    CU(cudaMallocHost(&nh, kPlanPad + want));
+    if (c->out_d) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemcpy(nd, c->out_d, kPlanPad, cudaMemcpyDeviceToDevice));
+        memcpy(nh, c->out_h, kPlanPad);
+        CU(cudaFree(c->out_d));
+        CU(cudaFreeHost(c->out_h));
+    } else {
+        CU(cudaMemset(nd, 0, kPlanPad));
+        memset(nh, 0, kPlanPad);
+    }
+    c->out_d = nd;
+    c->out_h = nh;
+    c->out_cap = want;
+    c->plan_d = reinterpret_cast<vk::Plan*>(nd);
+    c->plan_h = reinterpret_cast<vk::Plan*>(nh);
 }
 
 const Mapping& get_mapping(vk_ctx* c, int slot, int k)
@@ -350,12 +389,20 @@ int guarded(F&& f)
 template <typename F>
 void with_table_retry(vk_ctx* c, F&& body)
 {
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int attempt = 0; attempt < 3; ++attempt) {
         body();
         CU(cudaStreamSynchronize(c->stream));
-        if (!c->plan_h->table_overflow) return;
-        if (attempt == 1) throw ApiError{VK_ERANGE, "read table overflow after resize"};
-        ensure_tables_for(c, c->plan_h->n_reads + 16);          // exact size is known now
+        const bool t_over = c->plan_h->table_overflow != 0, b_over = c->plan_h->bucket_overflow != 0;
+        if (!t_over && !b_over) { c->exact_layout = false; return; }
+        if (attempt == 2) throw ApiError{VK_ERANGE, "read table overflow after resize"};
+        if (t_over) ensure_tables_for(c, c->plan_h->n_reads + 16);          // exact size is known now
+        else {
+            // a segment outgrew its expected-size region (or the table was too small for the layout): give every
+            // segment room for every read
+            c->exact_layout = true;
+            ++c->bucket_retries;
+            c->sorted.ensure(sorted_need(c->plan_h->n_reads, (uint64_t)std::max(c->plan_h->n_levels, 1), true));
+        }
     }
 }
 
@@ -382,14 +429,12 @@ int vk_ctx_create(int device, vk_ctx** out)
         c->n_sms = prop.multiProcessorCount;
         if (const char* e = getenv("VK_COUNT_THREADS")) c->count_threads = atoi(e);
         if (const char* e = getenv("VK_COUNT_CTAS")) c->count_ctas_per_sm = atoi(e);
+        if (const char* e = getenv("VK_TEST_TIGHT_BUCKETS")) c->test_tight = atoi(e) != 0;
         if (c->count_threads < 32 || c->count_threads > 1024 || c->count_threads % 32 || c->count_ctas_per_sm < 1 || c->count_ctas_per_sm > 3)
             throw ApiError{VK_EINVAL, "bad VK_COUNT_THREADS / VK_COUNT_CTAS"};
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (int i = 0; i < EV_N; ++i) CU(cudaEventCreate(&c->ev[i]));
-        CU(cudaMalloc(&c->plan_d, sizeof(vk::Plan)));
-        CU(cudaMemset(c->plan_d, 0, sizeof(vk::Plan)));
-        CU(cudaMallocHost(&c->plan_h, sizeof(vk::Plan)));
-        memset(c->plan_h, 0, sizeof(vk::Plan));
+        ensure_outbox(c, 0);
         *out = c;
     });
 }
@@ -412,11 +457,9 @@ int vk_ctx_destroy(vk_ctx* c)
     c->canon.release();
     c->vals.release();
     c->bins.release();
-    c->pixels.release();
     for (auto& m : c->maps) m.lut.release();
-    if (c->pix_h) cudaFreeHost(c->pix_h);
-    if (c->plan_h) cudaFreeHost(c->plan_h);
-    if (c->plan_d) cudaFree(c->plan_d);
+    if (c->out_h) cudaFreeHost(c->out_h);
+    if (c->out_d) cudaFree(c->out_d);
     for (int i = 0; i < EV_N; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -550,7 +593,7 @@ int vk_render(vk_ctx* c, int slot, int k, int n_levels, const uint64_t* seg_hist
         if (canon_host)
             CU(cudaMemcpyAsync(canon_host, c->canon.p, (size_t)n_levels * nk * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
         if (pixels_host)
-            CU(cudaMemcpyAsync(pixels_host, c->pixels.p, (size_t)n_levels * m->side * m->side, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaMemcpyAsync(pixels_host, c->pix_d(), (size_t)n_levels * m->side * m->side, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
     });
 }
@@ -567,7 +610,7 @@ int vk_render_counts(vk_ctx* c, int slot, int k, int n, const uint64_t* canon_ho
         c->canon.ensure((size_t)n * nk);
         CU(cudaMemcpyAsync(c->canon.p, canon_host, (size_t)n * nk * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
         enqueue_render(c, m, k, n, nullptr);      // canon is already in place: no fold
-        CU(cudaMemcpyAsync(pixels_host, c->pixels.p, (size_t)n * m.side * m.side, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(pixels_host, c->pix_d(), (size_t)n * m.side * m.side, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
     });
 }
@@ -588,7 +631,7 @@ int vk_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, int on_dev
         const size_t n_pix = (size_t)m.side * m.side;
         c->seg_hist.ensure((size_t)vk::kMaxLevels * nk);
         ensure_tables_for(c, reads_bound(n_bytes));
-        ensure_pix_h(c, (size_t)max_levels_out * n_pix);
+        ensure_outbox(c, (size_t)max_levels_out * n_pix);
         if (!on_device) {
             if (n_bytes >> 40) throw ApiError{VK_ERANGE, "buffers of 2^40 bytes or more are not supported"};
             c->text_own.ensure(n_bytes + 64);
@@ -608,8 +651,8 @@ int vk_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, int on_dev
             // the number of levels is only known on the device: render max_levels_out, rows beyond the ladder
             // come from all-zero segments and are ignored by the caller
             enqueue_render(c, m, k, max_levels_out, c->seg_hist.p);
-            CU(cudaMemcpyAsync(c->pix_h, c->pixels.p, (size_t)max_levels_out * n_pix, cudaMemcpyDeviceToHost, c->stream));
-            fetch_plan(c);
+            // Plan + pixels in one copy
+            CU(cudaMemcpyAsync(c->out_h, c->out_d, kPlanPad + (size_t)max_levels_out * n_pix, cudaMemcpyDeviceToHost, c->stream));
             c->mark(EV_DONE);
         });
         if (c->plan_h->long_reads) throw ApiError{VK_ERANGE, "a read is longer than 2^24-1 bases"};
@@ -620,11 +663,10 @@ int vk_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, int on_dev
         if (nl > max_levels_out) {
             // rare: more levels than the caller guessed; render the rest with a second pass
             enqueue_render(c, m, k, nl, c->seg_hist.p);
-            ensure_pix_h(c, (size_t)nl * n_pix);
-            CU(cudaMemcpyAsync(c->pix_h, c->pixels.p, (size_t)nl * n_pix, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaMemcpyAsync(c->pix_h(), c->pix_d(), (size_t)nl * n_pix, cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
         }
-        if (pixels_host && nl > 0) memcpy(pixels_host, c->pix_h, (size_t)nl * n_pix);
+        if (pixels_host && nl > 0) memcpy(pixels_host, c->pix_h(), (size_t)nl * n_pix);
         if (canon_host && nl > 0) {
             CU(cudaMemcpyAsync(canon_host, c->canon.p, (size_t)nl * nk * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
@@ -653,6 +695,7 @@ int vk_last_timings(vk_ctx* c, float* ms8)
 }
 
 uint64_t vk_launch_count(vk_ctx* c) { return c ? c->launches : 0; }
+uint64_t vk_bucket_retries(vk_ctx* c) { return c ? c->bucket_retries : 0; }
 
 int vk_synth_fastq(vk_ctx* c, void* dev_bytes, uint64_t capacity, uint64_t n_bases, int read_len, uint64_t seed,
                    uint64_t first_read, uint64_t* n_out)

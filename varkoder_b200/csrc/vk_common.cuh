@@ -33,12 +33,13 @@ struct Plan {
     // ---- bucket (K1b): segment s = reads in levels 0..s and not in s+1
     unsigned long long seg_reads[kMaxLevels];
     unsigned long long seg_bases[kMaxLevels];
-    unsigned long long seg_cursor[kMaxLevels];   // scatter cursors
+    unsigned long long seg_cursor[kMaxLevels];   // (unused)
     unsigned long long seg_next[kMaxLevels];     // dynamic unit counters of the count kernel
     uint64_t seg_begin[kMaxLevels + 1];          // offsets into the sorted entry array
     uint32_t seg_cta_begin[kMaxLevels + 1];      // CTA ranges of the count kernel
     uint32_t long_reads;                         // reads longer than 2^24-1 bases (unsupported)
-    uint32_t pad_;
+    uint32_t bucket_overflow;                    // a segment received more reads than its region holds (retry, exact layout)
+    uint64_t seg_cap[kMaxLevels];                // entries each segment's region of the sorted array can hold
 };
 
 // splitmix64 finaliser over (seed, global read index): the seeded per-read priority (DESIGN.md "Sub-sampling").

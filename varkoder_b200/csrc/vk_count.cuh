@@ -207,7 +207,8 @@ count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sort
     }
     if (seg < 0) return;
     const uint64_t* const seg_sorted = sorted + plan->seg_begin[seg];
-    const uint32_t seg_len = (uint32_t)plan->seg_reads[seg];            // reads of this segment (< 2^32)
+    // reads of this segment (< 2^32); never beyond the region (after a bucket overflow the step is repeated)
+    const uint32_t seg_len = (uint32_t)(plan->seg_reads[seg] < plan->seg_cap[seg] ? plan->seg_reads[seg] : plan->seg_cap[seg]);
     unsigned long long* const gh = SMEM ? nullptr : seg_hist + (size_t)seg * NK;
 
     const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(s_raw);

@@ -178,6 +178,10 @@ struct PlanArgs {
     vk_params p;
     uint64_t n_bytes;       // total bytes of the buffer
     uint64_t cap_reads;
+    uint64_t cap_sorted;    // entries the sorted array holds
+    uint32_t n_count_ctas;  // grid of the count kernel
+    uint32_t exact_layout;  // 1: every segment region holds all reads (retry after a bucket overflow)
+    uint32_t test_tight;    // tests only (VK_TEST_TIGHT_BUCKETS=1): regions of half the expected size, to force the retry
 };
 
 __device__ inline uint64_t div_2p64(uint64_t num, uint64_t den)
@@ -256,18 +260,84 @@ plan_kernel(const uint8_t* __restrict__ text, uint64_t* __restrict__ starts, uin
         s_nsites = nsites;
     }
     __syncthreads();
+    __shared__ double s_frac[kMaxLevels];            // share of the reads expected in segment l
     if (l < kMaxLevels) {
         const int nl = s_nl;
         const uint64_t nsites = s_nsites;
         const uint64_t bp = l < nl ? s_lv[l] : 0;
         const bool all = l < nl && (bp >= nsites || nsites == 0);
+        const uint64_t thr = l < nl ? (all ? kThrAll : div_2p64(bp, nsites)) : 0;
         plan->level_bp[l] = bp;
         plan->level_all[l] = all ? 1u : 0u;
-        plan->level_thr[l] = l < nl ? (all ? kThrAll : div_2p64(bp, nsites)) : 0;
+        plan->level_thr[l] = thr;
         plan->seg_reads[l] = 0;
         plan->seg_bases[l] = 0;
         plan->seg_cursor[l] = 0;
         plan->seg_next[l] = 0;
+        s_frac[l] = all ? 1.0 : (double)thr * 5.421010862427522e-20;      // thr / 2^64
+    }
+    __syncthreads();
+    if (l == 0) {
+        // ---- layout of the segment-sorted read table and of the count kernel's CTAs, from EXPECTED segment sizes:
+        // segment s holds the reads with thr[s+1] <= prio < thr[s], a binomial share of the n_reads reads.  A region
+        // gets its expectation + 8 sigma + slack (an overflow is detected by the scatter kernel and retried with
+        // exact_layout), so no counting pass over the read table is needed.
+        const int nl = s_nl;
+        const uint64_t n_reads = plan->n_reads;
+        const uint64_t stride = (n_reads + kUnitReads - 1) / kUnitReads * kUnitReads + kUnitReads;
+        uint64_t off = 0;
+        double w[kMaxLevels];
+        double wsum = 0.0;
+        for (int s = 0; s < kMaxLevels; ++s) {
+            double f = 0.0;
+            if (s < nl) f = s_frac[s] - (s + 1 < nl ? s_frac[s + 1] : 0.0);
+            if (f < 0.0) f = 0.0;
+            w[s] = f;
+            wsum += f;
+            uint64_t cap = 0;
+            if (s < nl) {
+                const double e = (double)n_reads * f;
+                cap = a.test_tight ? (uint64_t)(0.5 * e) + 1 : (uint64_t)(e + 8.0 * sqrt(e) + 1024.0);
+                cap = (cap + kUnitReads - 1) / kUnitReads * kUnitReads;
+                if (cap > stride || a.exact_layout) cap = stride;
+            }
+            plan->seg_begin[s] = off;
+            plan->seg_cap[s] = cap;
+            off += cap;
+        }
+        plan->seg_begin[kMaxLevels] = off;
+        plan->bucket_overflow = off > a.cap_sorted ? 1u : 0u;
+        // CTAs: one per segment, the rest in proportion to the expected bases, leftovers one by one to the segment
+        // with the most expected bases per CTA (minimises the slowest segment)
+        uint32_t n_cta[kMaxLevels];
+        uint32_t used = 0;
+        for (int s = 0; s < kMaxLevels; ++s) { n_cta[s] = (s < nl) ? 1u : 0u; used += n_cta[s]; }
+        if (used > a.n_count_ctas) {                   // more levels than CTAs (never with 148 SMs and <= 64 levels)
+            for (int s = 0; s < kMaxLevels; ++s) n_cta[s] = 0;
+            used = 0;
+        }
+        if (used > 0 && wsum > 0.0) {
+            const uint32_t spare = a.n_count_ctas - used;
+            uint32_t given = 0;
+            for (int s = 0; s < nl; ++s) {
+                const uint32_t e = (uint32_t)((double)spare * (w[s] / wsum));
+                n_cta[s] += e;
+                given += e;
+            }
+            for (uint32_t left = spare > given ? spare - given : 0; left > 0; --left) {
+                int best = -1;
+                double load = -1.0;
+                for (int s = 0; s < nl; ++s) {
+                    const double ld = w[s] / (double)n_cta[s];
+                    if (ld > load) { load = ld; best = s; }
+                }
+                if (best < 0) break;
+                ++n_cta[best];
+            }
+        }
+        uint32_t crun = 0;
+        for (int s = 0; s < kMaxLevels; ++s) { plan->seg_cta_begin[s] = crun; crun += n_cta[s]; }
+        plan->seg_cta_begin[kMaxLevels] = crun;
     }
 }
 

@@ -199,6 +199,9 @@ class Engine:
     def launch_count(self):
         return int(self._L.vk_launch_count(self._ctx))
 
+    def bucket_retries(self):
+        return int(self._L.vk_bucket_retries(self._ctx))
+
     def synth_fastq(self, dev_ptr, capacity, n_bases, read_len=150, seed=0, first_read=0):
         n = C.c_uint64()
         self._check(self._L.vk_synth_fastq(self._ctx, dev_ptr, capacity, n_bases, read_len, seed, first_read,
