@@ -24,33 +24,55 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
                       uint64_t read_index_base, uint64_t text_base, uint64_t* __restrict__ sorted,
                       Plan* __restrict__ plan)
 {
-    __shared__ uint32_t s_cnt[kMaxLevels], s_len[kMaxLevels];
+    constexpr uint32_t FULL = 0xffffffffu;
+    __shared__ uint32_t s_cnt[kMaxLevels], s_len[kMaxLevels], s_all[kMaxLevels];
     __shared__ unsigned long long s_base[kMaxLevels];
+    __shared__ uint64_t s_thr[kMaxLevels], s_begin[kMaxLevels], s_cap[kMaxLevels];
     __shared__ uint32_t s_long;
     const int nl = plan->n_levels;
     const uint64_t n_reads = plan->n_reads;
     const uint64_t per_iter = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31;
+    if (threadIdx.x < kMaxLevels) {
+        s_thr[threadIdx.x] = plan->level_thr[threadIdx.x];
+        s_all[threadIdx.x] = plan->level_all[threadIdx.x];
+        s_begin[threadIdx.x] = plan->seg_begin[threadIdx.x];
+        s_cap[threadIdx.x] = plan->seg_cap[threadIdx.x];
+    }
     if (threadIdx.x == 0) s_long = 0;
     for (uint64_t r0 = (uint64_t)blockIdx.x * blockDim.x; r0 < n_reads; r0 += per_iter) {
         if (threadIdx.x < kMaxLevels) { s_cnt[threadIdx.x] = 0; s_len[threadIdx.x] = 0; }
         __syncthreads();
         const uint64_t r = r0 + threadIdx.x;
         int seg = -1;
-        uint32_t rank = 0;
+        uint32_t len32 = 0;
         uint64_t entry = 0;
         if (r < n_reads) {
             const uint64_t st = starts[r];
             const uint64_t len = ends[r] - st;
             if (len > kEntryLenMask) atomicAdd(&s_long, 1u);
             else if (len >= (uint64_t)k) {
-                seg = levels_of(plan, nl, prio64(seed, read_index_base + r)) - 1;
+                const uint64_t h = prio64(seed, read_index_base + r);
+                int c = 0;
+                while (c < nl && (s_all[c] || h < s_thr[c])) ++c;
+                seg = c - 1;
                 if (seg >= 0) {
-                    rank = atomicAdd(&s_cnt[seg], 1u);
-                    atomicAdd(&s_len[seg], (uint32_t)len);               // 256 x 2^24 fits 32 bits
+                    len32 = (uint32_t)len;
                     entry = ((st - text_base) << kEntryLenBits) | len;
                 }
             }
         }
+        // warp-aggregated: one shared-memory atomic per (warp, segment) instead of one per read
+        const uint32_t peers = __match_any_sync(FULL, seg);
+        const uint32_t lsum = __reduce_add_sync(peers, len32);                   // 32 x 2^24 fits 32 bits
+        const int leader = __ffs(peers) - 1;
+        uint32_t wbase = 0;
+        if ((int)lane == leader && seg >= 0) {
+            wbase = atomicAdd(&s_cnt[seg], (uint32_t)__popc(peers));
+            atomicAdd(&s_len[seg], lsum);                                       // 256 x 2^24 fits 32 bits
+        }
+        wbase = __shfl_sync(peers, wbase, leader);
+        const uint32_t rank = wbase + __popc(peers & ((1u << lane) - 1u));
         __syncthreads();
         if (threadIdx.x < kMaxLevels && s_cnt[threadIdx.x]) {
             s_base[threadIdx.x] = atomicAdd(&plan->seg_reads[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
@@ -59,7 +81,7 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
         __syncthreads();
         if (seg >= 0) {
             const uint64_t slot = s_base[seg] + rank;
-            if (slot < plan->seg_cap[seg]) sorted[plan->seg_begin[seg] + slot] = entry;
+            if (slot < s_cap[seg]) sorted[s_begin[seg] + slot] = entry;
             else plan->bucket_overflow = 1u;
         }
         __syncthreads();

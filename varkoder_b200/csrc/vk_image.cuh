@@ -86,32 +86,39 @@ image_kernel_cluster(const unsigned long long* __restrict__ canon, const int32_t
         }
         __syncthreads();
     }
-    // ---- all-gather of the sorted slices over distributed shared memory
+    // ---- all-gather of the sorted slices over distributed shared memory (all remote loads of a thread in flight at once)
     cluster.sync();
-    for (uint32_t r = 0; r < kImgCluster; ++r) {
-        if (r == rank) continue;
-        const unsigned long long* src = cluster.map_shared_rank(s_keys + (size_t)r * S, r);
-        unsigned long long* dst = s_keys + (size_t)r * S;
-        for (uint32_t i = tid; i < S; i += nthr) dst[i] = src[i];
+    for (uint32_t i = tid; i < S; i += nthr) {
+        unsigned long long v[kImgCluster];
+#pragma unroll
+        for (uint32_t r = 0; r < kImgCluster; ++r) {
+            const unsigned long long* src = cluster.map_shared_rank(s_keys + (size_t)r * S, r);
+            v[r] = src[i];
+        }
+#pragma unroll
+        for (uint32_t r = 0; r < kImgCluster; ++r)
+            if (r != rank) s_keys[(size_t)r * S + i] = v[r];
     }
     cluster.sync();                                       // nobody leaves (or is overwritten) while peers still read
-    // ---- c(v) = sum over slices of the upper bound of v, then the closed form
+    // ---- c(v) = sum over slices of the upper bound of v, then the closed form.  The eight searches of an element
+    // advance in lock-step (S is a power of two: log2 S rounds of eight independent shared-memory loads).
     uint8_t* out = pixels + (size_t)level * n_pix;
     for (uint32_t e = tid; e < S; e += nthr) {
         const unsigned long long key = own[e];
         if (key == ~0ull) continue;
         const unsigned long long vmax = key | ((1ull << kImgIdxBits) - 1);      // every key of the same value is <= this
-        uint32_t c = 0;
-#pragma unroll 1
-        for (uint32_t r = 0; r < kImgCluster; ++r) {
-            const unsigned long long* sl = s_keys + (size_t)r * S;
-            uint32_t lo = 0, hi = S;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (sl[mid] <= vmax) lo = mid + 1; else hi = mid;
-            }
-            c += lo;
+        uint32_t pos[kImgCluster];
+#pragma unroll
+        for (uint32_t r = 0; r < kImgCluster; ++r) pos[r] = 0;
+        for (uint32_t step = S >> 1; step > 0; step >>= 1) {
+#pragma unroll
+            for (uint32_t r = 0; r < kImgCluster; ++r)
+                if (s_keys[(size_t)r * S + pos[r] + step - 1] <= vmax) pos[r] += step;
         }
+        uint32_t c = 0;
+#pragma unroll
+        for (uint32_t r = 0; r < kImgCluster; ++r)             // pos = # of the first S-1 elements <= vmax; the last one:
+            c += pos[r] + (s_keys[(size_t)r * S + pos[r]] <= vmax ? 1u : 0u);
         const uint32_t g = n_pix > 1 ? (256u * (c - 1)) / (n_pix - 1) : 0u;     // c <= 2^14: fits 32 bits
         out[(uint32_t)key & ((1u << kImgIdxBits) - 1)] = (uint8_t)(g > 255u ? 255u : g);
     }

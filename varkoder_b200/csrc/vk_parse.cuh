@@ -130,10 +130,30 @@ parse_emit_kernel(const uint64_t* __restrict__ masks, const uint64_t* __restrict
     const uint64_t wstride = (uint64_t)gridDim.x * (blockDim.x >> 5);
     uint64_t sum_s = 0, sum_e = 0;
     uint32_t overflow = 0;
-    for (uint64_t g = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < n_wt; g += wstride) {
+    // the loads of the next warp-tile are issued before the current one is decoded (a warp walks ~5 tiles; without
+    // this every tile exposed a full L2 round trip: profiles/r01b_ncu_full.txt)
+    uint64_t g = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint64_t m_nx = 0, pref_nx = 0;
+    uint32_t wc_nx = 0;
+    if (g < n_wt) {
         const uint32_t tile = (uint32_t)(g / kParseWarps), wit = (uint32_t)(g % kParseWarps);
-        uint64_t m = masks[g * 32 + lane];
-        const uint32_t wc = lane < wit ? warp_count[(uint64_t)tile * kParseWarps + lane] : 0u;
+        m_nx = masks[g * 32 + lane];
+        wc_nx = lane < wit ? warp_count[(uint64_t)tile * kParseWarps + lane] : 0u;
+        pref_nx = tile_prefix[tile];
+    }
+    for (; g < n_wt; g += wstride) {
+        uint64_t m = m_nx;
+        const uint32_t wc = wc_nx;
+        const uint64_t pref = pref_nx;
+        {
+            const uint64_t gn = g + wstride;
+            if (gn < n_wt) {
+                const uint32_t tile = (uint32_t)(gn / kParseWarps), wit = (uint32_t)(gn % kParseWarps);
+                m_nx = masks[gn * 32 + lane];
+                wc_nx = lane < wit ? warp_count[(uint64_t)tile * kParseWarps + lane] : 0u;
+                pref_nx = tile_prefix[tile];
+            }
+        }
         const uint32_t woff = __reduce_add_sync(0xffffffffu, wc);
         const uint32_t cnt = __popcll(m);
         uint32_t incl = cnt;
@@ -142,7 +162,7 @@ parse_emit_kernel(const uint64_t* __restrict__ masks, const uint64_t* __restrict
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= (uint32_t)d) incl += t;
         }
-        uint64_t line = tile_prefix[tile] + woff + (incl - cnt);
+        uint64_t line = pref + woff + (incl - cnt);
         const uint64_t pos0 = byte_base + g * 2048 + (uint64_t)lane * 64;
         while (m) {
             const int j = __ffsll((long long)m) - 1;
@@ -277,67 +297,80 @@ plan_kernel(const uint8_t* __restrict__ text, uint64_t* __restrict__ starts, uin
         s_frac[l] = all ? 1.0 : (double)thr * 5.421010862427522e-20;      // thr / 2^64
     }
     __syncthreads();
-    if (l == 0) {
-        // ---- layout of the segment-sorted read table and of the count kernel's CTAs, from EXPECTED segment sizes:
-        // segment s holds the reads with thr[s+1] <= prio < thr[s], a binomial share of the n_reads reads.  A region
-        // gets its expectation + 8 sigma + slack (an overflow is detected by the scatter kernel and retried with
-        // exact_layout), so no counting pass over the read table is needed.
+    // ---- layout of the segment-sorted read table and of the count kernel's CTAs, from EXPECTED segment sizes:
+    // segment s holds the reads with thr[s+1] <= prio < thr[s], a binomial share of the n_reads reads.  A region
+    // gets its expectation + 8 sigma + slack (an overflow is detected by the scatter kernel and retried with
+    // exact_layout), so no counting pass over the read table is needed.  Thread s owns segment s.
+    __shared__ double s_w[kMaxLevels], s_rem[kMaxLevels];
+    __shared__ uint64_t s_cap[kMaxLevels];
+    __shared__ uint32_t s_ncta[kMaxLevels];
+    __shared__ double s_wsum;
+    __shared__ uint32_t s_given;
+    {
         const int nl = s_nl;
         const uint64_t n_reads = plan->n_reads;
         const uint64_t stride = (n_reads + kUnitReads - 1) / kUnitReads * kUnitReads + kUnitReads;
-        uint64_t off = 0;
-        double w[kMaxLevels];
-        double wsum = 0.0;
-        for (int s = 0; s < kMaxLevels; ++s) {
-            double f = 0.0;
-            if (s < nl) f = s_frac[s] - (s + 1 < nl ? s_frac[s + 1] : 0.0);
-            if (f < 0.0) f = 0.0;
-            w[s] = f;
-            wsum += f;
-            uint64_t cap = 0;
-            if (s < nl) {
-                const double e = (double)n_reads * f;
-                cap = a.test_tight ? (uint64_t)(0.5 * e) + 1 : (uint64_t)(e + 8.0 * sqrt(e) + 1024.0);
-                cap = (cap + kUnitReads - 1) / kUnitReads * kUnitReads;
-                if (cap > stride || a.exact_layout) cap = stride;
-            }
-            plan->seg_begin[s] = off;
-            plan->seg_cap[s] = cap;
-            off += cap;
+        double f = 0.0;
+        if (l < nl) f = s_frac[l] - (l + 1 < nl ? s_frac[l + 1] : 0.0);
+        if (f < 0.0) f = 0.0;
+        uint64_t cap = 0;
+        if (l < nl) {
+            const double e = (double)n_reads * f;
+            cap = a.test_tight ? (uint64_t)(0.5 * e) + 1 : (uint64_t)(e + 8.0 * sqrt(e) + 1024.0);
+            cap = (cap + kUnitReads - 1) / kUnitReads * kUnitReads;
+            if (cap > stride || a.exact_layout) cap = stride;
         }
-        plan->seg_begin[kMaxLevels] = off;
-        plan->bucket_overflow = off > a.cap_sorted ? 1u : 0u;
-        // CTAs: one per segment, the rest in proportion to the expected bases, leftovers one by one to the segment
-        // with the most expected bases per CTA (minimises the slowest segment)
-        uint32_t n_cta[kMaxLevels];
-        uint32_t used = 0;
-        for (int s = 0; s < kMaxLevels; ++s) { n_cta[s] = (s < nl) ? 1u : 0u; used += n_cta[s]; }
-        if (used > a.n_count_ctas) {                   // more levels than CTAs (never with 148 SMs and <= 64 levels)
-            for (int s = 0; s < kMaxLevels; ++s) n_cta[s] = 0;
-            used = 0;
-        }
-        if (used > 0 && wsum > 0.0) {
-            const uint32_t spare = a.n_count_ctas - used;
-            uint32_t given = 0;
-            for (int s = 0; s < nl; ++s) {
-                const uint32_t e = (uint32_t)((double)spare * (w[s] / wsum));
-                n_cta[s] += e;
-                given += e;
+        s_w[l] = f;
+        s_cap[l] = cap;
+        plan->seg_cap[l] = cap;
+        __syncthreads();
+        if (l == 0) {
+            double wsum = 0.0;
+            uint64_t off = 0;
+            for (int s = 0; s < kMaxLevels; ++s) {
+                wsum += s_w[s];
+                plan->seg_begin[s] = off;
+                off += s_cap[s];
             }
-            for (uint32_t left = spare > given ? spare - given : 0; left > 0; --left) {
-                int best = -1;
-                double load = -1.0;
-                for (int s = 0; s < nl; ++s) {
-                    const double ld = w[s] / (double)n_cta[s];
-                    if (ld > load) { load = ld; best = s; }
-                }
-                if (best < 0) break;
-                ++n_cta[best];
-            }
+            plan->seg_begin[kMaxLevels] = off;
+            plan->bucket_overflow = off > a.cap_sorted ? 1u : 0u;
+            s_wsum = wsum;
         }
-        uint32_t crun = 0;
-        for (int s = 0; s < kMaxLevels; ++s) { plan->seg_cta_begin[s] = crun; crun += n_cta[s]; }
-        plan->seg_cta_begin[kMaxLevels] = crun;
+        __syncthreads();
+        // CTAs: one per segment, the rest in proportion to the expected bases (largest remainders get the leftovers)
+        const bool enough = (uint32_t)nl <= a.n_count_ctas;
+        const uint32_t spare = enough ? a.n_count_ctas - (uint32_t)nl : 0u;
+        uint32_t mine = (l < nl && enough) ? 1u : 0u;
+        double rem = -1.0;
+        if (l < nl && enough && s_wsum > 0.0) {
+            const double share = (double)spare * (f / s_wsum);
+            const uint32_t fl = (uint32_t)share;
+            mine += fl;
+            rem = share - (double)fl;
+        }
+        s_rem[l] = rem;
+        s_ncta[l] = mine;
+        __syncthreads();
+        if (l == 0) {
+            uint32_t g = 0;
+            for (int s = 0; s < kMaxLevels; ++s) g += s_ncta[s];
+            s_given = g;
+        }
+        __syncthreads();
+        if (l < nl && enough && s_wsum > 0.0) {
+            const uint32_t left = a.n_count_ctas > s_given ? a.n_count_ctas - s_given : 0u;     // < nl
+            uint32_t rank = 0;
+            for (int t = 0; t < nl; ++t)
+                if (s_rem[t] > rem || (s_rem[t] == rem && t < l)) ++rank;
+            if (rank < left) ++mine;
+        }
+        s_ncta[l] = mine;
+        __syncthreads();
+        if (l == 0) {
+            uint32_t crun = 0;
+            for (int s = 0; s < kMaxLevels; ++s) { plan->seg_cta_begin[s] = crun; crun += s_ncta[s]; }
+            plan->seg_cta_begin[kMaxLevels] = crun;
+        }
     }
 }
 
