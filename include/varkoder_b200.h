@@ -144,6 +144,11 @@ int vk_reads_to_images(vk_ctx* ctx, const void* text, uint64_t n_bytes, int on_d
  * [5] render, [6] read-back (D2H), [7] total. */
 int vk_last_timings(vk_ctx* ctx, float* ms8);
 
+/* on (default): CUDA events are recorded between the kernel groups so that vk_last_timings can split a step.  An event
+ * between two kernels is a full stream dependency and defeats programmatic dependent launch across it; off keeps only
+ * the first and last event ([7] total; the other entries read 0). */
+int vk_set_fine_timing(vk_ctx* ctx, int on);
+
 /* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
 uint64_t vk_launch_count(vk_ctx* ctx);
 

@@ -339,3 +339,56 @@ def test_bucket_overflow_retry_is_exact(monkeypatch):
         assert (canon2 == expect).all() and eng.bucket_retries() >= 2
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("k", [7, 8])
+def test_low_complexity_flood_16bit_bins(monkeypatch, k):
+    """k = 8 (default) and k = 7 in pair mode (VK_COUNT_PAIRS=1) count in 16-bit shared-memory bins; floods of one k-mer
+    (poly-A, poly-G, dinucleotide repeats) push bins past 2^16 many times per CTA and must come out exact
+    (rendezvous + fold, vk_count.cuh)."""
+    from varkoder_b200.engine import Engine
+    monkeypatch.setenv("VK_COUNT_PAIRS", "1")
+    engine = Engine(0)
+    rng = np.random.default_rng(900 + k)
+    reads = (["A" * 150] * 6000 + ["G" * 151] * 5000 + ["AC" * 75] * 3000 + ["ACGTN" * 30] * 500
+             + rand_reads(rng, 3000, 0, 200, p_n=0.01) + ["T" * 1200] * 50)
+    order = rng.permutation(len(reads))
+    buf = fastq([reads[i] for i in order])
+    _, res, canon, _ = gpu_counts(engine, buf, Params(k=k, min_bp=0, max_bp=None, is_query=True))
+    expect = dsk.canonical_counts(buf, k)
+    engine.close()
+    assert int(expect.max()) > 500_000                       # far beyond a 16-bit bin
+    assert (canon[0] == expect).all()
+
+
+def test_pair_counting_ladder_exact(monkeypatch):
+    """k = 7 pair mode over a whole ladder (several segments, so several CTAs and slabs per level)."""
+    from varkoder_b200.engine import Engine
+    monkeypatch.setenv("VK_COUNT_PAIRS", "1")
+    eng = Engine(0)
+    try:
+        buf = synth.fixed(900_000, 150, seed=31).tobytes()
+        table = get_kmer_mapping(7, "cgr")
+        res = eng.reads_to_images(buf, Params(k=7, min_bp=50_000, max_bp=None, seed=11), table, want_canon=True)
+        expect = oracle_levels(buf, 7, 11, res.levels, res.nsites)
+        assert len(res.levels) >= 5 and (res.canon == expect).all()
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("k", [7, 8])
+def test_u32_and_global_count_kernels_still_exact(monkeypatch, k):
+    """VK_COUNT16=0 selects the global-atomics kernel for k = 8 (k = 7 is the u32 shared-memory kernel either way)."""
+    from varkoder_b200.engine import Engine
+    monkeypatch.setenv("VK_COUNT16", "0")
+    eng = Engine(0)
+    try:
+        rng = np.random.default_rng(77 + k)
+        buf = fastq(rand_reads(rng, 4000, 0, 260, p_n=0.005) + ["ACGT" * 300, "G" * 90])
+        eng.upload(buf)
+        eng.parse()
+        res = eng.count(Params(k=k, min_bp=0, max_bp=None, is_query=True))
+        canon, _ = eng.render(None, k, len(res.levels))
+        assert (canon[0] == dsk.canonical_counts(buf, k)).all()
+    finally:
+        eng.close()

@@ -17,7 +17,7 @@ VK_LADDER_LESS_THAN_MIN = 1
 SYMBOLS = [
     "vk_abi_version", "vk_last_error", "vk_ctx_create", "vk_ctx_destroy", "vk_set_mapping", "vk_upload",
     "vk_attach", "vk_parse", "vk_count", "vk_render", "vk_render_counts", "vk_reads_to_images",
-    "vk_last_timings", "vk_launch_count", "vk_bucket_retries", "vk_synth_fastq",
+    "vk_last_timings", "vk_set_fine_timing", "vk_launch_count", "vk_bucket_retries", "vk_synth_fastq",
 ]
 
 
@@ -70,6 +70,7 @@ def load():
     L.vk_reads_to_images.argtypes = [vp, vp, C.c_uint64, C.c_int, C.POINTER(VkParams), C.c_int, C.c_int,
                                      C.POINTER(VkResult), vp, vp]
     L.vk_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
+    L.vk_set_fine_timing.argtypes = [vp, C.c_int]
     L.vk_launch_count.argtypes = [vp]
     L.vk_launch_count.restype = C.c_uint64
     L.vk_bucket_retries.argtypes = [vp]

@@ -24,6 +24,7 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
                       uint64_t read_index_base, uint64_t text_base, uint64_t* __restrict__ sorted,
                       Plan* __restrict__ plan)
 {
+    pdl_wait();
     constexpr uint32_t FULL = 0xffffffffu;
     __shared__ uint32_t s_cnt[kMaxLevels], s_len[kMaxLevels], s_all[kMaxLevels];
     __shared__ unsigned long long s_base[kMaxLevels];

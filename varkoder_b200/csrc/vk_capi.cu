@@ -91,6 +91,10 @@ struct vk_ctx {
     uint64_t n_bytes = 0;
     bool have_text = false, parsed = false, counted = false;
     bool exact_layout = false;      // segment regions sized for every read (set after a bucket overflow)
+    bool use_count16 = true;        // VK_COUNT16=0: k = 8 with global atomics instead of 16-bit shared-memory bins
+    bool use_pairs = false;         // VK_COUNT_PAIRS=1: k = 7 through 8-mer pairs in 16-bit bins (exact; halves the
+                                    // shared-memory traffic but costs more instructions: 168 vs 143 us, profiles/r01_notes.md)
+    bool use_pdl = true;            // VK_PDL=0 disables programmatic dependent launch
     bool test_tight = false;        // VK_TEST_TIGHT_BUCKETS=1: undersized regions, exercises the retry (tests only)
     uint64_t bucket_retries = 0;
     int counted_k = 0;
@@ -101,8 +105,10 @@ struct vk_ctx {
     DevBuf<unsigned long long> seg_hist, canon, vals, bins;
     Mapping maps[4];
 
+    bool fine_timing = true;        // vk_set_fine_timing: events between the kernel groups (they serialise the stream)
     void mark(int e)
     {
+        if (!fine_timing && e != EV_START && e != EV_DONE) { ev_valid[e] = false; return; }
         CU(cudaEventRecord(ev[e], stream));
         ev_valid[e] = true;
     }
@@ -111,6 +117,26 @@ struct vk_ctx {
 namespace {
 
 void set_device(vk_ctx* c) { CU(cudaSetDevice(c->device)); }
+
+// Every kernel of the path starts with griddepcontrol.wait (vk::pdl_wait) and is launched with programmatic stream
+// serialisation: the next kernel's CTAs are scheduled while the previous kernel drains, so launch latency and kernel
+// prologues overlap the tail of their predecessor (a dozen dependent launches per sample).  VK_PDL=0 turns it off.
+template <typename... KArgs, typename... Args>
+void launch(vk_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = c->use_pdl ? 1 : 0;
+    CU(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 
 // ---- K1: framing -------------------------------------------------------------------------------------
 void enqueue_parse(vk_ctx* c, const vk_params* params, bool rescan = true)
@@ -127,13 +153,13 @@ void enqueue_parse(vk_ctx* c, const vk_params* params, bool rescan = true)
         c->warp_count.ensure((size_t)n_tiles * kParseWarps);
         CU(cudaMemsetAsync(c->tile_count.p, 0, sizeof(uint32_t) * n_tiles, c->stream));
         const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)c->n_sms * 16);
-        parse_mask_kernel<<<grid, kParseThreads, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->text), n, n_tiles,
+        launch(c, parse_mask_kernel, dim3(grid), dim3(kParseThreads), 0, reinterpret_cast<const uint4*>(c->text), n, n_tiles,
                                                                  c->masks.p, c->tile_count.p, c->warp_count.p);
         CU(cudaGetLastError());
-        parse_scan_kernel<<<1, 1024, 0, c->stream>>>(c->tile_count.p, n_tiles, c->tile_status.p, c->plan_d);
+        launch(c, parse_scan_kernel, dim3(1), dim3(1024), 0, c->tile_count.p, n_tiles, c->tile_status.p, c->plan_d);
         CU(cudaGetLastError());
         const int egrid = (int)std::min<uint64_t>(((uint64_t)n_tiles * kParseWarps + 7) / 8, (uint64_t)c->n_sms * 32);
-        parse_emit_kernel<<<egrid, 256, 0, c->stream>>>(c->masks.p, c->tile_status.p, c->warp_count.p, n_tiles, 0,
+        launch(c, parse_emit_kernel, dim3(egrid), dim3(256), 0, c->masks.p, c->tile_status.p, c->warp_count.p, n_tiles, 0,
                                                         c->starts.p, c->ends.p, cap, c->plan_d);
         CU(cudaGetLastError());
         c->launches += 3;
@@ -147,7 +173,7 @@ void enqueue_parse(vk_ctx* c, const vk_params* params, bool rescan = true)
     a.n_count_ctas = (uint32_t)(c->n_sms * c->count_ctas_per_sm);
     a.exact_layout = c->exact_layout ? 1u : 0u;
     a.test_tight = c->test_tight ? 1u : 0u;
-    plan_kernel<<<1, 64, 0, c->stream>>>(c->text, c->starts.p, c->ends.p, a, c->plan_d);
+    launch(c, plan_kernel, dim3(1), dim3(64), 0, c->text, c->starts.p, c->ends.p, a, c->plan_d);
     CU(cudaGetLastError());
     ++c->launches;
 }
@@ -175,28 +201,38 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist, int breaklen)
 {
     using namespace vk;
     constexpr uint32_t NK = 1u << (2 * K);
-    if (K <= 7) {
-        // the histogram sits at a 64 KiB-aligned shared address (vk_count.cuh step16): up to 64 KiB of padding in front
+    const dim3 grid(c->n_sms * c->count_ctas_per_sm), block(c->count_threads);
+    const uint64_t total = (uint64_t)kMaxLevels * NK;
+    if constexpr (K == 7 || K == 8) {
+        if (K == 8 ? c->use_count16 : c->use_pairs) {
+            // 16-bit bins in shared memory: k = 8 directly, k = 7 through pairs (vk_count.cuh)
+            const size_t smem = (size_t)(32768 + (K == 7 ? 16384 : 0) + 32) * sizeof(uint32_t);
+            CU(cudaFuncSetAttribute(count16_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            launch(c, count16_kernel<K>, grid, block, smem, reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d,
+                   c->slabs.p, breaklen);
+            ++c->launches;
+            c->mark(EV_COUNT);
+            launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist);
+            ++c->launches;
+            return;
+        }
+    }
+    if constexpr (K <= 7) {
+        // the histogram sits at a 64 KiB-aligned shared address (vk_count.cuh): up to 64 KiB of padding in front
         const size_t smem = 0x10000 + (size_t)(NK + 32) * sizeof(uint32_t);
-        CU(cudaFuncSetAttribute(count_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        count_kernel<K, true><<<c->n_sms * c->count_ctas_per_sm, c->count_threads, smem, c->stream>>>(
-            reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d, c->slabs.p, seg_hist, breaklen);
-        CU(cudaGetLastError());
+        CU(cudaFuncSetAttribute(count_kernel<K, kSmem32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        launch(c, (count_kernel<K, kSmem32>), grid, block, smem, reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d,
+               c->slabs.p, seg_hist, breaklen);
         ++c->launches;
         c->mark(EV_COUNT);
-        const uint64_t total = (uint64_t)kMaxLevels * NK;
-        reduce_slabs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->slabs.p, c->plan_d, NK, seg_hist);
-        CU(cudaGetLastError());
+        launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist);
         ++c->launches;
     } else {
-        const uint64_t total = (uint64_t)kMaxLevels * NK;
-        zero_u64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(seg_hist, total);
-        CU(cudaGetLastError());
+        launch(c, zero_u64_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, seg_hist, total);
         ++c->launches;
         c->mark(EV_BUCKET);
-        count_kernel<K, false><<<c->n_sms * c->count_ctas_per_sm, c->count_threads, 0, c->stream>>>(
-            reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d, c->slabs.p, seg_hist, breaklen);
-        CU(cudaGetLastError());
+        launch(c, (count_kernel<K, kGlobal>), grid, block, 0, reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d,
+               c->slabs.p, seg_hist, breaklen);
         ++c->launches;
         c->mark(EV_COUNT);
     }
@@ -207,9 +243,9 @@ void enqueue_count(vk_ctx* c, const vk_params* p, unsigned long long* seg_hist, 
     using namespace vk;
     const int k = p->k;
     const uint32_t nk = 1u << (2 * k);
-    if (k <= 7) c->slabs.ensure((size_t)c->n_sms * c->count_ctas_per_sm * nk);
+    if (k <= 7 || (k == 8 && c->use_count16)) c->slabs.ensure((size_t)c->n_sms * c->count_ctas_per_sm * nk);
     const int bgrid = (int)std::min<uint64_t>((n_reads_bound + kBucketThreads - 1) / kBucketThreads + 1, (uint64_t)c->n_sms * 8);
-    bucket_scatter_kernel<<<bgrid, kBucketThreads, 0, c->stream>>>(c->starts.p, c->ends.p, k, p->seed, p->read_index_base, 0,
+    launch(c, bucket_scatter_kernel, dim3(bgrid), dim3(kBucketThreads), 0, c->starts.p, c->ends.p, k, p->seed, p->read_index_base, 0,
                                                                   c->sorted.p, c->plan_d);
     CU(cudaGetLastError());
     ++c->launches;
@@ -244,7 +280,7 @@ void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsign
     c->canon.ensure((size_t)levels * nk);
     ensure_outbox(c, (size_t)levels * n_pix);
     if (seg_hist) {
-        fold_kernel<<<(nk + 255) / 256, 256, 0, c->stream>>>(seg_hist, k, levels, c->canon.p);
+        launch(c, fold_kernel, dim3((nk + 255) / 256), dim3(256), 0, seg_hist, k, levels, c->canon.p);
         CU(cudaGetLastError());
         ++c->launches;
     }
@@ -256,35 +292,35 @@ void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsign
         const size_t smem = (size_t)vk::kImgCluster * S * sizeof(unsigned long long);
         const unsigned threads = S / 2 > 1024 ? 1024 : S / 2;
         CU(cudaFuncSetAttribute(image_kernel_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        image_kernel_cluster<<<dim3(vk::kImgCluster, levels), threads, smem, c->stream>>>(c->canon.p, m.lut.p, nk, n_pix, S, c->pix_d());
+        launch(c, image_kernel_cluster, dim3(vk::kImgCluster, levels), dim3(threads), smem, c->canon.p, m.lut.p, nk, n_pix, S, c->pix_d());
         CU(cudaGetLastError());
         ++c->launches;
     } else {
         c->vals.ensure((size_t)levels * n_pad);
         c->bins.ensure((size_t)levels * 256);
         dim3 g1((n_pad + 255) / 256, levels);
-        image_gather_kernel<<<g1, 256, 0, c->stream>>>(c->canon.p, m.lut.p, nk, n_pix, n_pad, c->vals.p);
+        launch(c, image_gather_kernel, dim3(g1), dim3(256), 0, c->canon.p, m.lut.p, nk, n_pix, n_pad, c->vals.p);
         CU(cudaGetLastError());
         ++c->launches;
         dim3 gt(n_pad / kSortTile, levels);
-        bitonic_tile_kernel<<<gt, 1024, 0, c->stream>>>(c->vals.p, n_pad, 2, kSortTile, kSortTile / 2);
+        launch(c, bitonic_tile_kernel, dim3(gt), dim3(1024), 0, c->vals.p, n_pad, 2, kSortTile, kSortTile / 2);
         CU(cudaGetLastError());
         ++c->launches;
         for (uint32_t size = 2 * kSortTile; size <= n_pad; size <<= 1) {
             for (uint32_t stride = size >> 1; stride >= kSortTile; stride >>= 1) {
                 dim3 gs((n_pad / 2 + 255) / 256, levels);
-                bitonic_global_step<<<gs, 256, 0, c->stream>>>(c->vals.p, n_pad, size, stride);
+                launch(c, bitonic_global_step, dim3(gs), dim3(256), 0, c->vals.p, n_pad, size, stride);
                 CU(cudaGetLastError());
                 ++c->launches;
             }
-            bitonic_tile_kernel<<<gt, 1024, 0, c->stream>>>(c->vals.p, n_pad, size, size, kSortTile / 2);
+            launch(c, bitonic_tile_kernel, dim3(gt), dim3(1024), 0, c->vals.p, n_pad, size, size, kSortTile / 2);
             CU(cudaGetLastError());
             ++c->launches;
         }
-        image_bins_kernel<<<levels, 256, 0, c->stream>>>(c->vals.p, n_pix, n_pad, c->bins.p);
+        launch(c, image_bins_kernel, dim3(levels), dim3(256), 0, c->vals.p, n_pix, n_pad, c->bins.p);
         CU(cudaGetLastError());
         dim3 gd((n_pix + 255) / 256, levels);
-        image_digitize_kernel<<<gd, 256, 0, c->stream>>>(c->canon.p, m.lut.p, nk, n_pix, c->bins.p, c->pix_d());
+        launch(c, image_digitize_kernel, dim3(gd), dim3(256), 0, c->canon.p, m.lut.p, nk, n_pix, c->bins.p, c->pix_d());
         CU(cudaGetLastError());
         c->launches += 2;
     }
@@ -430,6 +466,9 @@ int vk_ctx_create(int device, vk_ctx** out)
         if (const char* e = getenv("VK_COUNT_THREADS")) c->count_threads = atoi(e);
         if (const char* e = getenv("VK_COUNT_CTAS")) c->count_ctas_per_sm = atoi(e);
         if (const char* e = getenv("VK_TEST_TIGHT_BUCKETS")) c->test_tight = atoi(e) != 0;
+        if (const char* e = getenv("VK_PDL")) c->use_pdl = atoi(e) != 0;
+        if (const char* e = getenv("VK_COUNT16")) c->use_count16 = atoi(e) != 0;
+        if (const char* e = getenv("VK_COUNT_PAIRS")) c->use_pairs = atoi(e) != 0;
         if (c->count_threads < 32 || c->count_threads > 1024 || c->count_threads % 32 || c->count_ctas_per_sm < 1 || c->count_ctas_per_sm > 3)
             throw ApiError{VK_EINVAL, "bad VK_COUNT_THREADS / VK_COUNT_CTAS"};
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -586,7 +625,7 @@ int vk_render(vk_ctx* c, int slot, int k, int n_levels, const uint64_t* seg_hist
             enqueue_render(c, *m, k, n_levels, sh);
         } else {
             c->canon.ensure((size_t)n_levels * nk);
-            vk::fold_kernel<<<(nk + 255) / 256, 256, 0, c->stream>>>(sh, k, n_levels, c->canon.p);
+            launch(c, vk::fold_kernel, dim3((nk + 255) / 256), dim3(256), 0, sh, k, n_levels, c->canon.p);
             CU(cudaGetLastError());
             ++c->launches;
         }
@@ -686,12 +725,20 @@ int vk_last_timings(vk_ctx* c, float* ms8)
             }
         }
         const int last = c->ev_valid[EV_DONE] ? EV_DONE : EV_RENDER;
+        if (!c->ev_valid[last]) return;
         if (c->ev_valid[EV_START] && c->ev_valid[last]) {
             float t = 0.f;
             if (cudaEventElapsedTime(&t, c->ev[EV_START], c->ev[last]) == cudaSuccess) ms8[7] = t;
         }
         cudaGetLastError();
     });
+}
+
+int vk_set_fine_timing(vk_ctx* c, int on)
+{
+    if (!c) return VK_EINVAL;
+    c->fine_timing = on != 0;
+    return VK_OK;
 }
 
 uint64_t vk_launch_count(vk_ctx* c) { return c ? c->launches : 0; }
@@ -710,7 +757,7 @@ int vk_synth_fastq(vk_ctx* c, void* dev_bytes, uint64_t capacity, uint64_t n_bas
         const uint64_t total = (n_reads - 1) * (2 * L + 17) + 2 * last_len + 17;
         if (total > capacity) throw ApiError{VK_EINVAL, "synthetic FASTQ does not fit the buffer"};
         const int grid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->n_sms * 16);
-        vk::synth_fixed_kernel<<<grid, 256, 0, c->stream>>>(static_cast<uint8_t*>(dev_bytes), total, n_reads, (uint32_t)L,
+        launch(c, vk::synth_fixed_kernel, dim3(grid), dim3(256), 0, static_cast<uint8_t*>(dev_bytes), total, n_reads, (uint32_t)L,
                                                             (uint32_t)last_len, seed, first_read);
         CU(cudaGetLastError());
         ++c->launches;

@@ -81,6 +81,10 @@ __host__ __device__ __forceinline__ uint32_t internal_revcomp(uint32_t i, int k)
     return r;
 }
 
+// programmatic dependent launch: block until the preceding kernel of the stream has completed and its writes are
+// visible (no-op when the kernel was not launched with programmatic stream serialisation)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p)
 {
     uint64_t v;

@@ -7,49 +7,49 @@
 //   D4/D5 canonical abundance = forward count of K + forward count of rc(K): the fold happens after
 //   counting (vk_image.cuh), so the hot loop only builds a forward-strand histogram.
 //
-// Design (DESIGN.md "K2"): one thread walks one read, one aligned 16-byte word per step; the 16 bases are
-// packed to 2 bits with SIMD-in-register arithmetic and joined to the previous k-1 codes in a 64-bit window,
-// so each k-mer is one funnel shift + mask.  Validity (ACGT, read bounds, break points) is a bit mask whose
-// k-long runs give the 16-bit "emit" mask.  Every lane issues its shared-memory increment on every step
-// (invalid positions go to a per-lane trash word) because a fully populated ATOMS.POPC.INC costs the same as
-// a sparse one (tools/microbench_atomics2.cu: 12.2 increments/clk/SM full, 4.0 at 52 % lanes with branches).
-// Reads arrive sorted by segment (vk_bucket.cuh), a CTA serves one segment and keeps one 4^k x u32 histogram
-// in shared memory, written once at the end to its private slab (plain stores; no global atomics).
+// Design (DESIGN.md "K2").  Reads arrive sorted by segment (vk_bucket.cuh); a CTA serves one segment and keeps
+// that segment's histogram in shared memory, written to its private slab (plain stores; no global atomics).
+//
+// Work distribution ("flat lanes", struct ChunkStream).  A warp takes the segment's sorted reads in units of 32
+// (one entry per lane) from the segment's global counter.  Every read is cut into 32-byte chunks that start at a
+// 16-byte boundary of the text; the chunks of successive units form one stream, and in every iteration lane l
+// works on chunk pos + l of that stream, whichever read it belongs to.  The owner of a chunk is found without a
+// search: the lanes OR together one bit per read that starts inside the 32-chunk window (REDUX), and a lane's owner
+// is the read of the highest such bit at or below it (or the read that owned the end of the previous window).  All
+// 32 lanes classify and emit in every iteration (except at the very end of the segment), no lane waits for a longer
+// read of a neighbour, and there is no divergent control flow in the loop: ranges (read start / end inside the
+// chunk), invalid bytes and reformat.sh break points are bit masks.  The K-1 bases that precede a chunk come from
+// the lane to the left (one shuffle of the packed tail; lane 0 keeps the tail of lane 31 of the previous
+// iteration).  The text of iteration i+1 is requested before iteration i is counted.
+//
+// Per chunk: two LDG.128; the 32 bases are packed to 2 bits with SIMD-in-register arithmetic and joined to the
+// previous K-1 codes in 64-bit windows, so each k-mer is one funnel shift + mask; validity is a bit mask whose
+// K-long runs give the 32-bit "a k-mer ends here" mask E.
+//
+// Three ways to count (template MODE):
+//   kSmem32   k <= 7: 4^k x u32 bins in shared memory, one ATOMS.POPC.INC per base.  Lanes without a k-mer
+//             increment a per-lane trash word: ptxas cannot predicate ATOMS.POPC.INC (it branches around it) and a
+//             sparsely populated ATOMS costs as much as a full one (profiles/microbench_atomics_r01.txt).
+//   kSmem16   k = 7, 8: 4^8 16-bit bins (two per 32-bit word, 128 KiB).  k = 8 counts every 8-mer; k = 7 counts
+//             PAIRS: the 8-mer that ends at an odd chunk position stands for the two 7-mers it contains, so a base
+//             pair costs one shared-memory operation instead of two (the kernel is bound by the shared-memory data
+//             pipe: 3.5 wavefronts per 32 random banks, profiles/r01_notes.md); 7-mers whose pair partner is not
+//             countable (read ends, N, break points) go to a 4^7 x u32 table.  16-bit bins are kept exact by
+//             watching the values the atomics return (see count_flush / the rendezvous in the kernel).
+//   kGlobal   k = 9: increments go straight to the global (L2-resident) segment histogram.
 #pragma once
 #include "vk_common.cuh"
 
 namespace vk {
 
 constexpr int kCountThreads = 1024;
-
-// SIMD-in-register classification of 4 text bytes (one 32-bit word x).
-//   y     = per byte the 2-bit code (ascii >> 1) & 3                      (A0 C1 T2 G3)
-//   pack  : (y * 0x01041040) puts the four codes, densely packed, into byte 3 (partial products never overlap)
-//   valid : a byte is one of ACGTacgt iff it equals the letter rebuilt from its own code:
-//           letter = 'A' + 2*code + 15*[code == T]   ->  A 0x41, C 0x43, G 0x47, T 0x54;  bit 5 (case) is ignored.
-//           The rebuild runs on the FMA pipe (IMAD), which the rest of the loop leaves idle.
-struct Cls4 {
-    uint32_t packed_hi;   // byte 3 = 4 packed codes
-    uint32_t valid_hi;    // bits 28..31 = validity of bytes 0..3
-};
-__device__ __forceinline__ Cls4 classify4(uint32_t x)
-{
-    const uint32_t y = (x >> 1) & 0x03030303u;
-    const uint32_t t = (y >> 1) & ~y & 0x01010101u;                  // 1 where the code is T
-    const uint32_t e = t * 15u + (y * 2u + 0x41414141u);            // expected upper-case letter per byte
-    const uint32_t d = (x & 0xDFDFDFDFu) ^ e;                        // 0 in a byte <=> valid
-    const uint32_t z = ~(((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;   // 0x80 in every zero byte of d
-    Cls4 c;
-    c.packed_hi = y * 0x01041040u;
-    c.valid_hi = z * 0x00204081u;                                    // flags gathered into bits 28..31
-    return c;
-}
+enum { kSmem32 = 0, kGlobal = 1, kSmem16 = 2 };
 
 template <int K>
-__device__ __forceinline__ uint32_t runs_of_k(uint32_t m)
+__device__ __forceinline__ uint64_t runs_of_k64(uint64_t m)
 {
     // bit j of the result = bits j .. j+K-1 of m are all set
-    uint32_t r = m;
+    uint64_t r = m;
     int len = 1;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
@@ -70,11 +70,19 @@ __device__ __forceinline__ void smem_inc(uint32_t shared_addr)
 {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(shared_addr) : "memory");      // SASS: ATOMS.POPC.INC
 }
+__device__ __forceinline__ uint32_t smem_add_ret(uint32_t shared_addr, uint32_t v)
+{
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(shared_addr), "r"(v) : "memory");
+    return old;
+}
 
-// 8 validity flags of two classified words in byte 3: bits 24..27 = word a (bytes 0..3), bits 28..31 = word b.
-// za / zb carry 0x80 in every valid byte; one multiply gathers both nibbles (no two partial products share a bit).
-__device__ __forceinline__ uint32_t gather8(uint32_t za, uint32_t zb) { return (zb | (za >> 4)) * 0x00204081u; }
-
+// SIMD-in-register classification of 4 text bytes (one 32-bit word x).
+//   y     = per byte the 2-bit code (ascii >> 1) & 3                      (A0 C1 T2 G3)
+//   pack  : (y * 0x01041040) puts the four codes, densely packed, into byte 3 (partial products never overlap)
+//   valid : a byte is one of ACGTacgt iff it equals the letter rebuilt from its own code:
+//           letter = 'A' + 2*code + 15*[code == T]   ->  A 0x41, C 0x43, G 0x47, T 0x54;  bit 5 (case) is ignored.
+//           The rebuild runs on the FMA pipe (IMAD), which the rest of the loop leaves idle.
 struct Cls4z {
     uint32_t packed_hi;   // byte 3 = 4 packed codes
     uint32_t z;           // 0x80 in every byte that is one of ACGTacgt
@@ -92,48 +100,11 @@ __device__ __forceinline__ Cls4z classify4z(uint32_t x)
     c.packed_hi = y * 0x01041040u;
     return c;
 }
+// 8 validity flags of two classified words in byte 3: bits 24..27 = word a (bytes 0..3), bits 28..31 = word b.
+// za / zb carry 0x80 in every valid byte; one multiply gathers both nibbles (no two partial products share a bit).
+__device__ __forceinline__ uint32_t gather8(uint32_t za, uint32_t zb) { return (zb | (za >> 4)) * 0x00204081u; }
 
-template <int K>
-__device__ __forceinline__ uint64_t runs_of_k64(uint64_t m)
-{
-    uint64_t r = m;
-    int len = 1;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        if (len * 2 <= K) { r &= r >> len; len *= 2; }
-    }
-    if (len < K) r &= r >> (K - len);
-    return r;
-}
-
-// 16 increments: window W4 holds K-1 carried codes then 16 new ones, pre-multiplied by 4 (byte offsets);
-// bit j of E = the k-mer ending at new base j is to be counted.
-#ifndef VK_EMIT_TRASH
-#define VK_EMIT_TRASH 1      // 1: lanes without a k-mer increment a per-lane trash word.  ptxas cannot predicate
-                             // ATOMS.POPC.INC (it branches around it, BSSY/BRA/BSYNC per increment), so 0 is slower
-#endif
-template <int K, bool SMEM>
-__device__ __forceinline__ void emit16(const uint64_t W4, const uint32_t E, const uint32_t hist_addr,
-                                       const uint32_t trash_addr, unsigned long long* const gh)
-{
-    constexpr uint32_t KMASK = (1u << (2 * K)) - 1;
-    constexpr uint32_t fmask = KMASK << 2;
-    const uint32_t Wl = (uint32_t)W4, Wh = (uint32_t)(W4 >> 32);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const uint32_t sh = __funnelshift_r(Wl, Wh, 2 * j);
-        if (SMEM) {
-#if VK_EMIT_TRASH
-            smem_inc((E >> j) & 1u ? and_or(sh, fmask, hist_addr) : trash_addr);
-#else
-            if ((E >> j) & 1u) smem_inc(and_or(sh, fmask, hist_addr));
-#endif
-        } else {
-            if ((E >> j) & 1u) atomicAdd(gh + ((sh & fmask) >> 2), 1ull);
-        }
-    }
-}
-
+// ---------------------------------------------------------------------------------------- chunk stream
 // One unit = 32 sorted reads of the CTA's segment, one per lane, with the chunk numbering of the unit.
 struct Unit {
     uint64_t ent;      // start << 24 | len   (0: no read in this lane)
@@ -170,85 +141,44 @@ struct Chunk {
     int32_t q0;        // read position of byte 0 of the chunk (negative in a read's first chunk)
 };
 
-// SMEM = true : histogram of the CTA's segment in shared memory (k <= 7), flushed to slabs[blockIdx.x]
-// SMEM = false: increments go straight to the global (L2-resident) segment histogram (k = 8, 9)
-//
-// Work distribution ("flat lanes").  A warp takes the segment's sorted reads in units of 32 (one entry per lane)
-// from the segment's global counter.  Every read is cut into 32-byte chunks that start at a 16-byte boundary of
-// the text; the chunks of successive units form one stream, and in every iteration lane l works on chunk
-// pos + l of that stream, whichever read it belongs to.  The owner of a chunk is found without a search: the lanes
-// OR together one bit per read that starts inside the 32-chunk window (REDUX), and a lane's owner is the read of
-// the highest such bit at or below it (or the read that owned the end of the previous window).  All 32 lanes
-// classify and emit in every iteration (except at the very end of the segment), no lane waits for a longer read
-// of a neighbour, and there is no divergent control flow in the loop: ranges (read start / end inside the chunk),
-// invalid bytes and reformat.sh break points are bit masks.  The K-1 bases that precede a chunk come from the
-// lane to the left (one shuffle of the packed tail; lane 0 keeps the tail of lane 31 of the previous iteration).
-// The text of iteration i+1 is requested before iteration i is counted.
-template <int K, bool SMEM>
-__global__ void __launch_bounds__(kCountThreads)
-count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sorted, Plan* __restrict__ plan,
-             uint32_t* __restrict__ slabs, unsigned long long* __restrict__ seg_hist, int breaklen)
-{
-    constexpr uint32_t NK = 1u << (2 * K);
-    constexpr int KM1 = K - 1;
-    constexpr uint32_t FULL = 0xffffffffu;
-    extern __shared__ uint32_t s_raw[];           // SMEM: [pad to a 64 KiB shared address][NK bins][32 trash words]
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
+struct ChunkStream {
+    const uint4* text16;
+    const uint64_t* seg_sorted;
+    unsigned long long* seg_counter;
+    uint32_t seg_len, lane;
+    Unit A, B;         // A is being consumed, B follows it in the chunk stream
+    uint64_t entC;     // the unit after B, on its way from memory
+    uint32_t pos;      // stream position of lane 0, in A's chunk numbering
+    uint32_t own, own_j;   // owner (0..31: lane of A, 32..63: lane of B) and chunk number of the last chunk of the previous window
 
-    // ---- which segment does this CTA serve?
-    int seg = -1;
+    __device__ __forceinline__ uint64_t claim()
     {
-        const uint32_t b0 = plan->seg_cta_begin[lane], b1 = plan->seg_cta_begin[lane + 1];
-        const uint32_t b2 = plan->seg_cta_begin[lane + 32], b3 = plan->seg_cta_begin[lane + 33];
-        const uint32_t m0 = __ballot_sync(FULL, blockIdx.x >= b0 && blockIdx.x < b1);
-        const uint32_t m1 = __ballot_sync(FULL, blockIdx.x >= b2 && blockIdx.x < b3);
-        if (m0) seg = __ffs(m0) - 1;
-        else if (m1) seg = 32 + __ffs(m1) - 1;
-    }
-    if (seg < 0) return;
-    const uint64_t* const seg_sorted = sorted + plan->seg_begin[seg];
-    // reads of this segment (< 2^32); never beyond the region (after a bucket overflow the step is repeated)
-    const uint32_t seg_len = (uint32_t)(plan->seg_reads[seg] < plan->seg_cap[seg] ? plan->seg_reads[seg] : plan->seg_cap[seg]);
-    unsigned long long* const gh = SMEM ? nullptr : seg_hist + (size_t)seg * NK;
-
-    const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(s_raw);
-    const uint32_t hist_addr = SMEM ? (raw_addr + 0xFFFFu) & ~0xFFFFu : 0u;
-    uint32_t* const s_hist = s_raw + ((hist_addr - raw_addr) >> 2);
-    const uint32_t trash_addr = hist_addr + (NK + lane) * 4u;
-    if (SMEM) {
-        for (uint32_t i = tid; i < NK + 32; i += blockDim.x) s_hist[i] = 0;
-        __syncthreads();
-    }
-
-    unsigned long long* const seg_counter = &plan->seg_next[seg];
-    // units: A is being consumed, B follows it in the chunk stream, C is on its way from memory
-    auto claim = [&]() -> uint64_t {
         unsigned long long r0 = 0;
         if (lane == 0) r0 = atomicAdd(seg_counter, 32ull);
-        const uint32_t base = (uint32_t)__shfl_sync(FULL, r0, 0);
+        const uint32_t base = (uint32_t)__shfl_sync(0xffffffffu, r0, 0);
         return (base < seg_len && base + lane < seg_len) ? seg_sorted[base + lane] : 0ull;
-    };
-    Unit A = make_unit(claim(), lane);
-    Unit B = make_unit(claim(), lane);
-    uint64_t entC = claim();
-    uint32_t pos = 0;                  // stream position of lane 0, in A's chunk numbering
-    uint32_t own = 0;                  // owner (0..31: lane of A, 32..63: lane of B) and chunk number of the last
-    uint32_t own_j = 0;                //   chunk of the previous window
-    const bool has_break = breaklen > 0;
-
-    auto fetch = [&]() -> Chunk {
-        // rotate while A is used up
-        while (pos >= A.total && A.nz != 0) {
+    }
+    __device__ __forceinline__ void init(const uint4* t, const uint64_t* ss, uint32_t sl, unsigned long long* sc, uint32_t ln)
+    {
+        text16 = t; seg_sorted = ss; seg_len = sl; seg_counter = sc; lane = ln;
+        A = make_unit(claim(), lane);
+        B = make_unit(claim(), lane);
+        entC = claim();
+        pos = 0; own = 0; own_j = 0;
+    }
+    __device__ __forceinline__ Chunk fetch()
+    {
+        constexpr uint32_t FULL = 0xffffffffu;
+        while (pos >= A.total && A.nz != 0) {          // rotate while A is used up
             pos -= A.total;
-            own -= 32;                 // an owner in B keeps its lane
+            own -= 32;                                  // an owner in B keeps its lane
             A = B;
             B = make_unit(entC, lane);
             entC = claim();
         }
         Chunk c;
         const uint32_t f = pos + lane;
-        const uint32_t endAB = A.total + B.total;
-        const bool act = f < endAB;
+        const bool act = f < A.total + B.total;
         // one bit per read whose first chunk lies in the window [pos, pos + 32)
         const uint32_t sa = A.excl - pos, sb = A.total + B.excl - pos;
         const bool hasA = (uint32_t)(A.ent & kEntryLenMask) != 0, hasB = (uint32_t)(B.ent & kEntryLenMask) != 0;
@@ -267,8 +197,7 @@ count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sort
         }
         own = __shfl_sync(FULL, o, 31);
         own_j = __shfl_sync(FULL, j, 31);
-        const uint64_t ea = __shfl_sync(FULL, A.ent, (int)(o & 31u));
-        uint64_t e = ea;
+        uint64_t e = __shfl_sync(FULL, A.ent, (int)(o & 31u));
         if (pos + 32u > A.total) {                                  // warp-uniform: the window reaches into B
             const uint64_t eb = __shfl_sync(FULL, B.ent, (int)(o & 31u));
             if (o >= 32u) e = eb;
@@ -292,63 +221,294 @@ count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sort
         c.q0 = (int32_t)(32u * j) - (int32_t)rlo;
         pos += 32;
         return c;
-    };
+    }
+};
 
-    uint32_t carry = 0;                                             // tail of lane 31 of the previous iteration
-    Chunk cur = fetch();
-    while (__ballot_sync(FULL, cur.range != 0) != 0) {
-        const Chunk nxt = fetch();
-
-        const Cls4z c0 = classify4z(cur.wa.x), c1 = classify4z(cur.wa.y), c2 = classify4z(cur.wa.z), c3 = classify4z(cur.wa.w);
-        const Cls4z c4 = classify4z(cur.wb.x), c5 = classify4z(cur.wb.y), c6 = classify4z(cur.wb.z), c7 = classify4z(cur.wb.w);
-        const uint32_t v01 = gather8(c0.z, c1.z), v23 = gather8(c2.z, c3.z);
-        const uint32_t v45 = gather8(c4.z, c5.z), v67 = gather8(c6.z, c7.z);
-        const uint32_t V = __byte_perm(__byte_perm(v01, v23, 0x0073), __byte_perm(v45, v67, 0x0073), 0x5410) & cur.range;
-        const uint32_t Plo = __byte_perm(__byte_perm(c0.packed_hi, c1.packed_hi, 0x0073),
-                                         __byte_perm(c2.packed_hi, c3.packed_hi, 0x0073), 0x5410);
-        const uint32_t Phi = __byte_perm(__byte_perm(c4.packed_hi, c5.packed_hi, 0x0073),
-                                         __byte_perm(c6.packed_hi, c7.packed_hi, 0x0073), 0x5410);
-
-        // ---- the K-1 bases before this chunk: from the lane to the left when it holds the same read
-        const uint32_t tail = (Phi >> (32 - 2 * KM1)) | ((V >> (32 - KM1)) << 16);
-        uint32_t hist = __shfl_up_sync(FULL, tail, 1);
-        if (lane == 0) hist = carry;
-        if (cur.j == 0) hist = 0;
-        carry = __shfl_sync(FULL, tail, 31);
-        const uint32_t Cc = hist & 0xFFFFu, Vc = hist >> 16;
-
-        const uint64_t VW = (uint64_t)Vc | ((uint64_t)V << KM1);    // bit i <-> base i - (K-1) of the chunk
-        uint32_t E = (uint32_t)runs_of_k64<K>(VW);
-        if (has_break && __ballot_sync(FULL, cur.rlen > (uint32_t)breaklen) != 0) {
-            // reformat.sh breaklength: no k-mer may span a multiple of breaklen counted from the read's first base.
-            // byte b of the chunk is base q0 + b of the read; a window ending at base q spans the cut c
-            // (c = m * breaklen, 1 <= m, c < rlen) iff q - (K-1) < c <= q, i.e. q in [c, c + K - 2].
-            uint32_t dead = 0;
-            if (cur.rlen > (uint32_t)breaklen && cur.range != 0) {
-                const int32_t q0 = cur.q0;
-                int32_t c = (q0 > 0 ? q0 / breaklen : 0) * breaklen;
-                if (c < breaklen) c = breaklen;
-                for (; c - q0 < 32 && c < (int32_t)cur.rlen; c += breaklen) {
-                    const int32_t b = c - q0;                       // chunk byte that starts the new piece
-                    if (b > -KM1) {
-                        const uint32_t run = (1u << KM1) - 1u;     // K-1 window ends: b .. b+K-2
-                        dead |= b >= 0 ? run << b : run >> (-b);
-                    }
+// Codes and countable positions of one chunk.
+struct Decoded {
+    uint32_t Plo, Phi;   // 2-bit codes of bases 0..15 / 16..31
+    uint32_t Cc;         // codes of the K-1 bases to the left (first at bit 0)
+    uint32_t E;          // bit b: the K-mer that ENDS at base b is to be counted
+};
+template <int K>
+__device__ __forceinline__ Decoded decode_chunk(const Chunk& cur, uint32_t& carry, uint32_t lane, int breaklen)
+{
+    constexpr int KM1 = K - 1;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const Cls4z c0 = classify4z(cur.wa.x), c1 = classify4z(cur.wa.y), c2 = classify4z(cur.wa.z), c3 = classify4z(cur.wa.w);
+    const Cls4z c4 = classify4z(cur.wb.x), c5 = classify4z(cur.wb.y), c6 = classify4z(cur.wb.z), c7 = classify4z(cur.wb.w);
+    const uint32_t v01 = gather8(c0.z, c1.z), v23 = gather8(c2.z, c3.z);
+    const uint32_t v45 = gather8(c4.z, c5.z), v67 = gather8(c6.z, c7.z);
+    const uint32_t V = __byte_perm(__byte_perm(v01, v23, 0x0073), __byte_perm(v45, v67, 0x0073), 0x5410) & cur.range;
+    Decoded d;
+    d.Plo = __byte_perm(__byte_perm(c0.packed_hi, c1.packed_hi, 0x0073), __byte_perm(c2.packed_hi, c3.packed_hi, 0x0073), 0x5410);
+    d.Phi = __byte_perm(__byte_perm(c4.packed_hi, c5.packed_hi, 0x0073), __byte_perm(c6.packed_hi, c7.packed_hi, 0x0073), 0x5410);
+    // ---- the K-1 bases before this chunk: from the lane to the left when it holds the same read
+    const uint32_t tail = (d.Phi >> (32 - 2 * KM1)) | ((V >> (32 - KM1)) << 16);
+    uint32_t hist = __shfl_up_sync(FULL, tail, 1);
+    if (lane == 0) hist = carry;
+    if (cur.j == 0) hist = 0;
+    carry = __shfl_sync(FULL, tail, 31);
+    d.Cc = hist & 0xFFFFu;
+    const uint32_t Vc = hist >> 16;
+    const uint64_t VW = (uint64_t)Vc | ((uint64_t)V << KM1);        // bit i <-> base i - (K-1) of the chunk
+    uint32_t E = (uint32_t)runs_of_k64<K>(VW);
+    if (breaklen > 0 && __ballot_sync(FULL, cur.rlen > (uint32_t)breaklen) != 0) {
+        // reformat.sh breaklength: no k-mer may span a multiple of breaklen counted from the read's first base.
+        // byte b of the chunk is base q0 + b of the read; a window ending at base q spans the cut c
+        // (c = m * breaklen, 1 <= m, c < rlen) iff q - (K-1) < c <= q, i.e. q in [c, c + K - 2].
+        uint32_t dead = 0;
+        if (cur.rlen > (uint32_t)breaklen && cur.range != 0) {
+            const int32_t q0 = cur.q0;
+            int32_t c = (q0 > 0 ? q0 / breaklen : 0) * breaklen;
+            if (c < breaklen) c = breaklen;
+            for (; c - q0 < 32 && c < (int32_t)cur.rlen; c += breaklen) {
+                const int32_t b = c - q0;                           // chunk byte that starts the new piece
+                if (b > -KM1) {
+                    const uint32_t run = (1u << KM1) - 1u;         // K-1 window ends: b .. b+K-2
+                    dead |= b >= 0 ? run << b : run >> (-b);
                 }
             }
-            E &= ~dead;
         }
-        const uint64_t Wa = ((uint64_t)Cc | ((uint64_t)Plo << (2 * KM1))) << 2;
-        const uint64_t Wb = ((uint64_t)(Plo >> (32 - 2 * KM1)) | ((uint64_t)Phi << (2 * KM1))) << 2;
-        emit16<K, SMEM>(Wa, E & 0xFFFFu, hist_addr, trash_addr, gh);
-        emit16<K, SMEM>(Wb, E >> 16, hist_addr, trash_addr, gh);
+        E &= ~dead;
+    }
+    d.E = E;
+    return d;
+}
+
+// which segment does this CTA serve?  (-1: none)
+__device__ __forceinline__ int cta_segment(const Plan* __restrict__ plan, uint32_t lane)
+{
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t b0 = plan->seg_cta_begin[lane], b1 = plan->seg_cta_begin[lane + 1];
+    const uint32_t b2 = plan->seg_cta_begin[lane + 32], b3 = plan->seg_cta_begin[lane + 33];
+    const uint32_t m0 = __ballot_sync(FULL, blockIdx.x >= b0 && blockIdx.x < b1);
+    const uint32_t m1 = __ballot_sync(FULL, blockIdx.x >= b2 && blockIdx.x < b3);
+    if (m0) return __ffs(m0) - 1;
+    if (m1) return 32 + __ffs(m1) - 1;
+    return -1;
+}
+
+// ------------------------------------------------------------------------------ kSmem32 / kGlobal
+// 16 increments: window W4 holds K-1 carried codes then 16 new ones, pre-multiplied by 4 (byte offsets);
+// bit j of E = the k-mer ending at new base j is to be counted.
+template <int K, int MODE>
+__device__ __forceinline__ void emit16(const uint64_t W4, const uint32_t E, const uint32_t hist_addr,
+                                       const uint32_t trash_addr, unsigned long long* const gh)
+{
+    constexpr uint32_t KMASK = (1u << (2 * K)) - 1;
+    constexpr uint32_t fmask = KMASK << 2;
+    const uint32_t Wl = (uint32_t)W4, Wh = (uint32_t)(W4 >> 32);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t sh = __funnelshift_r(Wl, Wh, 2 * j);
+        if (MODE == kSmem32) {
+            smem_inc((E >> j) & 1u ? and_or(sh, fmask, hist_addr) : trash_addr);
+        } else {
+            if ((E >> j) & 1u) atomicAdd(gh + ((sh & fmask) >> 2), 1ull);
+        }
+    }
+}
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(kCountThreads)
+count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sorted, Plan* __restrict__ plan,
+             uint32_t* __restrict__ slabs, unsigned long long* __restrict__ seg_hist, int breaklen)
+{
+    pdl_wait();
+    static_assert(MODE == kSmem32 || MODE == kGlobal, "count16_kernel is the kSmem16 kernel");
+    constexpr uint32_t NK = 1u << (2 * K);
+    constexpr int KM1 = K - 1;
+    constexpr uint32_t FULL = 0xffffffffu;
+    extern __shared__ uint32_t s_raw[];           // kSmem32: [pad to a 64 KiB shared address][NK bins][32 trash words]
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+
+    const int seg = cta_segment(plan, lane);
+    if (seg < 0) return;
+    // reads of this segment (< 2^32); never beyond the region (after a bucket overflow the step is repeated)
+    const uint32_t seg_len = (uint32_t)(plan->seg_reads[seg] < plan->seg_cap[seg] ? plan->seg_reads[seg] : plan->seg_cap[seg]);
+    unsigned long long* const gh = MODE == kSmem32 ? nullptr : seg_hist + (size_t)seg * NK;
+
+    // the histogram sits at a 64 KiB-aligned shared address so that "mask the k-mer, add the base" is one LOP3
+    const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(s_raw);
+    const uint32_t hist_addr = MODE == kSmem32 ? (raw_addr + 0xFFFFu) & ~0xFFFFu : 0u;
+    uint32_t* const s_hist = s_raw + ((hist_addr - raw_addr) >> 2);
+    const uint32_t trash_addr = hist_addr + (NK + lane) * 4u;
+    if (MODE == kSmem32) {
+        for (uint32_t i = tid; i < NK + 32; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+    }
+
+    ChunkStream cs;
+    cs.init(text16, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane);
+    uint32_t carry = 0;                                             // tail of lane 31 of the previous iteration
+    Chunk cur = cs.fetch();
+    while (__ballot_sync(FULL, cur.range != 0) != 0) {
+        const Chunk nxt = cs.fetch();
+        const Decoded d = decode_chunk<K>(cur, carry, lane, breaklen);
+        const uint64_t Wa = ((uint64_t)d.Cc | ((uint64_t)d.Plo << (2 * KM1))) << 2;
+        const uint64_t Wb = ((uint64_t)(d.Plo >> (32 - 2 * KM1)) | ((uint64_t)d.Phi << (2 * KM1))) << 2;
+        emit16<K, MODE>(Wa, d.E & 0xFFFFu, hist_addr, trash_addr, gh);
+        emit16<K, MODE>(Wb, d.E >> 16, hist_addr, trash_addr, gh);
         cur = nxt;
     }
 
-    if (SMEM) {
+    if (MODE == kSmem32) {
         __syncthreads();
         uint32_t* slab = slabs + (size_t)blockIdx.x * NK;
         for (uint32_t i = tid; i < NK; i += blockDim.x) slab[i] = s_hist[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ kSmem16
+// 4^8 bins of 16 bits, two per 32-bit word: bin b lives in word (b & 0x7FFF); bins with bit 15 clear are counted
+// by adding 1, bins with bit 15 set by adding 0x10001.  So the LOW half of a word is the total of its two bins and
+// the HIGH half the count of the upper bin: the increment is (sh & 0x20000) / 2 + 1 (one LOP3 + one IMAD.HI), and
+// "the low half stays below 2^16" is the only overflow condition.
+//
+// Exactness.  Every increment is an ATOMS.ADD that returns the old word; a lane ORs what it gets back.  When some
+// low half has reached 0x4000 the warp raises the CTA's flag at the end of its iteration; every warp looks at the
+// flag once per iteration and then joins a rendezvous (also joined by warps that ran out of work, which simply wait
+// at its barrier), where the table is folded into the CTA's u32 slab in global memory and cleared.  Between a bin
+// reaching 0x4000 and the last warp stopping, every warp can add at most two iterations (2 x 32 lanes x 32), i.e.
+// 65 536 / 2 in total for 32 warps, so no low half can pass 0x4000 + 0x8400 < 2^16.  On ordinary reads the flag is
+// never raised (a CTA sees ~10^6 bases; one 8-mer would have to make up > 1 % of them).
+template <int K>
+__device__ __forceinline__ void count16_flush(uint32_t* __restrict__ h8, uint32_t* __restrict__ h7, uint32_t* __restrict__ slab,
+                                              bool first, uint32_t tid, uint32_t nthr)
+{
+    if (K == 8) {
+        for (uint32_t w = tid; w < 32768u; w += nthr) {
+            const uint32_t v = h8[w];
+            const uint32_t hi = v >> 16, lo = (v & 0xFFFFu) - hi;
+            h8[w] = 0;
+            if (first) { slab[w] = lo; slab[w | 0x8000u] = hi; }
+            else { slab[w] += lo; slab[w | 0x8000u] += hi; }
+        }
+    } else {
+        // 7-mer x: singles + 8-mers that start with it (x | c << 14) + 8-mers that end with it ((x << 2 | c) & 0xFFFF)
+        for (uint32_t x = tid; x < 16384u; x += nthr) {
+            uint32_t v = h7[x];
+            v += (h8[x] & 0xFFFFu) + (h8[x | 0x4000u] & 0xFFFFu);         // low halves = totals of both bins of a word
+            const uint32_t w0 = (x & 0x1FFFu) << 2;
+            const bool upper = (x & 0x2000u) != 0;                          // bit 15 of (x << 2 | c)
+#pragma unroll
+            for (uint32_t c = 0; c < 4; ++c) {
+                const uint32_t w = h8[w0 | c];
+                v += upper ? (w >> 16) : (w & 0xFFFFu) - (w >> 16);
+            }
+            if (first) slab[x] = v; else slab[x] += v;
+        }
+        __syncthreads();                                                    // all reads of h8 done before it is cleared
+        for (uint32_t w = tid; w < 32768u; w += nthr) h8[w] = 0;
+        for (uint32_t x = tid; x < 16384u; x += nthr) h7[x] = 0;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kCountThreads)
+count16_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sorted, Plan* __restrict__ plan,
+               uint32_t* __restrict__ slabs, int breaklen)
+{
+    pdl_wait();
+    static_assert(K == 7 || K == 8, "16-bit bins: k = 8 directly, k = 7 through pairs");
+    constexpr uint32_t NK = 1u << (2 * K);
+    constexpr int KM1 = K - 1;
+    constexpr uint32_t FULL = 0xffffffffu;
+    extern __shared__ uint32_t s_raw[];           // [h8: 32768 words][h7: 16384 words (k = 7)][32 trash words]
+    __shared__ volatile uint32_t s_flag;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
+
+    const int seg = cta_segment(plan, lane);
+    if (seg < 0) return;
+    const uint32_t seg_len = (uint32_t)(plan->seg_reads[seg] < plan->seg_cap[seg] ? plan->seg_reads[seg] : plan->seg_cap[seg]);
+
+    uint32_t* const h8 = s_raw;
+    uint32_t* const h7 = s_raw + 32768;
+    constexpr uint32_t kWords = 32768u + (K == 7 ? 16384u : 0u);
+    const uint32_t h8_addr = (uint32_t)__cvta_generic_to_shared(s_raw);
+    const uint32_t h7_addr = h8_addr + 32768u * 4u;
+    const uint32_t trash_off = (kWords + lane) * 4u;                   // byte offset from h8_addr
+    for (uint32_t i = tid; i < kWords + 32; i += nthr) s_raw[i] = 0;
+    if (tid == 0) s_flag = 0;
+    __syncthreads();
+    uint32_t* const slab = slabs + (size_t)blockIdx.x * NK;
+    bool first_flush = true;
+
+    ChunkStream cs;
+    cs.init(text16, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane);
+    uint32_t carry = 0;
+    uint32_t acc = 0;                                                   // OR of the words the atomics returned
+    Chunk cur = cs.fetch();
+    for (;;) {
+        const bool have = __ballot_sync(FULL, cur.range != 0) != 0;     // warp-uniform
+        if (!have || s_flag != 0) {
+            // ---- rendezvous of the whole CTA: fold + clear the table when asked to (or at the very end)
+            const int n_busy = __syncthreads_count(have && lane == 0);
+            const bool flush = s_flag != 0 || n_busy == 0;              // uniform: nobody changes the flag in here
+            __syncthreads();
+            if (flush) {
+                count16_flush<K>(h8, h7, slab, first_flush, tid, nthr);
+                first_flush = false;
+                if (tid == 0) s_flag = 0;
+            }
+            acc = 0;
+            __syncthreads();
+            if (n_busy == 0) break;
+            if (!have) continue;                                        // nothing left for this warp: wait for the others
+        }
+        const Chunk nxt = cs.fetch();
+        const Decoded d = decode_chunk<K>(cur, carry, lane, breaklen);
+        const uint64_t Wa = ((uint64_t)d.Cc | ((uint64_t)d.Plo << (2 * KM1))) << 2;
+        const uint64_t Wb = ((uint64_t)(d.Plo >> (32 - 2 * KM1)) | ((uint64_t)d.Phi << (2 * KM1))) << 2;
+        if (K == 8) {
+            // every 8-mer: window position j holds the 8-mer that ends at base j (7 carried codes in front)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint64_t W4 = h ? Wb : Wa;
+                const uint32_t Wl = (uint32_t)W4, Wh = (uint32_t)(W4 >> 32), E = h ? d.E >> 16 : d.E & 0xFFFFu;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t sh = __funnelshift_r(Wl, Wh, 2 * j);
+                    const uint32_t off = (E >> j) & 1u ? (sh & 0x1FFFCu) : trash_off;
+                    const uint32_t inc = __umulhi(sh & 0x20000u, 0x80000000u) + 1u;
+                    acc |= smem_add_ret(h8_addr + off, (E >> j) & 1u ? inc : 0u);      // the trash word stays 0
+                }
+            }
+        } else {
+            // pairs: positions (2m, 2m+1); Eb: both 7-mers countable -> one 8-mer; Es: exactly one -> a single 7-mer
+            const uint32_t Ee = d.E & 0x55555555u, Eo = (d.E >> 1) & 0x55555555u;
+            const uint32_t Eb = Ee & Eo;
+            uint32_t Es = Ee ^ Eo;                                      // bit 2m: pair m holds exactly one 7-mer
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint64_t W4 = h ? Wb : Wa;
+                const uint32_t Wl = (uint32_t)W4, Wh = (uint32_t)(W4 >> 32), E = h ? Eb >> 16 : Eb & 0xFFFFu;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    // the 8-mer that ends at base 2m+1 starts at window position 2m (6 carried codes in front)
+                    const uint32_t sh = __funnelshift_r(Wl, Wh, 4 * m);
+                    const bool on = (E >> (2 * m)) & 1u;
+                    const uint32_t off = on ? (sh & 0x1FFFCu) : trash_off;
+                    const uint32_t inc = __umulhi(sh & 0x20000u, 0x80000000u) + 1u;
+                    acc |= smem_add_ret(h8_addr + off, on ? inc : 0u);           // the trash word stays 0
+                }
+            }
+            // single 7-mers (read ends, N, break points): a few per warp and iteration
+            while (__ballot_sync(FULL, Es != 0) != 0) {
+                if (Es != 0) {
+                    const uint32_t b2 = __ffs(Es) - 1;                  // = 2m
+                    Es &= Es - 1;
+                    const uint64_t W4 = b2 >= 16 ? Wb : Wa;
+                    const uint32_t sh = (uint32_t)(W4 >> (2 * (b2 & 15u)));     // window position 2m, as above
+                    const bool second = (Eo >> b2) & 1u;                // the 7-mer that ends at 2m+1: last 7 bases
+                    const uint32_t off7 = (second ? sh >> 2 : sh) & 0xFFFCu;
+                    smem_inc(h7_addr + off7);
+                }
+            }
+        }
+        if (__ballot_sync(FULL, (acc & 0xC000u) != 0) != 0 && lane == 0) s_flag = 1;
+        cur = nxt;
     }
 }
 
@@ -358,6 +518,7 @@ __global__ void __launch_bounds__(256)
 reduce_slabs_kernel(const uint32_t* __restrict__ slabs, const Plan* __restrict__ plan, uint32_t nk,
                     unsigned long long* __restrict__ seg_hist)
 {
+    pdl_wait();
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (uint64_t)kMaxLevels * nk) return;
     const uint32_t s = (uint32_t)(g / nk), i = (uint32_t)(g % nk);
@@ -370,6 +531,7 @@ reduce_slabs_kernel(const uint32_t* __restrict__ slabs, const Plan* __restrict__
 __global__ void __launch_bounds__(256)
 zero_u64_kernel(unsigned long long* __restrict__ p, uint64_t n)
 {
+    pdl_wait();
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g < n) p[g] = 0;
 }

@@ -21,6 +21,7 @@ namespace cg = cooperative_groups;
 __global__ void __launch_bounds__(256)
 fold_kernel(const unsigned long long* __restrict__ seg_hist, int k, int n_levels, unsigned long long* __restrict__ canon)
 {
+    pdl_wait();
     const uint32_t nk = 1u << (2 * k);
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= nk) return;
@@ -59,6 +60,7 @@ __global__ void __cluster_dims__(kImgCluster, 1, 1) __launch_bounds__(1024, 1)
 image_kernel_cluster(const unsigned long long* __restrict__ canon, const int32_t* __restrict__ lut, uint32_t nk,
                      uint32_t n_pix, uint32_t S, uint8_t* __restrict__ pixels)
 {
+    pdl_wait();
     extern __shared__ unsigned long long s_keys[];        // [kImgCluster][S]: slice r at offset r * S, in every CTA
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t rank = cluster.block_rank();
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(256)
 image_gather_kernel(const unsigned long long* __restrict__ canon, const int32_t* __restrict__ lut, uint32_t nk,
                     uint32_t n_pix, uint32_t n_pad, unsigned long long* __restrict__ vals)
 {
+    pdl_wait();
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t l = blockIdx.y;
     if (p >= n_pad) return;
@@ -139,6 +142,7 @@ image_gather_kernel(const unsigned long long* __restrict__ canon, const int32_t*
 __global__ void __launch_bounds__(256)
 bitonic_global_step(unsigned long long* __restrict__ vals, uint32_t n_pad, uint32_t size, uint32_t stride)
 {
+    pdl_wait();
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (n_pad >> 1)) return;
     unsigned long long* v = vals + (size_t)blockIdx.y * n_pad;
@@ -155,6 +159,7 @@ __global__ void __launch_bounds__(1024)
 bitonic_tile_kernel(unsigned long long* __restrict__ vals, uint32_t n_pad, uint32_t size_begin, uint32_t size_end,
                     uint32_t first_stride)
 {
+    pdl_wait();
     // runs, for size = size_begin .. size_end (doubling), the strides min(size/2, first_stride) .. 1 inside a tile
     __shared__ unsigned long long s[kSortTile];
     unsigned long long* v = vals + (size_t)blockIdx.y * n_pad + (size_t)blockIdx.x * kSortTile;
@@ -182,6 +187,7 @@ __global__ void __launch_bounds__(256)
 image_bins_kernel(const unsigned long long* __restrict__ vals, uint32_t n_pix, uint32_t n_pad,
                   unsigned long long* __restrict__ bins)
 {
+    pdl_wait();
     const uint32_t i = threadIdx.x, l = blockIdx.x;
     const unsigned long long* s = vals + (size_t)l * n_pad;
     const uint64_t t = (uint64_t)(n_pix - 1) * i;
@@ -194,6 +200,7 @@ __global__ void __launch_bounds__(256)
 image_digitize_kernel(const unsigned long long* __restrict__ canon, const int32_t* __restrict__ lut, uint32_t nk,
                       uint32_t n_pix, const unsigned long long* __restrict__ bins, uint8_t* __restrict__ pixels)
 {
+    pdl_wait();
     __shared__ unsigned long long s_bins[256];
     const uint32_t l = blockIdx.y;
     s_bins[threadIdx.x] = bins[(size_t)l * 256 + threadIdx.x];

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(kParseThreads)
 parse_mask_kernel(const uint4* __restrict__ text16, uint64_t n_bytes, uint32_t n_tiles,
                   uint64_t* __restrict__ masks, uint32_t* __restrict__ tile_count, uint32_t* __restrict__ warp_count)
 {
+    pdl_wait();
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t tbyte = (uint64_t)tile * kParseTileBytes + (uint64_t)tid * 64;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(1024)
 parse_scan_kernel(const uint32_t* __restrict__ tile_count, uint32_t n_tiles, uint64_t* __restrict__ tile_prefix,
                   Plan* __restrict__ plan)
 {
+    pdl_wait();
     __shared__ uint32_t s_cnt[kScanChunk];
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total;
@@ -125,6 +127,7 @@ parse_emit_kernel(const uint64_t* __restrict__ masks, const uint64_t* __restrict
                   const uint32_t* __restrict__ warp_count, uint32_t n_tiles, uint64_t byte_base,
                   uint64_t* __restrict__ starts, uint64_t* __restrict__ ends, uint64_t cap_reads, Plan* __restrict__ plan)
 {
+    pdl_wait();
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t n_wt = (uint64_t)n_tiles * kParseWarps;                 // warp-tiles
     const uint64_t wstride = (uint64_t)gridDim.x * (blockDim.x >> 5);
@@ -221,6 +224,7 @@ __global__ void __launch_bounds__(64)
 plan_kernel(const uint8_t* __restrict__ text, uint64_t* __restrict__ starts, uint64_t* __restrict__ ends, PlanArgs a,
             Plan* __restrict__ plan)
 {
+    pdl_wait();
     // one CTA of 64 threads: thread 0 finishes the framing and walks the ladder (sequential by nature, ~10 levels),
     // then thread l computes level l's priority threshold (a 64-step long division each) and clears its segment slots
     __shared__ uint64_t s_lv[kMaxLevels];
@@ -301,11 +305,10 @@ plan_kernel(const uint8_t* __restrict__ text, uint64_t* __restrict__ starts, uin
     // segment s holds the reads with thr[s+1] <= prio < thr[s], a binomial share of the n_reads reads.  A region
     // gets its expectation + 8 sigma + slack (an overflow is detected by the scatter kernel and retried with
     // exact_layout), so no counting pass over the read table is needed.  Thread s owns segment s.
-    __shared__ double s_w[kMaxLevels], s_rem[kMaxLevels];
+    __shared__ double s_w[kMaxLevels];
     __shared__ uint64_t s_cap[kMaxLevels];
     __shared__ uint32_t s_ncta[kMaxLevels];
     __shared__ double s_wsum;
-    __shared__ uint32_t s_given;
     {
         const int nl = s_nl;
         const uint64_t n_reads = plan->n_reads;
@@ -337,34 +340,27 @@ plan_kernel(const uint8_t* __restrict__ text, uint64_t* __restrict__ starts, uin
             s_wsum = wsum;
         }
         __syncthreads();
-        // CTAs: one per segment, the rest in proportion to the expected bases (largest remainders get the leftovers)
+        // CTAs: one per segment, the rest in proportion to the expected bases; leftovers one by one to the segment with
+        // the most expected bases per CTA (greedy = optimal for the slowest segment, which is what the kernel waits for)
         const bool enough = (uint32_t)nl <= a.n_count_ctas;
         const uint32_t spare = enough ? a.n_count_ctas - (uint32_t)nl : 0u;
         uint32_t mine = (l < nl && enough) ? 1u : 0u;
-        double rem = -1.0;
-        if (l < nl && enough && s_wsum > 0.0) {
-            const double share = (double)spare * (f / s_wsum);
-            const uint32_t fl = (uint32_t)share;
-            mine += fl;
-            rem = share - (double)fl;
-        }
-        s_rem[l] = rem;
+        if (l < nl && enough && s_wsum > 0.0) mine += (uint32_t)((double)spare * (f / s_wsum));
         s_ncta[l] = mine;
         __syncthreads();
-        if (l == 0) {
-            uint32_t g = 0;
-            for (int s = 0; s < kMaxLevels; ++s) g += s_ncta[s];
-            s_given = g;
+        if (l == 0 && enough && s_wsum > 0.0) {
+            uint32_t given = 0;
+            for (int s = 0; s < nl; ++s) given += s_ncta[s];
+            for (uint32_t left = a.n_count_ctas > given ? a.n_count_ctas - given : 0u; left > 0; --left) {
+                int best = 0;
+                float load = -1.f;
+                for (int s = 0; s < nl; ++s) {
+                    const float ld = (float)s_w[s] / (float)s_ncta[s];
+                    if (ld > load) { load = ld; best = s; }
+                }
+                ++s_ncta[best];
+            }
         }
-        __syncthreads();
-        if (l < nl && enough && s_wsum > 0.0) {
-            const uint32_t left = a.n_count_ctas > s_given ? a.n_count_ctas - s_given : 0u;     // < nl
-            uint32_t rank = 0;
-            for (int t = 0; t < nl; ++t)
-                if (s_rem[t] > rem || (s_rem[t] == rem && t < l)) ++rank;
-            if (rank < left) ++mine;
-        }
-        s_ncta[l] = mine;
         __syncthreads();
         if (l == 0) {
             uint32_t crun = 0;

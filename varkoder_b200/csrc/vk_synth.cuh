@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256)
 synth_fixed_kernel(uint8_t* __restrict__ out, uint64_t n_out, uint64_t n_reads, uint32_t L, uint32_t last_len,
                    uint64_t seed, uint64_t first_read)
 {
+    pdl_wait();
     const uint64_t rs = 2ull * L + 17ull;
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_out; g += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t rl = g / rs;

@@ -196,6 +196,10 @@ class Engine:
         self._check(self._L.vk_last_timings(self._ctx, ms))
         return dict(zip(TIMING_KEYS, [float(x) for x in ms]))
 
+    def set_fine_timing(self, on):
+        """events between kernel groups (per-kernel split of timings()) on/off; off lets dependent launches overlap"""
+        self._check(self._L.vk_set_fine_timing(self._ctx, 1 if on else 0))
+
     def launch_count(self):
         return int(self._L.vk_launch_count(self._ctx))
 
