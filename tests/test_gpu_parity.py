@@ -392,3 +392,45 @@ def test_u32_and_global_count_kernels_still_exact(monkeypatch, k):
         assert (canon[0] == dsk.canonical_counts(buf, k)).all()
     finally:
         eng.close()
+
+
+def test_batch_of_bembidion_shaped_samples(engine, tmp_path):
+    """BASELINE configs[3] in miniature: several samples with variable read lengths (60..280, 1 % shorter than k, some
+    empty), gzip files, dealt to 'ranks' by size, processed through the batch entry point (threaded inflate -> GPU ->
+    PNG); every level's pixels equal the oracle's and the files carry the reference's names and metadata."""
+    import gzip
+    from PIL import Image
+    from varkoder_b200 import sharding, stages
+    from varkoder_b200.ladder import image_name, ladder
+    table = get_kmer_mapping(7, "varKode")
+    samples, bufs = [], {}
+    for i, n_reads in enumerate([900, 2500, 1400, 3100, 600]):
+        buf = synth.variable(n_reads, seed=500 + i).tobytes()
+        p = tmp_path / f"S{i}.fq.gz"
+        with gzip.open(p, "wb", compresslevel=1) as f:
+            f.write(buf)
+        samples.append(dict(sample=f"S{i}", path=str(p), labels=[f"sp{i % 2}", "genus"], base_sd=0.002 * i))
+        bufs[f"S{i}"] = buf
+    owner, loads = sharding.assign_samples([len(bufs[s["sample"]]) for s in samples], 2)
+    assert sorted(set(owner)) == [0, 1] and abs(loads[0] - loads[1]) <= max(loads) // 2
+    out = tmp_path / "images"
+    seeds = [1000 + i for i in range(len(samples))]
+    stats = stages.images_for_samples(samples, out, table, k=7, mapping_code="varKode", min_bp=20_000, max_bp=None,
+                                      seeds=seeds, threads=3, engine=engine)
+    assert list(stats) == [s["sample"] for s in samples]
+    for i, s in enumerate(samples):
+        buf = bufs[s["sample"]]
+        p = dsk.parse_fastq(buf)
+        levels = ladder(p["nsites_ref"], 20_000, None)
+        assert stats[s["sample"]]["splitting_bp_per_file"] == ",".join(str(x) for x in levels)
+        canon = oracle_levels(buf, 7, seeds[i], levels, p["nsites_ref"])
+        pix = oracle_images(canon, table.lut)
+        for lvl, bp in enumerate(levels):
+            f = out / image_name(s["sample"], bp, "varKode", 7)
+            img = Image.open(f)
+            assert img.mode == "L" and (np.asarray(img) == pix[lvl]).all()
+            assert img.info["varkoderKeywords"] == ";".join(s["labels"]) and img.info["varkoderMapping"] == "varKode"
+    # a sample below min_bp is recorded the way run_clean2img records a split failure
+    small = dict(sample="tiny", path=samples[4]["path"])
+    st = stages.images_for_samples([small], out, table, k=7, min_bp=10**9, max_bp=10**10, engine=engine)
+    assert st["tiny"] == {"failed_step": "split"}

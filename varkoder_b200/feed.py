@@ -1,0 +1,151 @@
+"""Host feed of the image hot path: cleaned ``.fq.gz`` files -> pinned host buffers -> GPU, several samples in flight.
+
+The reference reads ``<int>/clean_reads/<sample>.fq.gz`` (single-member gzip written by pigz,
+varKoder/commands/image.py:529-540) with Python's gzip module, once in ``split_fastq`` (:662-667) and then L more
+times through ``reformat.sh``.  Here every sample is inflated ONCE, by a worker thread (zlib releases the GIL, so N
+threads inflate N samples in parallel -- a single gzip member cannot be split), straight into page-locked memory, and
+handed to the GPU in submission order while the next samples are still inflating.  PNG encoding of finished samples
+runs in the same pool, off the critical path.
+"""
+import os
+import threading
+import zlib
+from collections import deque
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+_CHUNK = 1 << 20
+
+
+def gzip_isize(path):
+    """ISIZE field of the last gzip member: uncompressed size mod 2^32 (a hint for the buffer size)."""
+    with open(path, "rb") as f:
+        f.seek(0, os.SEEK_END)
+        if f.tell() < 18:
+            return 0
+        f.seek(-4, os.SEEK_END)
+        return int.from_bytes(f.read(4), "little")
+
+
+class PinnedBuffer:
+    """A growable page-locked byte buffer (torch pinned memory when CUDA is there, plain numpy otherwise)."""
+
+    def __init__(self, nbytes=0, pinned=True):
+        self.pinned = pinned
+        self._t = None
+        self.array = np.empty(0, dtype=np.uint8)
+        self.reserve(max(int(nbytes), 1))
+
+    def reserve(self, nbytes):
+        if nbytes <= self.array.size:
+            return
+        new = int(nbytes + nbytes // 8 + 4096)
+        old = self.array
+        t = None
+        if self.pinned:
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    t = torch.empty(new, dtype=torch.uint8, pin_memory=True)
+            except Exception:
+                t = None
+        arr = t.numpy() if t is not None else np.empty(new, dtype=np.uint8)
+        if old.size:
+            arr[:old.size] = old
+        self._t, self.array = t, arr
+
+    @property
+    def is_pinned(self):
+        return self._t is not None
+
+
+def inflate_into(path, buf: PinnedBuffer):
+    """Read a FASTQ file (gzip, possibly multi-member, or plain text) into ``buf``; returns the number of bytes."""
+    path = str(path)
+    with open(path, "rb") as f:
+        magic = f.read(2)
+        f.seek(0)
+        if magic != b"\x1f\x8b":
+            n = os.fstat(f.fileno()).st_size
+            buf.reserve(n)
+            got = f.readinto(memoryview(buf.array)[:n]) if n else 0
+            return int(got)
+        hint = gzip_isize(path)
+        buf.reserve(max(hint, _CHUNK))
+        n = 0
+        d = zlib.decompressobj(wbits=31)
+        while True:
+            raw = f.read(_CHUNK)
+            if not raw:
+                break
+            while raw:
+                out = d.decompress(raw, 8 * _CHUNK)
+                if out:
+                    if n + len(out) > buf.array.size:
+                        buf.reserve(max(2 * buf.array.size, n + len(out)))
+                    buf.array[n:n + len(out)] = np.frombuffer(out, dtype=np.uint8)
+                    n += len(out)
+                if d.eof:                                   # next member of a multi-member file (cat of .gz files)
+                    raw = d.unused_data
+                    d = zlib.decompressobj(wbits=31)
+                else:
+                    raw = d.unconsumed_tail
+        tail = d.flush()
+        if tail:
+            if n + len(tail) > buf.array.size:
+                buf.reserve(n + len(tail))
+            buf.array[n:n + len(tail)] = np.frombuffer(tail, dtype=np.uint8)
+            n += len(tail)
+        return n
+
+
+class SampleFeeder:
+    """Iterate ``(index, item, PinnedBuffer, n_bytes)`` over samples in submission order, inflating up to ``depth``
+    samples ahead on ``threads`` worker threads.  Buffers are recycled: hand one back with :meth:`release`."""
+
+    def __init__(self, items, path_of=lambda it: it, threads=None, depth=None, pinned=True):
+        self.items = list(items)
+        self.path_of = path_of
+        self.threads = threads or max(1, min(len(os.sched_getaffinity(0)), 16))
+        self.depth = depth or self.threads + 1
+        self.pinned = pinned
+        self._free = deque()
+        self._lock = threading.Lock()
+        self.pool = ThreadPoolExecutor(max_workers=self.threads, thread_name_prefix="vk-inflate")
+
+    def _job(self, it):
+        with self._lock:
+            buf = self._free.popleft() if self._free else None
+        if buf is None:
+            buf = PinnedBuffer(0, self.pinned)
+        n = inflate_into(self.path_of(it), buf)
+        return buf, n
+
+    def release(self, buf):
+        with self._lock:
+            self._free.append(buf)
+
+    def __iter__(self):
+        pending = deque()
+        nxt = 0
+        try:
+            while nxt < len(self.items) or pending:
+                while nxt < len(self.items) and len(pending) < self.depth:
+                    pending.append((nxt, self.items[nxt], self.pool.submit(self._job, self.items[nxt])))
+                    nxt += 1
+                i, it, fut = pending.popleft()
+                buf, n = fut.result()
+                yield i, it, buf, n
+        finally:
+            for _, _, fut in pending:
+                fut.cancel()
+
+    def close(self):
+        self.pool.shutdown(wait=True, cancel_futures=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
