@@ -275,6 +275,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-concurrent", action="store_true", help="skip the several-samples-in-flight side measurement")
     ap.add_argument("--bases", type=int, default=None, help="debug: smaller sample (invalidates the bench line)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
                     help="c2 = BASELINE configs[1] (the bench line); c3 = configs[2]: 1 Gbp, k=9 varKode, -M 0 (side measurement)")
@@ -378,6 +379,36 @@ def main():
     assert (r2.pixels == res.pixels).all()
     d2h = int(res.pixels.size) + 4096
 
+    # ---- several samples in flight on one GPU (the by-sample batch regime, BASELINE configs[3]): T host threads, each
+    # with its own context, push the same resident sample through the path concurrently.  Not the bench line.
+    conc = None
+    if not args.no_concurrent:
+        T = 4
+        c_steps = max(5, min(args.steps, 100))
+        engs = [Engine(local) for _ in range(T)]
+        for e in engs:
+            e.set_fine_timing(False)
+            e.reads_to_images(dev.data_ptr(), params, table, on_device=True, n_bytes=total, max_levels=len(LEVELS))
+
+        def work(e):
+            for _ in range(c_steps):
+                e.reads_to_images(dev.data_ptr(), params, table, on_device=True, n_bytes=total, max_levels=len(LEVELS))
+
+        th = [threading.Thread(target=work, args=(e,)) for e in engs]
+        barrier()
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        torch.cuda.synchronize()
+        c_ms = 1e3 * (time.perf_counter() - t0)
+        for e in engs:
+            e.close()
+        conc = {"contexts": T, "steps_per_context": c_steps, "ms_per_sample_wall": c_ms / (T * c_steps),
+                "value_this_rank": n_bases * T * c_steps / (c_ms * 1e-3) / 1e9, "unit": "Gbases/s",
+                "note": "same 200 Mbp resident sample through 4 contexts at once (host threads); wall clock; rank-local"}
+
     # ---- N > 1 only: ONE sample of N x 200 Mbp read-sharded over the ranks (BASELINE configs[4] shape): every rank
     # frames and counts its shard, one NCCL all-reduce sums the per-segment histograms, every rank renders.
     sharded = None
@@ -442,6 +473,8 @@ def main():
         }
         if sharded is not None:
             out["read_sharded"] = sharded
+        if conc is not None:
+            out["samples_in_flight"] = conc
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = run_cpu_baseline(host.numpy())
         print(json.dumps(out), flush=True)

@@ -237,50 +237,89 @@ def make_image(infile, outfolder, kmer_mapping, threads=1, overwrite=False, verb
 # ------------------------------------------------------------------------------------------ batch
 def images_for_samples(samples, outfolder, kmer_mapping, k=7, mapping_code="varKode", min_bp=50000, max_bp=None,
                        is_query=False, seeds=None, subfolder_levels=0, overwrite=False, threads=None, engine=None,
-                       on_error=None):
+                       on_error=None, gpu_workers=3, device=None):
     """Steps C-E of run_clean2img for MANY samples (the loop of ImageCommand.process_samples, image.py:1265-1294) on
-    one GPU: samples are inflated ahead by worker threads into pinned memory (varkoder_b200.feed), counted on the GPU in
-    order, and their PNGs are written by the same pool while the next sample is on the GPU.
+    one GPU: samples are inflated ahead by worker threads into pinned memory (varkoder_b200.feed), pushed through the
+    GPU by ``gpu_workers`` threads that each own a context (the path of one sample is a chain of short dependent
+    kernels; three or four samples in flight fill the gaps: 485 -> 680 Gbases/s on 200 Mbp samples, 68 -> 180 on
+    10 Mbp ones, profiles/r01_notes.md), and their PNGs are written by the inflate pool off the critical path.
 
     ``samples``: iterable of dicts ``{"sample": name, "path": clean .fq(.gz), "labels": [...], "base_sd": float}``.
-    ``seeds``: per-sample seeds (default: the sample's position).  Returns ``{sample: stats}`` with the reference's
-    stats keys; a sample with too little data gets ``{"failed_step": "split"}`` exactly as run_clean2img records it
-    (image.py:1020-1027) -- or ``on_error(sample, exc)`` is called when given."""
+    ``seeds``: per-sample seeds (default: the sample's position).  ``engine``: use this one context only.
+    Returns ``{sample: stats}`` (submission order) with the reference's stats keys; a sample with too little data gets
+    ``{"failed_step": "split"}`` exactly as run_clean2img records it (image.py:1020-1027), and ``on_error(sample,
+    exc)`` is called when given."""
+    import threading
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
     from .feed import SampleFeeder
-    eng = engine or default_engine()
     table = as_pixel_table(kmer_mapping, mapping_code)
     samples = list(samples)
+    if engine is not None:
+        gpu_workers = 1
+    if device is None:
+        device = int(os.environ.get("VARKODER_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    tls = threading.local()
+    made = []
+
+    def gpu_job(i, s, buf, n, feeder):
+        eng = engine
+        if eng is None:
+            eng = getattr(tls, "eng", None)
+            if eng is None:
+                eng = tls.eng = Engine(device)
+                made.append(eng)
+        seed = seeds[i] if seeds is not None else i
+        params = Params(k=int(k), min_bp=int(min_bp), max_bp=None if max_bp is None else int(max_bp),
+                        is_query=bool(is_query), seed=seed)
+        t0 = time.perf_counter()
+        try:
+            res = eng.reads_to_images(buf.array[:n], params, table)
+            tm = eng.timings()
+        finally:
+            feeder.release(buf)
+        return res, tm, time.perf_counter() - t0
+
     all_stats = OrderedDict()
     png_jobs = []
-    with SampleFeeder(samples, path_of=lambda s: s["path"], threads=threads) as feeder:
-        for i, s, buf, n in feeder:
-            name = str(s["sample"])
-            seed = seeds[i] if seeds is not None else i
-            params = Params(k=int(k), min_bp=int(min_bp), max_bp=None if max_bp is None else int(max_bp),
-                            is_query=bool(is_query), seed=seed)
-            t0 = time.perf_counter()
-            res = eng.reads_to_images(buf.array[:n], params, table)
-            feeder.release(buf)
-            if res.status != 0:
-                err = LessThanMinimumData()
-                if on_error is not None:
-                    on_error(s, err)
-                all_stats[name] = OrderedDict(failed_step="split")
+
+    def finish(s, res, tm, dt, feeder):
+        name = str(s["sample"])
+        if res.status != 0:
+            if on_error is not None:
+                on_error(s, LessThanMinimumData())
+            all_stats[name] = OrderedDict(failed_step="split")
+            return
+        stats = OrderedDict()
+        stats["splitting_time"] = (tm["upload"] + tm["parse"] + tm["plan_bucket"]) / 1e3
+        stats["splitting_bp_per_file"] = ",".join(str(x) for x in res.levels)
+        stats[str(k) + "mer_counting_time"] = (tm["count"] + tm["reduce_fold"]) / 1e3
+        stats["k" + str(k) + "_img_time"] = dt
+        all_stats[name] = stats
+        for lvl, bp in enumerate(res.levels):
+            outfile = image_name(name, bp, mapping_code, k)
+            folder = _image_folder(outfolder, outfile, subfolder_levels)
+            if not overwrite and (folder / outfile).is_file():
                 continue
-            tm = eng.timings()
-            stats = OrderedDict()
-            stats["splitting_time"] = (tm["upload"] + tm["parse"] + tm["plan_bucket"]) / 1e3
-            stats["splitting_bp_per_file"] = ",".join(str(x) for x in res.levels)
-            stats[str(k) + "mer_counting_time"] = (tm["count"] + tm["reduce_fold"]) / 1e3
-            stats["k" + str(k) + "_img_time"] = time.perf_counter() - t0
-            all_stats[name] = stats
-            for lvl, bp in enumerate(res.levels):
-                outfile = image_name(name, bp, mapping_code, k)
-                folder = _image_folder(outfolder, outfile, subfolder_levels)
-                if not overwrite and (folder / outfile).is_file():
-                    continue
-                png_jobs.append(feeder.pool.submit(write_png, res.pixels[lvl].copy(), folder / outfile,
-                                                   s.get("labels", ()), s.get("base_sd", 0), QUAL_THRESH, mapping_code))
-        for j in png_jobs:
-            j.result()
+            png_jobs.append(feeder.pool.submit(write_png, res.pixels[lvl].copy(), folder / outfile,
+                                               s.get("labels", ()), s.get("base_sd", 0), QUAL_THRESH, mapping_code))
+
+    gpu_pool = ThreadPoolExecutor(max_workers=max(1, int(gpu_workers)), thread_name_prefix="vk-gpu")
+    try:
+        with SampleFeeder(samples, path_of=lambda s: s["path"], threads=threads) as feeder:
+            inflight = deque()
+            for i, s, buf, n in feeder:
+                inflight.append((s, gpu_pool.submit(gpu_job, i, s, buf, n, feeder)))
+                while len(inflight) > gpu_workers:
+                    s0, fut = inflight.popleft()
+                    finish(s0, *fut.result(), feeder)
+            while inflight:
+                s0, fut = inflight.popleft()
+                finish(s0, *fut.result(), feeder)
+            for j in png_jobs:
+                j.result()
+    finally:
+        gpu_pool.shutdown(wait=True)
+        for e in made:
+            e.close()
     return all_stats
