@@ -15,6 +15,7 @@
 namespace vk {
 
 constexpr int kBucketThreads = 256;
+constexpr int kBucketItems = 4;      // reads per thread and iteration of the scatter kernel
 
 // One pass: scatter (start, len) entries into their segment's region, count reads and bases per segment.
 // Regions were sized from the expected segment shares by plan_kernel (vk_parse.cuh); a read that does not fit
@@ -26,7 +27,8 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
 {
     pdl_wait();
     constexpr uint32_t FULL = 0xffffffffu;
-    __shared__ uint32_t s_cnt[kMaxLevels], s_len[kMaxLevels], s_all[kMaxLevels];
+    __shared__ uint32_t s_cnt[kMaxLevels], s_all[kMaxLevels];
+    __shared__ unsigned long long s_len[kMaxLevels];
     __shared__ unsigned long long s_base[kMaxLevels];
     __shared__ uint64_t s_thr[kMaxLevels], s_begin[kMaxLevels], s_cap[kMaxLevels];
     __shared__ uint32_t s_long;
@@ -41,49 +43,66 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
         s_cap[threadIdx.x] = plan->seg_cap[threadIdx.x];
     }
     if (threadIdx.x == 0) s_long = 0;
-    for (uint64_t r0 = (uint64_t)blockIdx.x * blockDim.x; r0 < n_reads; r0 += per_iter) {
+    // kBucketItems reads per thread and iteration: their table loads are in flight together, and one round trip of the
+    // global cursors serves 1024 reads (the kernel is latency-bound: ~1 iteration per CTA at 200 Mbp)
+    for (uint64_t r0 = (uint64_t)blockIdx.x * (blockDim.x * kBucketItems); r0 < n_reads; r0 += per_iter * kBucketItems) {
         if (threadIdx.x < kMaxLevels) { s_cnt[threadIdx.x] = 0; s_len[threadIdx.x] = 0; }
         __syncthreads();
-        const uint64_t r = r0 + threadIdx.x;
-        int seg = -1;
-        uint32_t len32 = 0;
-        uint64_t entry = 0;
-        if (r < n_reads) {
-            const uint64_t st = starts[r];
-            const uint64_t len = ends[r] - st;
-            if (len > kEntryLenMask) atomicAdd(&s_long, 1u);
-            else if (len >= (uint64_t)k) {
-                const uint64_t h = prio64(seed, read_index_base + r);
-                int c = 0;
-                while (c < nl && (s_all[c] || h < s_thr[c])) ++c;
-                seg = c - 1;
-                if (seg >= 0) {
-                    len32 = (uint32_t)len;
-                    entry = ((st - text_base) << kEntryLenBits) | len;
+        uint64_t st[kBucketItems], en[kBucketItems];
+#pragma unroll
+        for (int i = 0; i < kBucketItems; ++i) {
+            const uint64_t r = r0 + (uint64_t)i * blockDim.x + threadIdx.x;
+            st[i] = r < n_reads ? starts[r] : 0;
+            en[i] = r < n_reads ? ends[r] : 0;
+        }
+        int seg[kBucketItems];
+        uint32_t rank[kBucketItems];
+        uint64_t entry[kBucketItems];
+#pragma unroll
+        for (int i = 0; i < kBucketItems; ++i) {
+            const uint64_t r = r0 + (uint64_t)i * blockDim.x + threadIdx.x;
+            seg[i] = -1;
+            entry[i] = 0;
+            uint32_t len32 = 0;
+            if (r < n_reads) {
+                const uint64_t len = en[i] - st[i];
+                if (len > kEntryLenMask) atomicAdd(&s_long, 1u);
+                else if (len >= (uint64_t)k) {
+                    const uint64_t h = prio64(seed, read_index_base + r);
+                    int c = 0;
+                    while (c < nl && (s_all[c] || h < s_thr[c])) ++c;
+                    seg[i] = c - 1;
+                    if (seg[i] >= 0) {
+                        len32 = (uint32_t)len;
+                        entry[i] = ((st[i] - text_base) << kEntryLenBits) | len;
+                    }
                 }
             }
+            // warp-aggregated: one shared-memory atomic per (warp, segment) instead of one per read
+            const uint32_t peers = __match_any_sync(FULL, seg[i]);
+            const uint32_t lsum = __reduce_add_sync(peers, len32);               // 32 x 2^24 fits 32 bits
+            const int leader = __ffs(peers) - 1;
+            uint32_t wbase = 0;
+            if ((int)lane == leader && seg[i] >= 0) {
+                wbase = atomicAdd(&s_cnt[seg[i]], (uint32_t)__popc(peers));
+                atomicAdd(&s_len[seg[i]], (unsigned long long)lsum);
+            }
+            wbase = __shfl_sync(peers, wbase, leader);
+            rank[i] = wbase + __popc(peers & ((1u << lane) - 1u));
         }
-        // warp-aggregated: one shared-memory atomic per (warp, segment) instead of one per read
-        const uint32_t peers = __match_any_sync(FULL, seg);
-        const uint32_t lsum = __reduce_add_sync(peers, len32);                   // 32 x 2^24 fits 32 bits
-        const int leader = __ffs(peers) - 1;
-        uint32_t wbase = 0;
-        if ((int)lane == leader && seg >= 0) {
-            wbase = atomicAdd(&s_cnt[seg], (uint32_t)__popc(peers));
-            atomicAdd(&s_len[seg], lsum);                                       // 256 x 2^24 fits 32 bits
-        }
-        wbase = __shfl_sync(peers, wbase, leader);
-        const uint32_t rank = wbase + __popc(peers & ((1u << lane) - 1u));
         __syncthreads();
         if (threadIdx.x < kMaxLevels && s_cnt[threadIdx.x]) {
             s_base[threadIdx.x] = atomicAdd(&plan->seg_reads[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
-            atomicAdd(&plan->seg_bases[threadIdx.x], (unsigned long long)s_len[threadIdx.x]);
+            atomicAdd(&plan->seg_bases[threadIdx.x], s_len[threadIdx.x]);
         }
         __syncthreads();
-        if (seg >= 0) {
-            const uint64_t slot = s_base[seg] + rank;
-            if (slot < s_cap[seg]) sorted[s_begin[seg] + slot] = entry;
-            else plan->bucket_overflow = 1u;
+#pragma unroll
+        for (int i = 0; i < kBucketItems; ++i) {
+            if (seg[i] >= 0) {
+                const uint64_t slot = s_base[seg[i]] + rank[i];
+                if (slot < s_cap[seg[i]]) sorted[s_begin[seg[i]] + slot] = entry[i];
+                else plan->bucket_overflow = 1u;
+            }
         }
         __syncthreads();
     }

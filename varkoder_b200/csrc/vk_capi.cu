@@ -244,7 +244,8 @@ void enqueue_count(vk_ctx* c, const vk_params* p, unsigned long long* seg_hist, 
     const int k = p->k;
     const uint32_t nk = 1u << (2 * k);
     if (k <= 7 || (k == 8 && c->use_count16)) c->slabs.ensure((size_t)c->n_sms * c->count_ctas_per_sm * nk);
-    const int bgrid = (int)std::min<uint64_t>((n_reads_bound + kBucketThreads - 1) / kBucketThreads + 1, (uint64_t)c->n_sms * 8);
+    const int bgrid = (int)std::min<uint64_t>((n_reads_bound + kBucketThreads * kBucketItems - 1) / (kBucketThreads * kBucketItems) + 1,
+                                             (uint64_t)c->n_sms * 8);
     launch(c, bucket_scatter_kernel, dim3(bgrid), dim3(kBucketThreads), 0, c->starts.p, c->ends.p, k, p->seed, p->read_index_base, 0,
                                                                   c->sorted.p, c->plan_d);
     CU(cudaGetLastError());

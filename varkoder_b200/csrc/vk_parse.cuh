@@ -145,7 +145,7 @@ parse_emit_kernel(const uint64_t* __restrict__ masks, const uint64_t* __restrict
         pref_nx = tile_prefix[tile];
     }
     for (; g < n_wt; g += wstride) {
-        uint64_t m = m_nx;
+        const uint64_t m = m_nx;
         const uint32_t wc = wc_nx;
         const uint64_t pref = pref_nx;
         {
@@ -158,30 +158,44 @@ parse_emit_kernel(const uint64_t* __restrict__ masks, const uint64_t* __restrict
             }
         }
         const uint32_t woff = __reduce_add_sync(0xffffffffu, wc);
-        const uint32_t cnt = __popcll(m);
+        uint32_t w0 = (uint32_t)m, w1 = (uint32_t)(m >> 32);
+        const uint32_t cnt = __popc(w0) + __popc(w1);
         uint32_t incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= (uint32_t)d) incl += t;
         }
-        uint64_t line = pref + woff + (incl - cnt);
-        const uint64_t pos0 = byte_base + g * 2048 + (uint64_t)lane * 64;
-        while (m) {
-            const int j = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            const uint64_t pos = pos0 + j;
-            const uint32_t ph = (uint32_t)line & 3u;
-            const uint64_t r = line >> 2;
-            if (ph == 0) {                      // header line ends: the sequence line starts at pos + 1
-                sum_s += pos + 1;
-                if (r < cap_reads) starts[r] = pos + 1; else overflow = 1;
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        // everything per newline in 32 bits, relative to the warp-tile: line index = line_base + q, byte = tile0 + rel
+        const uint64_t line_base = pref + woff;                        // warp-uniform
+        const uint64_t r_base = line_base >> 2;
+        uint32_t q = ((uint32_t)line_base & 3u) + (incl - cnt);        // (line index of this lane's first newline) - 4 r_base
+        const uint64_t tile0 = byte_base + g * 2048;
+        const bool fits = r_base + ((((uint32_t)line_base & 3u) + total) >> 2) < cap_reads;      // warp-uniform
+        if (!fits) overflow = 1;
+        uint64_t* const ps = starts + r_base;
+        uint64_t* const pe = ends + r_base;
+        uint32_t ss = 0, se = 0, ns = 0, ne = 0;                       // sums of rel (+1) and counts, this tile
+        const uint32_t rel0 = lane * 64u;
+        while (w0 | w1) {                                              // one trip per newline of the busiest lane
+            const bool lo = w0 != 0;
+            const uint32_t w = lo ? w0 : w1;
+            const uint32_t rel = rel0 + (lo ? 0u : 32u) + (uint32_t)__ffs(w) - 1u;
+            const uint32_t cleared = w & (w - 1);
+            if (lo) w0 = cleared; else w1 = cleared;
+            const uint32_t ph = q & 3u, rr = q >> 2;
+            if (ph == 0) {                      // header line ends: the sequence line starts at the next byte
+                ss += rel + 1; ++ns;
+                if (fits) ps[rr] = tile0 + rel + 1;
             } else if (ph == 1) {               // sequence line ends
-                sum_e += pos;
-                if (r < cap_reads) ends[r] = pos; else overflow = 1;
+                se += rel; ++ne;
+                if (fits) pe[rr] = tile0 + rel;
             }
-            ++line;
+            ++q;
         }
+        sum_s += (uint64_t)ss + (uint64_t)ns * tile0;
+        sum_e += (uint64_t)se + (uint64_t)ne * tile0;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -268,8 +282,8 @@ plan_kernel(const uint8_t* __restrict__ text, uint64_t* __restrict__ starts, uin
             while (s_lv[nl - 1] > a.p.min_bp && nl < kMaxLevels) {
                 const uint64_t oneless = s_lv[nl - 1] - 1;
                 if (oneless == 0) break;                      // the reference would raise in log10(0); min_bp = 0 only
-                uint64_t p10 = 1;
-                while (oneless / p10 >= 10) p10 *= 10;        // 10^floor(log10(oneless))
+                uint64_t p10 = 1;                             // 10^floor(log10(oneless)), without a division per digit
+                while (p10 <= 1000000000000000000ull && p10 * 10 <= oneless) p10 *= 10;
                 const uint64_t fd = oneless / p10;
                 const uint64_t mult = fd >= 5 ? 5 : (fd >= 2 ? 2 : 1);   // largest of {1,2,5} <= first digit
                 s_lv[nl++] = mult * p10;
