@@ -121,7 +121,41 @@ parse_scan_kernel(const uint32_t* __restrict__ tile_count, uint32_t n_tiles, uin
 }
 
 // K1b: one WARP per 2 KiB of text (32 masks); no block-level synchronisation.
-// line index of a newline = tile prefix + newlines in earlier warps of the tile + newlines in earlier lanes + rank.
+// A warp walks a CONTIGUOUS range of warp-tiles, so the line index simply runs on from tile to tile (the tile prefix
+// and the counts of the earlier warps of the tile are looked up once per warp, not per tile) and the masks are read
+// through one pointer that advances by 256 bytes.  Everything per newline is 32-bit and relative to the warp-tile:
+// line index = line_base + q, byte = tile0 + rel.  nsites = sum(ends) - sum(starts) is accumulated as one difference
+// (added to plan->sum_ends; plan_kernel only ever uses sum_ends - sum_starts).
+__device__ __forceinline__ uint32_t count_phase(uint32_t q0, uint32_t cnt, uint32_t ph)
+{
+    // #{ i in [q0, q0 + cnt) : i mod 4 == ph }
+    return ((q0 + cnt + 3u - ph) >> 2) - ((q0 + 3u - ph) >> 2);
+}
+
+template <bool STORE>
+__device__ __forceinline__ int32_t emit_tile(uint32_t w0, uint32_t w1, uint32_t q, uint32_t rel0, uint64_t tile0,
+                                             uint64_t* __restrict__ ps, uint64_t* __restrict__ pe)
+{
+    int32_t d = 0;                              // sum over sequence ends of rel - sum over sequence starts of rel
+    while (w0 | w1) {                           // one trip per newline of the busiest lane
+        const bool lo = w0 != 0;
+        const uint32_t w = lo ? w0 : w1;
+        const uint32_t rel = rel0 + (lo ? 0u : 32u) + (uint32_t)__ffs(w) - 1u;
+        const uint32_t cleared = w & (w - 1);
+        if (lo) w0 = cleared; else w1 = cleared;
+        const uint32_t ph = q & 3u, rr = q >> 2;
+        if (ph == 0) {                          // header line ends: the sequence line starts at the next byte
+            d -= (int32_t)(rel + 1);
+            if (STORE) ps[rr] = tile0 + rel + 1;
+        } else if (ph == 1) {                   // sequence line ends
+            d += (int32_t)rel;
+            if (STORE) pe[rr] = tile0 + rel;
+        }
+        ++q;
+    }
+    return d;
+}
+
 __global__ void __launch_bounds__(256)
 parse_emit_kernel(const uint64_t* __restrict__ masks, const uint64_t* __restrict__ tile_prefix,
                   const uint32_t* __restrict__ warp_count, uint32_t n_tiles, uint64_t byte_base,
@@ -130,82 +164,55 @@ parse_emit_kernel(const uint64_t* __restrict__ masks, const uint64_t* __restrict
     pdl_wait();
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t n_wt = (uint64_t)n_tiles * kParseWarps;                 // warp-tiles
-    const uint64_t wstride = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    uint64_t sum_s = 0, sum_e = 0;
+    const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    const uint64_t per = (n_wt + n_warps - 1) / n_warps;
+    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t g0 = wid * per, g1 = g0 + per < n_wt ? g0 + per : n_wt;
+    int64_t diff = 0;
     uint32_t overflow = 0;
-    // the loads of the next warp-tile are issued before the current one is decoded (a warp walks ~5 tiles; without
-    // this every tile exposed a full L2 round trip: profiles/r01b_ncu_full.txt)
-    uint64_t g = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    uint64_t m_nx = 0, pref_nx = 0;
-    uint32_t wc_nx = 0;
-    if (g < n_wt) {
-        const uint32_t tile = (uint32_t)(g / kParseWarps), wit = (uint32_t)(g % kParseWarps);
-        m_nx = masks[g * 32 + lane];
-        wc_nx = lane < wit ? warp_count[(uint64_t)tile * kParseWarps + lane] : 0u;
-        pref_nx = tile_prefix[tile];
-    }
-    for (; g < n_wt; g += wstride) {
-        const uint64_t m = m_nx;
-        const uint32_t wc = wc_nx;
-        const uint64_t pref = pref_nx;
-        {
-            const uint64_t gn = g + wstride;
-            if (gn < n_wt) {
-                const uint32_t tile = (uint32_t)(gn / kParseWarps), wit = (uint32_t)(gn % kParseWarps);
-                m_nx = masks[gn * 32 + lane];
-                wc_nx = lane < wit ? warp_count[(uint64_t)tile * kParseWarps + lane] : 0u;
-                pref_nx = tile_prefix[tile];
-            }
-        }
-        const uint32_t woff = __reduce_add_sync(0xffffffffu, wc);
-        uint32_t w0 = (uint32_t)m, w1 = (uint32_t)(m >> 32);
-        const uint32_t cnt = __popc(w0) + __popc(w1);
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (uint32_t)d) incl += t;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        // everything per newline in 32 bits, relative to the warp-tile: line index = line_base + q, byte = tile0 + rel
-        const uint64_t line_base = pref + woff;                        // warp-uniform
-        const uint64_t r_base = line_base >> 2;
-        uint32_t q = ((uint32_t)line_base & 3u) + (incl - cnt);        // (line index of this lane's first newline) - 4 r_base
-        const uint64_t tile0 = byte_base + g * 2048;
-        const bool fits = r_base + ((((uint32_t)line_base & 3u) + total) >> 2) < cap_reads;      // warp-uniform
-        if (!fits) overflow = 1;
-        uint64_t* const ps = starts + r_base;
-        uint64_t* const pe = ends + r_base;
-        uint32_t ss = 0, se = 0, ns = 0, ne = 0;                       // sums of rel (+1) and counts, this tile
+    if (g0 < g1) {
+        // line index of the first newline of warp-tile g0
+        const uint32_t tile = (uint32_t)(g0 / kParseWarps), wit = (uint32_t)(g0 % kParseWarps);
+        const uint32_t wc = lane < wit ? warp_count[(uint64_t)tile * kParseWarps + lane] : 0u;
+        uint64_t line_base = tile_prefix[tile] + __reduce_add_sync(0xffffffffu, wc);
+        const uint64_t* mp = masks + g0 * 32 + lane;
+        uint64_t m_nx = *mp;
         const uint32_t rel0 = lane * 64u;
-        while (w0 | w1) {                                              // one trip per newline of the busiest lane
-            const bool lo = w0 != 0;
-            const uint32_t w = lo ? w0 : w1;
-            const uint32_t rel = rel0 + (lo ? 0u : 32u) + (uint32_t)__ffs(w) - 1u;
-            const uint32_t cleared = w & (w - 1);
-            if (lo) w0 = cleared; else w1 = cleared;
-            const uint32_t ph = q & 3u, rr = q >> 2;
-            if (ph == 0) {                      // header line ends: the sequence line starts at the next byte
-                ss += rel + 1; ++ns;
-                if (fits) ps[rr] = tile0 + rel + 1;
-            } else if (ph == 1) {               // sequence line ends
-                se += rel; ++ne;
-                if (fits) pe[rr] = tile0 + rel;
+        for (uint64_t g = g0; g < g1; ++g) {
+            const uint64_t m = m_nx;
+            mp += 32;
+            if (g + 1 < g1) m_nx = *mp;                                   // next tile's masks in flight while this one is decoded
+            const uint32_t w0 = (uint32_t)m, w1 = (uint32_t)(m >> 32);
+            const uint32_t cnt = __popc(w0) + __popc(w1);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += t;
             }
-            ++q;
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t lb = (uint32_t)line_base & 3u;
+            const uint64_t r_base = line_base >> 2;
+            const uint32_t q = lb + (incl - cnt);                          // (line index of this lane's first newline) - 4 r_base
+            const uint64_t tile0 = byte_base + g * 2048;
+            const bool fits = r_base + ((lb + total) >> 2) < cap_reads;    // warp-uniform
+            int32_t d;
+            if (fits) d = emit_tile<true>(w0, w1, q, rel0, tile0, starts + r_base, ends + r_base);
+            else { d = emit_tile<false>(w0, w1, q, rel0, tile0, nullptr, nullptr); overflow = 1; }
+            // + tile0 * (#ends - #starts), - #starts for the "+1"s already taken above via rel + 1
+            const int32_t dn = (int32_t)count_phase(q, cnt, 1) - (int32_t)count_phase(q, cnt, 0);
+            diff += (int64_t)d + (int64_t)dn * (int64_t)tile0;
+            line_base += total;
         }
-        sum_s += (uint64_t)ss + (uint64_t)ns * tile0;
-        sum_e += (uint64_t)se + (uint64_t)ne * tile0;
     }
+    uint64_t sum = (uint64_t)diff;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
-        sum_s += __shfl_xor_sync(0xffffffffu, sum_s, d);
-        sum_e += __shfl_xor_sync(0xffffffffu, sum_e, d);
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
         overflow |= __shfl_xor_sync(0xffffffffu, overflow, d);
     }
     if (lane == 0) {
-        if (sum_s) atomicAdd((unsigned long long*)&plan->sum_starts, (unsigned long long)sum_s);
-        if (sum_e) atomicAdd((unsigned long long*)&plan->sum_ends, (unsigned long long)sum_e);
+        if (sum) atomicAdd((unsigned long long*)&plan->sum_ends, (unsigned long long)sum);
         if (overflow) atomicOr(&plan->table_overflow, 1u);
     }
 }
