@@ -1,4 +1,4 @@
-// vk_bucket.cuh -- K1b: seeded nested sub-sampling as a counting sort of the read table by ladder segment.
+// vk_bucket.cuh -- K1c: seeded nested sub-sampling as a one-pass scatter of the read table into ladder segments.
 //
 // Stands in for the L independent `reformat.sh samplebasestarget=... sampleseed=seed+i` runs of
 // run_parallel_reformats (varKoder/commands/image.py:577-627).  The Java RNG stream cannot be reproduced, so

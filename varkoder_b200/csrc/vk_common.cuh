@@ -8,7 +8,7 @@ namespace vk {
 
 constexpr int kMaxLevels = VK_MAX_LEVELS;
 constexpr int kNumSMs = 148;              // B200
-constexpr uint32_t kUnitReads = 256;      // reads a warp takes from its segment at a time (count kernel)
+constexpr uint32_t kUnitReads = 256;      // granularity of the segment regions of the sorted read table
 constexpr int kEntryLenBits = 24;         // sorted read entry = start << 24 | len
 constexpr uint64_t kEntryLenMask = (1ull << kEntryLenBits) - 1;
 constexpr uint64_t kThrAll = ~0ull;
@@ -30,10 +30,9 @@ struct Plan {
     uint64_t level_bp[kMaxLevels];
     uint64_t level_thr[kMaxLevels];   // read is in level l iff prio < thr[l]; kThrAll + level_all => every read
     uint32_t level_all[kMaxLevels];
-    // ---- bucket (K1b): segment s = reads in levels 0..s and not in s+1
+    // ---- bucket (K1c): segment s = reads in levels 0..s and not in s+1
     unsigned long long seg_reads[kMaxLevels];
     unsigned long long seg_bases[kMaxLevels];
-    unsigned long long seg_cursor[kMaxLevels];   // (unused)
     unsigned long long seg_next[kMaxLevels];     // dynamic unit counters of the count kernel
     uint64_t seg_begin[kMaxLevels + 1];          // offsets into the sorted entry array
     uint32_t seg_cta_begin[kMaxLevels + 1];      // CTA ranges of the count kernel
