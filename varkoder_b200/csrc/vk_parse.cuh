@@ -53,7 +53,7 @@ parse_mask_kernel(const uint4* __restrict__ text16, uint64_t n_bytes, uint32_t n
 #pragma unroll
             for (int i = 0; i < kParseWordsPerThread; ++i) {
                 const uint64_t b = tbyte + 16ull * i;
-                w[i] = (b < n_bytes) ? __ldg(text16 + (b >> 4)) : make_uint4(0, 0, 0, 0);
+                w[i] = (b < n_bytes) ? __ldcs(text16 + (b >> 4)) : make_uint4(0, 0, 0, 0);      // streaming: the text must not evict the masks
             }
 #pragma unroll
             for (int i = 0; i < kParseWordsPerThread; ++i) m |= (uint64_t)nl16(w[i]) << (16 * i);
