@@ -262,7 +262,7 @@ def workload_config():
     return {"workload": "configs[1]: single 200 Mbp synthetic sample per GPU, read length 150, k=7, cgr mapping, "
                         "full subsample ladder 200M..500K (9 levels) from one pass",
             "bases_per_step_per_gpu": N_BASES, "bytes_per_base": round(BYTES_PER_BASE, 4), "k": K, "mapping": MAPPING,
-            "levels": len(LEVELS), "l2_policy": "input (423 MB) larger than L2 (126 MB); no flush needed",
+            "levels": len(LEVELS), "l2_policy": "input (423 MB) larger than L2 (126 MB), and consecutive steps read two different samples alternately",
             "parallelism": "by-sample, one process per GPU, no collective"}
 
 
@@ -312,12 +312,22 @@ def main():
     table = get_kmer_mapping(K, MAPPING)
     params = Params(k=K, min_bp=MIN_BP, max_bp=MAX_BP, seed=1 + rank)
     total = synth.fixed_total_bytes(n_bases, READ_LEN)
-    dev = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
-    first_read = rank * ((n_bases + READ_LEN - 1) // READ_LEN)           # every rank gets its own sample
-    assert eng.synth_fastq(dev.data_ptr(), dev.numel(), n_bases, READ_LEN, seed=20260118 + 2000, first_read=first_read) == total
+    # two different samples per rank, used alternately: whatever one step leaves in the 126 MB L2 (the tail of a
+    # 423 MB text) is of no use to the next step, which reads the other sample
+    n_reads_sample = (n_bases + READ_LEN - 1) // READ_LEN
+    devs = []
+    for j in range(2):
+        d = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+        first_read = (2 * rank + j) * n_reads_sample                      # every rank gets its own samples
+        assert eng.synth_fastq(d.data_ptr(), d.numel(), n_bases, READ_LEN, seed=20260118 + 2000, first_read=first_read) == total
+        devs.append(d)
+    dev = devs[0]
+    step_no = [0]
 
     def step_device():
-        r = eng.reads_to_images(dev.data_ptr(), params, table, on_device=True, n_bytes=total, max_levels=len(LEVELS))
+        d = devs[step_no[0] & 1]
+        step_no[0] += 1
+        r = eng.reads_to_images(d.data_ptr(), params, table, on_device=True, n_bytes=total, max_levels=len(LEVELS))
         return r, eng.timings()
 
     def barrier():
@@ -376,7 +386,8 @@ def main():
         r2 = eng.reads_to_images(host, params, table, max_levels=len(LEVELS))
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
-    assert (r2.pixels == res.pixels).all()
+    res0 = eng.reads_to_images(devs[0].data_ptr(), params, table, on_device=True, n_bytes=total, max_levels=len(LEVELS))
+    assert (r2.pixels == res0.pixels).all()                # host-buffer path == device-resident path, same sample
     d2h = int(res.pixels.size) + 4096
 
     # ---- several samples in flight on one GPU (the by-sample batch regime, BASELINE configs[3]): T host threads, each
