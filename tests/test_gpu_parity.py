@@ -434,3 +434,57 @@ def test_batch_of_bembidion_shaped_samples(engine, tmp_path):
     small = dict(sample="tiny", path=samples[4]["path"])
     st = stages.images_for_samples([small], out, table, k=7, min_bp=10**9, max_bp=10**10, engine=engine)
     assert st["tiny"] == {"failed_step": "split"}
+
+
+def test_full_size_properties_config3(engine):
+    """BASELINE config 3 shape (1 Gbp, k=9, varKode, -M 0: 11 levels; the 4^9 histogram lives in L2) on device-resident
+    synthetic reads: ladder, nesting, reverse-complement symmetry, window conservation, rank-transform invariants, exact
+    agreement with the CPU oracle on a prefix, and exact additivity over read shards."""
+    import torch
+    k, L, n_bases = 9, 150, 1_000_000_000
+    table = get_kmer_mapping(k, "varKode")
+    total = synth.fixed_total_bytes(n_bases, L)
+    dev = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+    assert engine.synth_fastq(dev.data_ptr(), dev.numel(), n_bases, L, seed=909) == total
+    params = Params(k=k, min_bp=500_000, max_bp=None, seed=3)
+    res = engine.reads_to_images(dev.data_ptr(), params, table, on_device=True, n_bytes=total, want_canon=True)
+    assert res.nsites == n_bases
+    assert res.levels == [1_000_000_000, 500_000_000, 200_000_000, 100_000_000, 50_000_000, 20_000_000, 10_000_000,
+                          5_000_000, 2_000_000, 1_000_000, 500_000]
+    canon = res.canon
+    assert (canon[:-1] >= canon[1:]).all()
+    from varkoder_b200.mapping import revcomp_index
+    rc = revcomp_index(np.arange(4 ** k), k)
+    assert (canon[:, rc] == canon).all()
+    windows = canon.sum(axis=1) // 2                             # k odd: no palindromes
+    for lvl in range(len(res.levels)):
+        full = res.level_bases[lvl] - (k - 1) * res.level_reads[lvl]
+        assert 0.96 * full <= windows[lvl] <= full
+        assert abs(res.level_bases[lvl] - res.levels[lvl]) <= 0.05 * res.levels[lvl]
+    assert res.level_bases[0] == n_bases
+    assert res.pixels.shape == (11, 363, 363) and (res.pixels.max(axis=(1, 2)) == 255).all()
+    for lvl in (0, 10):
+        assert (res.pixels[lvl] == oimg.image_exact(canon[lvl], table.lut)).all()
+    # two read shards of the same buffer, counted separately with the sample-wide ladder, add up exactly
+    n_reads = res.n_reads
+    cut_reads = (n_reads // 3) & ~15                          # record size 317 x 16: the shard stays 16-byte aligned
+    cut = cut_reads * synth.record_size(L)
+    nk = 4 ** k
+    segs = []
+    for (off, nb, base) in ((0, cut, 0), (cut, total - cut, cut_reads)):
+        engine.attach(dev.data_ptr() + off, nb)
+        engine.parse()
+        seg = torch.zeros(64 * nk, dtype=torch.int64, device="cuda")
+        r = engine.count(Params(k=k, min_bp=500_000, max_bp=None, seed=3, read_index_base=base, nsites_override=n_bases),
+                         seg.data_ptr())
+        assert r.levels == res.levels
+        segs.append(seg)
+    both = segs[0] + segs[1]
+    torch.cuda.synchronize()
+    canon2, _ = engine.render(None, k, len(res.levels), both.data_ptr())
+    assert (canon2 == canon).all()
+    # a 1 Mbp prefix, counted by the CPU oracle
+    nb = synth.fixed_total_bytes(1_000_050, L)
+    head = dev[:nb].cpu().numpy().tobytes()
+    r2 = engine.reads_to_images(head, Params(k=k, min_bp=0, max_bp=None, is_query=True), table, want_canon=True)
+    assert (r2.canon[0] == dsk.canonical_counts(head, k, threads=0)).all()

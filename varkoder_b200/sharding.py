@@ -99,8 +99,9 @@ def sharded_count(engine, shard_bytes, params: Params, seg_hist, group=None):
     base, total, per_rank = _exchange_shard_stats(st["n_reads"], st["nsites"], group)
     p = replace(params, read_index_base=base, nsites_override=total)      # 0 bases in total: every shard is empty too
     res = engine.count(p, seg_hist.data_ptr())
-    # the one exchange step of the path
-    dist.all_reduce(seg_hist.view(torch.int64), op=dist.ReduceOp.SUM, group=group)
+    # the one exchange step of the path; every rank derives the same ladder, so only its levels are exchanged
+    n_words = max(len(res.levels), 1) * nk
+    dist.all_reduce(seg_hist.view(torch.int64)[:n_words], op=dist.ReduceOp.SUM, group=group)
     # realised reads / bases per level, summed over shards (same reduction, tiny)
     nl = len(res.levels)
     dev = seg_hist.device
