@@ -237,12 +237,14 @@ def make_image(infile, outfolder, kmer_mapping, threads=1, overwrite=False, verb
 # ------------------------------------------------------------------------------------------ batch
 def images_for_samples(samples, outfolder, kmer_mapping, k=7, mapping_code="varKode", min_bp=50000, max_bp=None,
                        is_query=False, seeds=None, subfolder_levels=0, overwrite=False, threads=None, engine=None,
-                       on_error=None, gpu_workers=3, device=None):
+                       on_error=None, gpu_workers=1, device=None):
     """Steps C-E of run_clean2img for MANY samples (the loop of ImageCommand.process_samples, image.py:1265-1294) on
     one GPU: samples are inflated ahead by worker threads into pinned memory (varkoder_b200.feed), pushed through the
-    GPU by ``gpu_workers`` threads that each own a context (the path of one sample is a chain of short dependent
-    kernels; three or four samples in flight fill the gaps: 485 -> 680 Gbases/s on 200 Mbp samples, 68 -> 180 on
-    10 Mbp ones, profiles/r01_notes.md), and their PNGs are written by the inflate pool off the critical path.
+    GPU by ``gpu_workers`` threads that each own a context, and their PNGs are written by the inflate pool off the
+    critical path.  From gzip files the batch is bound by zlib on the host cores (0.6 Gbases/s with 16 threads,
+    tools/bench_feed.py), so one GPU worker is the default; with inputs that are already in memory the path of one
+    sample is a chain of short dependent kernels and three or four samples in flight fill the gaps (582 -> 737
+    Gbases/s on 200 Mbp samples, 68 -> 180 on 10 Mbp ones, profiles/r01_notes.md).
 
     ``samples``: iterable of dicts ``{"sample": name, "path": clean .fq(.gz), "labels": [...], "base_sd": float}``.
     ``seeds``: per-sample seeds (default: the sample's position).  ``engine``: use this one context only.
