@@ -347,19 +347,22 @@ plan_kernel(const uint8_t* __restrict__ text, uint64_t* __restrict__ starts, uin
         s_cap[l] = cap;
         plan->seg_cap[l] = cap;
         __syncthreads();
+        __shared__ uint64_t s_off;
         if (l == 0) {
             double wsum = 0.0;
             uint64_t off = 0;
-            for (int s = 0; s < kMaxLevels; ++s) {
+            for (int s = 0; s < nl; ++s) {                 // only the ladder's segments have a share / a region
                 wsum += s_w[s];
                 plan->seg_begin[s] = off;
                 off += s_cap[s];
             }
-            plan->seg_begin[kMaxLevels] = off;
+            s_off = off;
             plan->bucket_overflow = off > a.cap_sorted ? 1u : 0u;
             s_wsum = wsum;
         }
         __syncthreads();
+        if (l >= nl) plan->seg_begin[l] = s_off;           // empty regions at the end
+        if (l == 0) plan->seg_begin[kMaxLevels] = s_off;
         // CTAs: one per segment, the rest in proportion to the expected bases; leftovers one by one to the segment with
         // the most expected bases per CTA (greedy = optimal for the slowest segment, which is what the kernel waits for)
         const bool enough = (uint32_t)nl <= a.n_count_ctas;
@@ -375,18 +378,22 @@ plan_kernel(const uint8_t* __restrict__ text, uint64_t* __restrict__ starts, uin
                 int best = 0;
                 float load = -1.f;
                 for (int s = 0; s < nl; ++s) {
-                    const float ld = (float)s_w[s] / (float)s_ncta[s];
+                    const float ld = __fdividef((float)s_w[s], (float)s_ncta[s]);
                     if (ld > load) { load = ld; best = s; }
                 }
                 ++s_ncta[best];
             }
         }
         __syncthreads();
+        __shared__ uint32_t s_crun;
         if (l == 0) {
             uint32_t crun = 0;
-            for (int s = 0; s < kMaxLevels; ++s) { plan->seg_cta_begin[s] = crun; crun += s_ncta[s]; }
+            for (int s = 0; s < nl; ++s) { plan->seg_cta_begin[s] = crun; crun += s_ncta[s]; }
+            s_crun = crun;
             plan->seg_cta_begin[kMaxLevels] = crun;
         }
+        __syncthreads();
+        if (l >= nl) plan->seg_cta_begin[l] = s_crun;      // no CTAs beyond the ladder
     }
 }
 
