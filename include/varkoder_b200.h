@@ -139,6 +139,26 @@ int vk_render_counts(vk_ctx* ctx, int slot, int k, int n, const uint64_t* canon_
 int vk_reads_to_images(vk_ctx* ctx, const void* text, uint64_t n_bytes, int on_device, const vk_params* params,
                        int slot, int max_levels_out, vk_result* result, uint64_t* canon_host, uint8_t* pixels_host);
 
+/*
+ * The pixels of the last vk_reads_to_images / vk_render call as they lie in DEVICE memory (n_levels x side x side
+ * uint8, row-major, level 0 first), for a consumer that stays on the GPU: `varKoder query` feeds the images to a
+ * classifier (query.py:283-314) and need not go through PNG files.  The pointer belongs to the context and is valid
+ * until the next call that renders or until the context is destroyed.
+ */
+int vk_device_pixels(vk_ctx* ctx, const uint8_t** dev_pixels, int32_t* n_levels, int32_t* side);
+
+/*
+ * convert.remap (varKoder/commands/convert.py:34-77) for a batch of images: move pixels from one pixel table to another
+ * (varKode <-> cgr).  The join of the two tables is passed as, per OUTPUT pixel, two source pixels (src0, src1; -1 =
+ * none) and their multiplicities mult[2 p], mult[2 p + 1] (varkoder_b200/mapping.py: remap_plan).
+ * sum_rc = 0: out[p] = in[src0[p]] (0 where src0 < 0).
+ * sum_rc = 1: out[p] = (mult0 * in[src0] + mult1 * in[src1]) mod 256, then rescaled over the image as
+ *             uint8((a - min) / max * 255) in float64, exactly as the reference does.
+ * in_host: n_images x n_in_pixels uint8; out_host: n_images x n_out_pixels uint8.  Synchronises.
+ */
+int vk_remap(vk_ctx* ctx, int n_images, uint32_t n_in_pixels, uint32_t n_out_pixels, const uint8_t* in_host,
+             const int32_t* src0, const int32_t* src1, const uint8_t* mult, int sum_rc, uint8_t* out_host);
+
 /* Device time of the last vk_reads_to_images / stage call, per kernel group, in milliseconds (CUDA events on
  * the context stream): [0] upload (H2D), [1] parse, [2] plan+bucket, [3] count kernel, [4] slab reduce+fold,
  * [5] render, [6] read-back (D2H), [7] total. */

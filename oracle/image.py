@@ -169,3 +169,67 @@ def image_float(canon_full, lut):
     a = pixel_values(canon_full, lut).astype(np.float64)
     bins = np.quantile(a, np.arange(0, 1, 1 / 256))
     return np.uint8(np.digitize(a, bins, right=False) - 1)
+
+
+# ---------------------------------------------------------------------------------------------- remap (convert)
+def remap_plan(lut_in, lut_out, k, in_is_cgr, out_is_cgr):
+    """Restatement of the pandas merge of ``convert.remap`` (varKoder/commands/convert.py:52-72) for one direction.
+
+    Returns ``(src0, src1, mult)`` per OUTPUT pixel (flattened, final image orientation): the output pixel takes
+    ``old[src0]`` in plain mode and ``mult * (old[src0] + old[src1]) / 2 ...`` -- precisely: in sum_rc mode it receives
+    ``m0 * old[src0] + m1 * old[src1]`` with ``(m0, m1) = mult``; unused output pixels have src0 = -1.
+
+    Row multiplicities of the merge: the varKode table lists K and rc K on one pixel (a palindrome twice), the cgr table
+    lists every K twice, once at its own pixel and once at the pixel of rc K (utils.py:199-208).
+    """
+    n = 4 ** k
+    idx = np.arange(n, dtype=np.int64)
+    rc = np.array([revcomp_index(int(i), k) for i in idx], dtype=np.int64)
+    lin, lout = np.asarray(lut_in).reshape(-1), np.asarray(lut_out).reshape(-1)
+
+    def kmer_to_pixel(lut_flat, is_cgr):
+        pix = np.full(n, -1, dtype=np.int64)
+        used = np.flatnonzero(lut_flat >= 0)
+        pix[lut_flat[used]] = used
+        if not is_cgr:                                  # varKode: rc K is drawn on the same pixel
+            pix[rc[lut_flat[used]]] = used
+        return pix
+
+    pin = kmer_to_pixel(lin, in_is_cgr)
+    n_out = lout.size
+    src0 = np.full(n_out, -1, dtype=np.int32)
+    src1 = np.full(n_out, -1, dtype=np.int32)
+    mult = np.zeros((n_out, 2), dtype=np.uint8)
+    used = np.flatnonzero(lout >= 0)
+    K = lout[used].astype(np.int64)                     # a k-mer shown at the output pixel (its own K for cgr)
+    pal = rc[K] == K
+    if out_is_cgr and not in_is_cgr:                    # varKode -> cgr: pixel xy(K) <- old[vk(K)] (+ old[vk(rc K)], same pixel)
+        src0[used] = pin[K]
+        src1[used] = pin[rc[K]]
+        mult[used, 0] = np.where(pal, 4, 1)
+        mult[used, 1] = np.where(pal, 0, 1)
+    elif in_is_cgr and not out_is_cgr:                  # cgr -> varKode: pixel vk(S) <- old[cgr(S)], old[cgr(rc S)]
+        src0[used] = pin[K]
+        src1[used] = pin[rc[K]]
+        mult[used, 0] = np.where(pal, 4, 2)
+        mult[used, 1] = np.where(pal, 0, 2)
+    else:
+        raise ValueError("remap is between varKode and cgr")
+    return src0, src1, mult
+
+
+def remap_exact(img, lut_in, lut_out, k, in_is_cgr, out_is_cgr, sum_rc=False):
+    """pixels of ``convert.remap(img, k, in, out, sum_rc)`` for an image that is consistent under reverse complement"""
+    old = np.asarray(img, dtype=np.uint8).reshape(-1)
+    src0, src1, mult = remap_plan(lut_in, lut_out, k, in_is_cgr, out_is_cgr)
+    used = src0 >= 0
+    new = np.zeros(src0.size, dtype=np.uint8)
+    if not sum_rc:
+        new[used] = old[src0[used]]
+        return new.reshape(np.asarray(lut_out).shape)
+    acc = (mult[used, 0].astype(np.uint32) * old[src0[used]] + mult[used, 1].astype(np.uint32) * old[np.maximum(src1[used], 0)])
+    new[used] = (acc & 0xFF).astype(np.uint8)           # np.add.at on a uint8 array wraps
+    mn, mx = int(new.min()), int(new.max())
+    with np.errstate(all="ignore"):
+        out = np.uint8((new - np.uint8(mn)) / np.uint8(mx) * 255) if mx else np.zeros_like(new)
+    return out.reshape(np.asarray(lut_out).shape)

@@ -488,3 +488,52 @@ def test_full_size_properties_config3(engine):
     head = dev[:nb].cpu().numpy().tobytes()
     r2 = engine.reads_to_images(head, Params(k=k, min_bp=0, max_bp=None, is_query=True), table, want_canon=True)
     assert (r2.canon[0] == dsk.canonical_counts(head, k, threads=0)).all()
+
+
+def test_query_mode_device_handoff(engine):
+    """`varKoder query` (image.py:1028-1048): one level of min(nsites, max_bp), no min_bp check -- and the images can be
+    handed to a GPU consumer without leaving the device (vk_device_pixels)."""
+    import torch
+    buf = synth.fixed(120_000, 150, seed=17).tobytes()
+    table = get_kmer_mapping(7, "cgr")
+    res = engine.reads_to_images(buf, Params(k=7, min_bp=10**9, max_bp=100_000, is_query=True, seed=4), table, want_canon=True)
+    assert res.levels == [100_000]                                   # min_bp is ignored in query mode
+    expect = oracle_levels(buf, 7, 4, res.levels, res.nsites)
+    assert (res.canon == expect).all()
+    dev = engine.device_pixels()
+    assert dev.is_cuda and dev.dtype == torch.uint8 and tuple(dev.shape) == (1, 128, 128)
+    assert (dev.cpu().numpy() == res.pixels).all()
+    x = dev.float().div_(255.0)                                       # what a classifier's first op would do
+    assert float(x.max()) == 1.0
+
+
+@pytest.mark.parametrize("k", [5, 6, 7])
+def test_remap_matches_reference_golden(engine, golden_dir, k):
+    """vk_remap (convert.remap on the GPU) against the outputs of the imported reference, both directions, with and
+    without sum_rc, one image at a time and as a batch"""
+    from varkoder_b200 import convert
+    z = np.load(os.path.join(golden_dir, f"remap_k{k}.npz"))
+    keys = sorted(set(n.rsplit("__", 1)[0] for n in z.files))
+    batches = {}
+    for key in keys:
+        d, _, mode = key.split("__")
+        src, dst = d.split("_to_")
+        got = convert.remap_arrays(z[key + "__in"], k, src, dst, sum_rc=(mode == "sum"), engine=engine)
+        assert got.dtype == np.uint8 and (got == z[key + "__out"]).all(), key
+        batches.setdefault((src, dst, mode), []).append(key)
+    for (src, dst, mode), ks in batches.items():
+        got = convert.remap_arrays(np.stack([z[x + "__in"] for x in ks]), k, src, dst, sum_rc=(mode == "sum"), engine=engine)
+        assert (got == np.stack([z[x + "__out"] for x in ks])).all()
+
+
+def test_remap_shipped_docs_pngs(engine, golden_dir):
+    """the reference's own example images: remapping the shipped varKode PNG gives the shipped cgr PNG exactly"""
+    from PIL import Image
+    from varkoder_b200 import convert
+    d = os.path.join(golden_dir, "docs_png")
+    names = sorted(f for f in os.listdir(d) if "+varKode+" in f)
+    assert len(names) == 3
+    for fn in names:
+        got = convert.remap(Image.open(os.path.join(d, fn)), 7, "varKode", "cgr", engine=engine)
+        want = np.array(Image.open(os.path.join(d, fn.replace("+varKode+", "+cgr+"))))
+        assert got.mode == "L" and (np.array(got) == want).all(), fn

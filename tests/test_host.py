@@ -137,3 +137,17 @@ def test_synthetic_generator_shape_and_determinism():
     v = synth.variable(500, seed=1)
     pv = dsk.parse_fastq(v)
     assert pv["n_reads"] == 500 and pv["lens"].min() < 7 and pv["lens"].max() <= 280
+
+
+@pytest.mark.parametrize("k", [5, 6, 7])
+def test_remap_plan_matches_oracle(golden_dir, k):
+    """the product's join of the two pixel tables (mapping.remap_plan) against the oracle's restatement, which is
+    pinned to the reference's convert.remap by tests/golden/remap_k*.npz (test_oracle.py)"""
+    from oracle import image as oimg
+    for src, dst in (("varKode", "cgr"), ("cgr", "varKode")):
+        s0, s1, mult, shape = vm.remap_plan(k, src, dst)
+        e0, e1, em = oimg.remap_plan(vm.get_kmer_mapping(k, src).lut, vm.get_kmer_mapping(k, dst).lut, k, src == "cgr", dst == "cgr")
+        assert shape == vm.get_kmer_mapping(k, dst).lut.shape
+        assert (s0 == e0).all() and (s1 == e1).all() and (mult == em).all()
+    with pytest.raises(Exception, match="Input and output mapping must be one of"):
+        vm.remap_plan(k, "varKode", "nope")

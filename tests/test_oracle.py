@@ -138,3 +138,17 @@ def test_restatement_against_live_reference(tmp_path):
         canon = rng.integers(0, 50, n).astype(np.uint64)[np.minimum(np.arange(n), rcs)]
         png, _ = ref_shim.reference_make_image(dsk.dsk2ascii_text(canon, k), tmp_path, table, k=k, mapping_code=mapping)
         assert (np.array(Image.open(png)) == oimg.image_exact(canon, lut)).all()
+
+
+@pytest.mark.parametrize("k", [5, 6, 7])
+def test_remap_golden(golden_dir, k):
+    """oracle restatement of convert.remap against the outputs of the imported reference (oracle/make_golden_remap.py)"""
+    z = np.load(os.path.join(golden_dir, f"remap_k{k}.npz"))
+    luts = {m: np.load(os.path.join(golden_dir, f"lut_k{k}_{m}.npy")) for m in ("varKode", "cgr")}
+    keys = sorted(set(n.rsplit("__", 1)[0] for n in z.files))
+    assert len(keys) == 10
+    for key in keys:
+        d, _, mode = key.split("__")
+        src, dst = d.split("_to_")
+        got = oimg.remap_exact(z[key + "__in"], luts[src], luts[dst], k, src == "cgr", dst == "cgr", mode == "sum")
+        assert (got == z[key + "__out"]).all(), key

@@ -24,4 +24,7 @@ def __getattr__(name):
     if name in ("split_fastq", "count_kmers", "make_image", "reads_to_images", "default_engine"):
         from . import stages
         return getattr(stages, name)
+    if name in ("remap", "remap_arrays"):
+        from . import convert
+        return getattr(convert, name)
     raise AttributeError(name)

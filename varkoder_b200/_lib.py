@@ -16,7 +16,7 @@ VK_LADDER_LESS_THAN_MIN = 1
 # every symbol include/varkoder_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "vk_abi_version", "vk_last_error", "vk_ctx_create", "vk_ctx_destroy", "vk_set_mapping", "vk_upload",
-    "vk_attach", "vk_parse", "vk_count", "vk_render", "vk_render_counts", "vk_reads_to_images",
+    "vk_attach", "vk_parse", "vk_count", "vk_render", "vk_render_counts", "vk_reads_to_images", "vk_device_pixels", "vk_remap",
     "vk_last_timings", "vk_set_fine_timing", "vk_launch_count", "vk_bucket_retries", "vk_synth_fastq",
 ]
 
@@ -69,6 +69,8 @@ def load():
     L.vk_render_counts.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
     L.vk_reads_to_images.argtypes = [vp, vp, C.c_uint64, C.c_int, C.POINTER(VkParams), C.c_int, C.c_int,
                                      C.POINTER(VkResult), vp, vp]
+    L.vk_device_pixels.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.vk_remap.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, vp, vp, vp, vp, C.c_int, vp]
     L.vk_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.vk_set_fine_timing.argtypes = [vp, C.c_int]
     L.vk_launch_count.argtypes = [vp]

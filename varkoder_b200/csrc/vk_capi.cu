@@ -90,6 +90,7 @@ struct vk_ctx {
     const uint8_t* text = nullptr;  // device
     uint64_t n_bytes = 0;
     bool have_text = false, parsed = false, counted = false;
+    int last_levels = 0, last_side = 0;     // what pix_d() holds (vk_device_pixels)
     bool exact_layout = false;      // segment regions sized for every read (set after a bucket overflow)
     bool use_count16 = true;        // VK_COUNT16=0: k = 8 with global atomics instead of 16-bit shared-memory bins
     bool use_pairs = false;         // VK_COUNT_PAIRS=1: k = 7 through 8-mer pairs in 16-bit bins (exact; halves the
@@ -103,6 +104,8 @@ struct vk_ctx {
     DevBuf<uint32_t> tile_count, warp_count;
     DevBuf<uint32_t> slabs;
     DevBuf<unsigned long long> seg_hist, canon, vals, bins;
+    DevBuf<uint8_t> remap_in, remap_out, remap_mult;
+    DevBuf<int32_t> remap_src;
     Mapping maps[4];
 
     bool fine_timing = true;        // vk_set_fine_timing: events between the kernel groups (they serialise the stream)
@@ -280,6 +283,8 @@ void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsign
     const uint32_t n_pad = next_pow2(n_pix);
     c->canon.ensure((size_t)levels * nk);
     ensure_outbox(c, (size_t)levels * n_pix);
+    c->last_levels = levels;
+    c->last_side = m.side;
     if (seg_hist) {
         launch(c, fold_kernel, dim3((nk + 255) / 256), dim3(256), 0, seg_hist, k, levels, c->canon.p);
         CU(cudaGetLastError());
@@ -497,6 +502,10 @@ int vk_ctx_destroy(vk_ctx* c)
     c->canon.release();
     c->vals.release();
     c->bins.release();
+    c->remap_in.release();
+    c->remap_out.release();
+    c->remap_mult.release();
+    c->remap_src.release();
     for (auto& m : c->maps) m.lut.release();
     if (c->out_h) cudaFreeHost(c->out_h);
     if (c->out_d) cudaFree(c->out_d);
@@ -706,6 +715,7 @@ int vk_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, int on_dev
             CU(cudaMemcpyAsync(c->pix_h(), c->pix_d(), (size_t)nl * n_pix, cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
         }
+        c->last_levels = nl;
         if (pixels_host && nl > 0) memcpy(pixels_host, c->pix_h(), (size_t)nl * n_pix);
         if (canon_host && nl > 0) {
             CU(cudaMemcpyAsync(canon_host, c->canon.p, (size_t)nl * nk * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
@@ -732,6 +742,46 @@ int vk_last_timings(vk_ctx* c, float* ms8)
             if (cudaEventElapsedTime(&t, c->ev[EV_START], c->ev[last]) == cudaSuccess) ms8[7] = t;
         }
         cudaGetLastError();
+    });
+}
+
+int vk_device_pixels(vk_ctx* c, const uint8_t** dev_pixels, int32_t* n_levels, int32_t* side)
+{
+    return guarded([&] {
+        if (!c || !dev_pixels || !n_levels || !side) throw ApiError{VK_EINVAL, "NULL argument"};
+        if (c->last_side <= 0) throw ApiError{VK_ESTATE, "nothing has been rendered on this context yet"};
+        set_device(c);
+        CU(cudaStreamSynchronize(c->stream));
+        *dev_pixels = c->pix_d();
+        *n_levels = c->last_levels;
+        *side = c->last_side;
+    });
+}
+
+int vk_remap(vk_ctx* c, int n_images, uint32_t n_in, uint32_t n_out, const uint8_t* in_host, const int32_t* src0,
+             const int32_t* src1, const uint8_t* mult, int sum_rc, uint8_t* out_host)
+{
+    return guarded([&] {
+        if (!c || !in_host || !src0 || !src1 || !mult || !out_host) throw ApiError{VK_EINVAL, "NULL argument"};
+        if (n_images < 1 || n_in == 0 || n_out == 0 || n_in > (1u << 20) || n_out > (1u << 20))
+            throw ApiError{VK_EINVAL, "bad image count or size"};
+        for (uint32_t p = 0; p < n_out; ++p)
+            if (src0[p] < -1 || src1[p] < -1 || src0[p] >= (int32_t)n_in || src1[p] >= (int32_t)n_in)
+                throw ApiError{VK_EINVAL, "remap source pixel outside the input image"};
+        set_device(c);
+        c->remap_in.ensure((size_t)n_images * n_in);
+        c->remap_out.ensure((size_t)n_images * n_out);
+        c->remap_src.ensure((size_t)2 * n_out);
+        c->remap_mult.ensure((size_t)2 * n_out);
+        CU(cudaMemcpyAsync(c->remap_in.p, in_host, (size_t)n_images * n_in, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->remap_src.p, src0, sizeof(int32_t) * n_out, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->remap_src.p + n_out, src1, sizeof(int32_t) * n_out, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->remap_mult.p, mult, (size_t)2 * n_out, cudaMemcpyHostToDevice, c->stream));
+        launch(c, vk::remap_kernel, dim3(n_images), dim3(256), 0, c->remap_in.p, n_in, c->remap_src.p, c->remap_src.p + n_out,
+               c->remap_mult.p, n_out, sum_rc, c->remap_out.p);
+        ++c->launches;
+        CU(cudaMemcpyAsync(out_host, c->remap_out.p, (size_t)n_images * n_out, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
     });
 }
 

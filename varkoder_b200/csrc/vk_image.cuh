@@ -216,4 +216,50 @@ image_digitize_kernel(const unsigned long long* __restrict__ canon, const int32_
     pixels[(size_t)l * n_pix + p] = (uint8_t)(lo - 1);
 }
 
+// ---- remap between pixel tables (the "next" row N3 of SURVEY.md section 8f) ---------------------------------------
+// convert.remap (varKoder/commands/convert.py:34-77): new[pixel_out(K)] = old[pixel_in(K)] over the inner join of the two
+// tables; with sum_rc the contributions are ADDED in a uint8 array (np.add.at wraps modulo 256) and the result is
+// rescaled as np.uint8((a - a.min()) / a.max() * 255) in float64.  The join is precomputed on the host as, per output
+// pixel, two source pixels and their multiplicities (varkoder_b200/mapping.py: remap_plan).  One CTA per image.
+__global__ void __launch_bounds__(256)
+remap_kernel(const uint8_t* __restrict__ in, uint32_t n_in, const int32_t* __restrict__ src0,
+             const int32_t* __restrict__ src1, const uint8_t* __restrict__ mult, uint32_t n_out, int sum_rc,
+             uint8_t* __restrict__ out)
+{
+    pdl_wait();
+    __shared__ uint32_t s_min, s_max;
+    const uint8_t* inb = in + (size_t)blockIdx.x * n_in;
+    uint8_t* outb = out + (size_t)blockIdx.x * n_out;
+    if (!sum_rc) {
+        for (uint32_t p = threadIdx.x; p < n_out; p += blockDim.x) {
+            const int32_t s = src0[p];
+            outb[p] = s >= 0 ? inb[s] : (uint8_t)0;
+        }
+        return;
+    }
+    if (threadIdx.x == 0) { s_min = 255u; s_max = 0u; }
+    __syncthreads();
+    uint32_t mn = 255u, mx = 0u;
+    for (uint32_t p = threadIdx.x; p < n_out; p += blockDim.x) {
+        const int32_t a = src0[p], b = src1[p];
+        uint32_t v = 0;
+        if (a >= 0) v = (uint32_t)mult[2 * p] * inb[a] + (b >= 0 ? (uint32_t)mult[2 * p + 1] * inb[b] : 0u);
+        v &= 0xFFu;
+        outb[p] = (uint8_t)v;
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&s_min, mn); atomicMax(&s_max, mx); }
+    __syncthreads();
+    mn = s_min;
+    mx = s_max;
+    for (uint32_t p = threadIdx.x; p < n_out; p += blockDim.x) {
+        const uint32_t v = outb[p];
+        // float64, in numpy's order of operations; IEEE division and multiplication, no contraction possible
+        outb[p] = mx ? (uint8_t)(int)(__dmul_rn(__ddiv_rn((double)(v - mn), (double)mx), 255.0)) : (uint8_t)0;
+    }
+}
+
 }  // namespace vk

@@ -190,6 +190,39 @@ class Engine:
         nl = r.n_levels
         return _result_from(r, canon[:nl] if canon is not None else None, pixels[:nl])
 
+    def remap(self, images, src0, src1, mult, n_out_shape, sum_rc=False):
+        """batch of uint8 images [n, H_in, W_in] -> [n, H_out, W_out] through a remap plan (mapping.remap_plan)"""
+        imgs = np.ascontiguousarray(images, dtype=np.uint8)
+        if imgs.ndim == 2:
+            imgs = imgs[None]
+        n, n_in = imgs.shape[0], imgs.shape[1] * imgs.shape[2]
+        src0 = np.ascontiguousarray(src0, dtype=np.int32)
+        src1 = np.ascontiguousarray(src1, dtype=np.int32)
+        mult = np.ascontiguousarray(mult, dtype=np.uint8)
+        n_out = int(n_out_shape[0]) * int(n_out_shape[1])
+        if src0.size != n_out or src1.size != n_out or mult.size != 2 * n_out:
+            raise ValueError("remap plan does not match the output shape")
+        out = np.empty((n, int(n_out_shape[0]), int(n_out_shape[1])), dtype=np.uint8)
+        self._check(self._L.vk_remap(self._ctx, n, n_in, n_out, imgs.ctypes.data, src0.ctypes.data, src1.ctypes.data,
+                                     mult.ctypes.data, 1 if sum_rc else 0, out.ctypes.data))
+        return out
+
+    def device_pixels(self):
+        """the images of the last render as a torch uint8 CUDA tensor [levels, side, side] that ALIASES the context's
+        buffer (valid until the next render): the hand-off to a classifier that stays on the GPU (query.py:283-314)."""
+        import torch
+        ptr, nl, side = C.c_void_p(), C.c_int32(), C.c_int32()
+        self._check(self._L.vk_device_pixels(self._ctx, C.byref(ptr), C.byref(nl), C.byref(side)))
+
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (nl.value, side.value, side.value), "typestr": "|u1",
+                                      "data": (ptr.value, False), "version": 2, "strides": None}
+        if nl.value == 0:
+            return torch.empty((0, side.value, side.value), dtype=torch.uint8, device=f"cuda:{self.device}")
+        return torch.as_tensor(v, device=f"cuda:{self.device}")
+
     # ------------------------------------------------------------------ misc
     def timings(self):
         ms = (C.c_float * 8)()

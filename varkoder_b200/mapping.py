@@ -131,3 +131,47 @@ def as_pixel_table(kmer_mapping, mapping_code=None):
 
 
 _DF_CACHE = {}
+
+
+# ------------------------------------------------------------------------------------------------- remap (convert)
+@lru_cache(maxsize=None)
+def remap_plan(k, in_mapping, out_mapping):
+    """The inner join of ``convert.remap`` (varKoder/commands/convert.py:52-60) between the two pixel tables of size k,
+    reduced to what the GPU needs: per output pixel (flattened, final orientation) two source pixels and how many rows
+    of the join carry each.  Returns ``(src0, src1, mult[n_out, 2], out_shape)``.
+
+    Multiplicities: the varKode table lists K and rc K on one pixel (a palindrome twice); get_cgr lists every K twice,
+    at its own pixel and at the pixel of rc K (core/utils.py:199-208).  So varKode -> cgr puts old[vk(K)] on pixel
+    cgr(K) once through K and once through rc K (the same source pixel: 1 + 1, a palindrome 4), and cgr -> varKode
+    puts old[cgr(S)] and old[cgr(rc S)] on pixel vk(S) twice each (a palindrome 4 times its one pixel).  Without
+    sum_rc the reference keeps the last row written; for images whose pixels agree under reverse complement (anything
+    ``varKoder image`` wrote) every row carries the same value and src0 is used.
+    """
+    if in_mapping not in MAPPING_CHOICES or out_mapping not in MAPPING_CHOICES:
+        raise Exception("Input and output mapping must be one of: " + str(MAPPING_CHOICES))      # convert.py:49
+    if in_mapping == out_mapping:
+        raise ValueError("input and output mapping are the same: nothing to remap")
+    tin, tout = get_kmer_mapping(k, in_mapping), get_kmer_mapping(k, out_mapping)
+    n = 4 ** k
+    rc = revcomp_index(np.arange(n, dtype=np.int64), k)
+    lin = tin.lut.reshape(-1).astype(np.int64)
+    used_in = np.flatnonzero(lin >= 0)
+    pin = np.full(n, -1, dtype=np.int64)
+    pin[lin[used_in]] = used_in
+    if in_mapping == "varKode":
+        pin[rc[lin[used_in]]] = used_in
+    lout = tout.lut.reshape(-1).astype(np.int64)
+    used = np.flatnonzero(lout >= 0)
+    kk = lout[used]
+    pal = rc[kk] == kk
+    src0 = np.full(lout.size, -1, dtype=np.int32)
+    src1 = np.full(lout.size, -1, dtype=np.int32)
+    mult = np.zeros((lout.size, 2), dtype=np.uint8)
+    src0[used] = pin[kk]
+    src1[used] = pin[rc[kk]]
+    each = 1 if out_mapping == "cgr" else 2
+    mult[used, 0] = np.where(pal, 4, each)
+    mult[used, 1] = np.where(pal, 0, each)
+    for a in (src0, src1, mult):
+        a.setflags(write=False)
+    return src0, src1, mult, (tout.side, tout.side)
