@@ -537,3 +537,23 @@ def test_remap_shipped_docs_pngs(engine, golden_dir):
         got = convert.remap(Image.open(os.path.join(d, fn)), 7, "varKode", "cgr", engine=engine)
         want = np.array(Image.open(os.path.join(d, fn.replace("+varKode+", "+cgr+"))))
         assert got.mode == "L" and (np.array(got) == want).all(), fn
+
+
+@pytest.mark.parametrize("k", [7, 8, 9])
+def test_very_long_reads_and_limits(engine, k):
+    """reads of megabases (nanopore-like): one read spans tens of thousands of chunks, units hold 1..3 reads, break points
+    every 500 bases or none; and the documented limit: a read of 2^24 bases or more is refused, not mis-counted."""
+    from varkoder_b200.engine import VkError
+    rng = np.random.default_rng(40 + k)
+    big = "".join(rng.choice(list("ACGT"), 1_300_003))
+    big = big[:500_000] + "N" + big[500_001:]
+    reads = [big, "ACGTACGTACGTA", big[::-1][:700_001], "", "G" * 70_000]
+    buf = fastq(reads, quals=["#" * len(r) for r in reads])
+    for bl in (500, 0, 64):
+        _, res, canon, _ = gpu_counts(engine, buf, Params(k=k, min_bp=0, max_bp=None, is_query=True, breaklength=bl))
+        assert (canon[0] == dsk.canonical_counts(buf, k, breaklen=bl)).all(), bl
+    huge = fastq(["A" * (1 << 24)], quals=["#"])            # malformed quality line: framing is by line count only
+    engine.upload(huge)
+    engine.parse()
+    with pytest.raises(VkError, match="longer than 2\\^24-1"):
+        engine.count(Params(k=k, min_bp=0, max_bp=None, is_query=True))
