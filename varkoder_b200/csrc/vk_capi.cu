@@ -209,7 +209,7 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist, int breaklen)
     if constexpr (K == 7 || K == 8) {
         if (K == 8 ? c->use_count16 : c->use_pairs) {
             // 16-bit bins in shared memory: k = 8 directly, k = 7 through pairs (vk_count.cuh)
-            const size_t smem = (size_t)(32768 + (K == 7 ? 16384 : 0) + 32) * sizeof(uint32_t);
+            const size_t smem = (size_t)(32768 + (K == 7 ? 16384 : 0)) * sizeof(uint32_t);
             CU(cudaFuncSetAttribute(count16_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             launch(c, count16_kernel<K>, grid, block, smem, reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d,
                    c->slabs.p, breaklen);

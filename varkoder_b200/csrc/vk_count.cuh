@@ -35,7 +35,7 @@
 //             pair costs one shared-memory operation instead of two (the kernel is bound by the shared-memory data
 //             pipe: 3.5 wavefronts per 32 random banks, profiles/r01_notes.md); 7-mers whose pair partner is not
 //             countable (read ends, N, break points) go to a 4^7 x u32 table.  16-bit bins are kept exact by
-//             watching the values the atomics return (see count_flush / the rendezvous in the kernel).
+//             watching the values the atomics return and draining hot words to the slab (see count16_kernel).
 //   kGlobal   k = 9: increments go straight to the global (L2-resident) segment histogram.
 #pragma once
 #include "vk_common.cuh"
@@ -366,24 +366,48 @@ count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sort
 // the HIGH half the count of the upper bin: the increment is (sh & 0x20000) / 2 + 1 (one LOP3 + one IMAD.HI), and
 // "the low half stays below 2^16" is the only overflow condition.
 //
-// Exactness.  Every increment is an ATOMS.ADD that returns the old word; a lane ORs what it gets back.  When some
-// low half has reached 0x4000 the warp raises the CTA's flag at the end of its iteration; every warp looks at the
-// flag once per iteration and then joins a rendezvous (also joined by warps that ran out of work, which simply wait
-// at its barrier), where the table is folded into the CTA's u32 slab in global memory and cleared.  Between a bin
-// reaching 0x4000 and the last warp stopping, every warp can add at most two iterations (2 x 32 lanes x 32), i.e.
-// 65 536 / 2 in total for 32 warps, so no low half can pass 0x4000 + 0x8400 < 2^16.  On ordinary reads the flag is
-// never raised (a CTA sees ~10^6 bases; one 8-mer would have to make up > 1 % of them).
+// Exactness.  Every increment is an ATOMS.ADD that returns the old word; a lane ORs what it gets back and looks at
+// the OR after every 16 increments.  A returned low half of 0x4000 or more means that word is running hot: the lane
+// then re-reads the (at most 16) words it has just touched and DRAINS the hot ones -- compare-and-swap the word to 0
+// and credit what it held to the CTA's u32 slab in global memory (rare global atomics).  The swap makes a drain happen
+// once however many lanes notice the same word.  Bound: after a word reaches 0x4000, every warp can add at most the
+// 16 increments per lane it may be in the middle of plus 16 more before its own next look, 32 warps x 32 lanes x 32 =
+// 32 768, so a low half never passes 0x4000 + 0x8000 < 2^16.  No barrier is involved; on ordinary reads nothing is
+// ever drained (a CTA sees ~10^6 bases; one 8-mer would have to make up more than 1 % of them).
+template <int K>
+__device__ __forceinline__ void credit16(uint32_t* __restrict__ slab, uint32_t word_idx, uint32_t w)
+{
+    const uint32_t hi = w >> 16, lo = (w & 0xFFFFu) - hi;           // counts of the upper / lower bin of the word
+    const uint32_t bl = word_idx, bu = word_idx | 0x8000u;
+    if (K == 8) {
+        if (lo) atomicAdd(slab + bl, lo);
+        if (hi) atomicAdd(slab + bu, hi);
+    } else {                                                        // an 8-mer stands for its first and its last 7-mer
+        if (lo) { atomicAdd(slab + (bl & 0x3FFFu), lo); atomicAdd(slab + (bl >> 2), lo); }
+        if (hi) { atomicAdd(slab + (bu & 0x3FFFu), hi); atomicAdd(slab + (bu >> 2), hi); }
+    }
+}
+template <int K>
+__device__ __forceinline__ void drain16(uint32_t* __restrict__ h8, uint32_t* __restrict__ slab, uint32_t word_idx)
+{
+    uint32_t w = *reinterpret_cast<volatile uint32_t*>(h8 + word_idx);
+    while ((w & 0xFFFFu) >= 0x4000u) {
+        const uint32_t seen = atomicCAS(h8 + word_idx, w, 0u);
+        if (seen == w) { credit16<K>(slab, word_idx, w); break; }
+        w = seen;
+    }
+}
+
 template <int K>
 __device__ __forceinline__ void count16_flush(uint32_t* __restrict__ h8, uint32_t* __restrict__ h7, uint32_t* __restrict__ slab,
-                                              bool first, uint32_t tid, uint32_t nthr)
+                                              uint32_t tid, uint32_t nthr)
 {
     if (K == 8) {
         for (uint32_t w = tid; w < 32768u; w += nthr) {
             const uint32_t v = h8[w];
             const uint32_t hi = v >> 16, lo = (v & 0xFFFFu) - hi;
-            h8[w] = 0;
-            if (first) { slab[w] = lo; slab[w | 0x8000u] = hi; }
-            else { slab[w] += lo; slab[w | 0x8000u] += hi; }
+            slab[w] += lo;
+            slab[w | 0x8000u] += hi;
         }
     } else {
         // 7-mer x: singles + 8-mers that start with it (x | c << 14) + 8-mers that end with it ((x << 2 | c) & 0xFFFF)
@@ -397,11 +421,8 @@ __device__ __forceinline__ void count16_flush(uint32_t* __restrict__ h8, uint32_
                 const uint32_t w = h8[w0 | c];
                 v += upper ? (w >> 16) : (w & 0xFFFFu) - (w >> 16);
             }
-            if (first) slab[x] = v; else slab[x] += v;
+            slab[x] += v;
         }
-        __syncthreads();                                                    // all reads of h8 done before it is cleared
-        for (uint32_t w = tid; w < 32768u; w += nthr) h8[w] = 0;
-        for (uint32_t x = tid; x < 16384u; x += nthr) h7[x] = 0;
     }
 }
 
@@ -415,8 +436,7 @@ count16_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ so
     constexpr uint32_t NK = 1u << (2 * K);
     constexpr int KM1 = K - 1;
     constexpr uint32_t FULL = 0xffffffffu;
-    extern __shared__ uint32_t s_raw[];           // [h8: 32768 words][h7: 16384 words (k = 7)][32 trash words]
-    __shared__ volatile uint32_t s_flag;
+    extern __shared__ uint32_t s_raw[];           // [h8: 32768 words][h7: 16384 words (k = 7)]
     const uint32_t tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
 
     const int seg = cta_segment(plan, lane);
@@ -428,51 +448,38 @@ count16_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ so
     constexpr uint32_t kWords = 32768u + (K == 7 ? 16384u : 0u);
     const uint32_t h8_addr = (uint32_t)__cvta_generic_to_shared(s_raw);
     const uint32_t h7_addr = h8_addr + 32768u * 4u;
-    const uint32_t trash_off = (kWords + lane) * 4u;                   // byte offset from h8_addr
-    for (uint32_t i = tid; i < kWords + 32; i += nthr) s_raw[i] = 0;
-    if (tid == 0) s_flag = 0;
-    __syncthreads();
     uint32_t* const slab = slabs + (size_t)blockIdx.x * NK;
-    bool first_flush = true;
+    for (uint32_t i = tid; i < kWords; i += nthr) s_raw[i] = 0;
+    for (uint32_t i = tid; i < NK; i += nthr) slab[i] = 0;             // drains and the final fold ADD to the slab
+    __syncthreads();
 
     ChunkStream cs;
     cs.init(text16, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane);
     uint32_t carry = 0;
-    uint32_t acc = 0;                                                   // OR of the words the atomics returned
     Chunk cur = cs.fetch();
-    for (;;) {
-        const bool have = __ballot_sync(FULL, cur.range != 0) != 0;     // warp-uniform
-        if (!have || s_flag != 0) {
-            // ---- rendezvous of the whole CTA: fold + clear the table when asked to (or at the very end)
-            const int n_busy = __syncthreads_count(have && lane == 0);
-            const bool flush = s_flag != 0 || n_busy == 0;              // uniform: nobody changes the flag in here
-            __syncthreads();
-            if (flush) {
-                count16_flush<K>(h8, h7, slab, first_flush, tid, nthr);
-                first_flush = false;
-                if (tid == 0) s_flag = 0;
-            }
-            acc = 0;
-            __syncthreads();
-            if (n_busy == 0) break;
-            if (!have) continue;                                        // nothing left for this warp: wait for the others
-        }
+    while (__ballot_sync(FULL, cur.range != 0) != 0) {
         const Chunk nxt = cs.fetch();
         const Decoded d = decode_chunk<K>(cur, carry, lane, breaklen);
         const uint64_t Wa = ((uint64_t)d.Cc | ((uint64_t)d.Plo << (2 * KM1))) << 2;
         const uint64_t Wb = ((uint64_t)(d.Plo >> (32 - 2 * KM1)) | ((uint64_t)d.Phi << (2 * KM1))) << 2;
         if (K == 8) {
-            // every 8-mer: window position j holds the 8-mer that ends at base j (7 carried codes in front)
+            // every 8-mer: window position j holds the 8-mer that ends at base j (7 carried codes in front).  A lane
+            // without an 8-mer at j adds 0 to whatever word the window names (always inside the table).
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint64_t W4 = h ? Wb : Wa;
                 const uint32_t Wl = (uint32_t)W4, Wh = (uint32_t)(W4 >> 32), E = h ? d.E >> 16 : d.E & 0xFFFFu;
+                uint32_t acc = 0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const uint32_t sh = __funnelshift_r(Wl, Wh, 2 * j);
-                    const uint32_t off = (E >> j) & 1u ? (sh & 0x1FFFCu) : trash_off;
                     const uint32_t inc = __umulhi(sh & 0x20000u, 0x80000000u) + 1u;
-                    acc |= smem_add_ret(h8_addr + off, (E >> j) & 1u ? inc : 0u);      // the trash word stays 0
+                    acc |= smem_add_ret(h8_addr + (sh & 0x1FFFCu), (E >> j) & 1u ? inc : 0u);
+                }
+                if (__ballot_sync(FULL, (acc & 0xC000u) != 0) != 0) {          // rare: some word is running hot
+                    if (acc & 0xC000u)
+                        for (int j = 0; j < 16; ++j)
+                            drain16<K>(h8, slab, ((uint32_t)(W4 >> (2 * j)) & 0x1FFFCu) >> 2);
                 }
             }
         } else {
@@ -480,6 +487,7 @@ count16_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ so
             const uint32_t Ee = d.E & 0x55555555u, Eo = (d.E >> 1) & 0x55555555u;
             const uint32_t Eb = Ee & Eo;
             uint32_t Es = Ee ^ Eo;                                      // bit 2m: pair m holds exactly one 7-mer
+            uint32_t acc = 0;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint64_t W4 = h ? Wb : Wa;
@@ -488,11 +496,14 @@ count16_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ so
                 for (int m = 0; m < 8; ++m) {
                     // the 8-mer that ends at base 2m+1 starts at window position 2m (6 carried codes in front)
                     const uint32_t sh = __funnelshift_r(Wl, Wh, 4 * m);
-                    const bool on = (E >> (2 * m)) & 1u;
-                    const uint32_t off = on ? (sh & 0x1FFFCu) : trash_off;
                     const uint32_t inc = __umulhi(sh & 0x20000u, 0x80000000u) + 1u;
-                    acc |= smem_add_ret(h8_addr + off, on ? inc : 0u);           // the trash word stays 0
+                    acc |= smem_add_ret(h8_addr + (sh & 0x1FFFCu), (E >> (2 * m)) & 1u ? inc : 0u);
                 }
+            }
+            if (__ballot_sync(FULL, (acc & 0xC000u) != 0) != 0) {              // rare: some word is running hot
+                if (acc & 0xC000u)
+                    for (int m = 0; m < 16; ++m)
+                        drain16<K>(h8, slab, ((uint32_t)((m < 8 ? Wa : Wb) >> (4 * (m & 7))) & 0x1FFFCu) >> 2);
             }
             // single 7-mers (read ends, N, break points): a few per warp and iteration
             while (__ballot_sync(FULL, Es != 0) != 0) {
@@ -507,9 +518,10 @@ count16_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ so
                 }
             }
         }
-        if (__ballot_sync(FULL, (acc & 0xC000u) != 0) != 0 && lane == 0) s_flag = 1;
         cur = nxt;
     }
+    __syncthreads();
+    count16_flush<K>(h8, h7, slab, tid, nthr);
 }
 
 // K3: per-segment histograms (uint64) = sum of the slabs of the CTAs that served the segment.
