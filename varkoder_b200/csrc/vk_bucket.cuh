@@ -100,6 +100,7 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
         for (int i = 0; i < kBucketItems; ++i) {
             if (seg[i] >= 0) {
                 const uint64_t slot = s_base[seg[i]] + rank[i];
+                VK_ASSERT(seg[i] < nl && s_begin[seg[i]] + s_cap[seg[i]] <= plan->seg_begin[kMaxLevels]);
                 if (slot < s_cap[seg[i]]) sorted[s_begin[seg[i]] + slot] = entry[i];
                 else plan->bucket_overflow = 1u;
             }

@@ -4,6 +4,15 @@
 #include <cuda_runtime.h>
 #include "../../include/varkoder_b200.h"
 
+// make -C varkoder_b200/csrc DEBUG=1 builds with device-side assertions on every data-dependent address (the pool's
+// compute-sanitizer is closed): a failed one aborts the kernel and the C ABI call returns VK_ECUDA.
+#ifdef VK_DEBUG
+#include <cassert>
+#define VK_ASSERT(c) assert(c)
+#else
+#define VK_ASSERT(c) ((void)0)
+#endif
+
 namespace vk {
 
 constexpr int kMaxLevels = VK_MAX_LEVELS;

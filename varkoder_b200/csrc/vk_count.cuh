@@ -146,6 +146,7 @@ struct ChunkStream {
     const uint64_t* seg_sorted;
     unsigned long long* seg_counter;
     uint32_t seg_len, lane;
+    uint64_t text_words;   // 16-byte words of the text buffer (VK_ASSERT only)
     Unit A, B;         // A is being consumed, B follows it in the chunk stream
     uint64_t entC;     // the unit after B, on its way from memory
     uint32_t pos;      // stream position of lane 0, in A's chunk numbering
@@ -158,9 +159,11 @@ struct ChunkStream {
         const uint32_t base = (uint32_t)__shfl_sync(0xffffffffu, r0, 0);
         return (base < seg_len && base + lane < seg_len) ? seg_sorted[base + lane] : 0ull;
     }
-    __device__ __forceinline__ void init(const uint4* t, const uint64_t* ss, uint32_t sl, unsigned long long* sc, uint32_t ln)
+    __device__ __forceinline__ void init(const uint4* t, const uint64_t* ss, uint32_t sl, unsigned long long* sc, uint32_t ln,
+                                         uint64_t n_bytes)
     {
         text16 = t; seg_sorted = ss; seg_len = sl; seg_counter = sc; lane = ln;
+        text_words = (n_bytes + 15) >> 4;
         A = make_unit(claim(), lane);
         B = make_unit(claim(), lane);
         entC = claim();
@@ -212,6 +215,7 @@ struct ChunkStream {
         c.wa = make_uint4(0, 0, 0, 0);
         c.wb = c.wa;
         if (act) {
+            VK_ASSERT((uint64_t)(ptr - text16) + (hi > 16u ? 1 : 0) < text_words && rlen != 0 && j < ((rlo + rlen + 31u) >> 5));
             c.wa = __ldg(ptr);
             if (hi > 16u) c.wb = __ldg(ptr + 1);
         }
@@ -340,7 +344,7 @@ count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sort
     }
 
     ChunkStream cs;
-    cs.init(text16, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane);
+    cs.init(text16, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane, plan->n_bytes);
     uint32_t carry = 0;                                             // tail of lane 31 of the previous iteration
     Chunk cur = cs.fetch();
     while (__ballot_sync(FULL, cur.range != 0) != 0) {
@@ -390,6 +394,7 @@ __device__ __forceinline__ void credit16(uint32_t* __restrict__ slab, uint32_t w
 template <int K>
 __device__ __forceinline__ void drain16(uint32_t* __restrict__ h8, uint32_t* __restrict__ slab, uint32_t word_idx)
 {
+    VK_ASSERT(word_idx < 32768u);
     uint32_t w = *reinterpret_cast<volatile uint32_t*>(h8 + word_idx);
     while ((w & 0xFFFFu) >= 0x4000u) {
         const uint32_t seen = atomicCAS(h8 + word_idx, w, 0u);
@@ -454,7 +459,7 @@ count16_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ so
     __syncthreads();
 
     ChunkStream cs;
-    cs.init(text16, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane);
+    cs.init(text16, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane, plan->n_bytes);
     uint32_t carry = 0;
     Chunk cur = cs.fetch();
     while (__ballot_sync(FULL, cur.range != 0) != 0) {

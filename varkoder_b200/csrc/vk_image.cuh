@@ -40,6 +40,7 @@ __device__ __forceinline__ unsigned long long pixel_value(const unsigned long lo
                                                           const int32_t* __restrict__ lut, uint32_t p)
 {
     const int32_t x = lut[p];
+    VK_ASSERT(x >= -1);
     return x < 0 ? 0ull : canon_l[x] + 1ull;
 }
 

@@ -146,6 +146,7 @@ __device__ __forceinline__ int32_t emit_tile(uint32_t w0, uint32_t w1, uint32_t 
         const uint32_t ph = q & 3u, rr = q >> 2;
         if (ph == 0) {                          // header line ends: the sequence line starts at the next byte
             d -= (int32_t)(rel + 1);
+            VK_ASSERT(rel < 2048u && rr < 2048u);
             if (STORE) ps[rr] = tile0 + rel + 1;
         } else if (ph == 1) {                   // sequence line ends
             d += (int32_t)rel;
