@@ -161,7 +161,7 @@ void enqueue_parse(vk_ctx* c, const vk_params* params, bool rescan = true)
         CU(cudaGetLastError());
         launch(c, parse_scan_kernel, dim3(1), dim3(1024), 0, c->tile_count.p, n_tiles, c->tile_status.p, c->plan_d);
         CU(cudaGetLastError());
-        const int egrid = (int)std::min<uint64_t>(((uint64_t)n_tiles * kParseWarps + 7) / 8, (uint64_t)c->n_sms * 32);
+        const int egrid = (int)std::min<uint64_t>(((uint64_t)n_tiles * kEmitUnitsPerTile + 7) / 8, (uint64_t)c->n_sms * 32);
         launch(c, parse_emit_kernel, dim3(egrid), dim3(256), 0, c->masks.p, c->tile_status.p, c->warp_count.p, n_tiles, 0,
                                                         c->starts.p, c->ends.p, cap, c->plan_d);
         CU(cudaGetLastError());

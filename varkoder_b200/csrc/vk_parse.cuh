@@ -120,8 +120,8 @@ parse_scan_kernel(const uint32_t* __restrict__ tile_count, uint32_t n_tiles, uin
     if (tid == 0) plan->n_newlines = carry;
 }
 
-// K1b: one WARP per 2 KiB of text (32 masks); no block-level synchronisation.
-// A warp walks a CONTIGUOUS range of warp-tiles, so the line index simply runs on from tile to tile (the tile prefix
+// K1b: one WARP per 4 KiB of text (64 masks, two per lane); no block-level synchronisation.
+// A warp walks a CONTIGUOUS range of 4 KiB units, so the line index simply runs on from tile to tile (the tile prefix
 // and the counts of the earlier warps of the tile are looked up once per warp, not per tile) and the masks are read
 // through one pointer that advances by 256 bytes.  Everything per newline is 32-bit and relative to the warp-tile:
 // line index = line_base + q, byte = tile0 + rel.  nsites = sum(ends) - sum(starts) is accumulated as one difference
@@ -132,25 +132,43 @@ __device__ __forceinline__ uint32_t count_phase(uint32_t q0, uint32_t cnt, uint3
     return ((q0 + cnt + 3u - ph) >> 2) - ((q0 + 3u - ph) >> 2);
 }
 
+// One lane decodes kEmitMasks consecutive 64-byte masks (128 bytes of text); a warp-unit is 4 KiB.
+constexpr int kEmitMasks = 2;
+constexpr uint32_t kEmitUnitBytes = 32u * 64u * kEmitMasks;                      // 4 KiB
+constexpr uint32_t kEmitUnitsPerTile = kParseTileBytes / kEmitUnitBytes;         // 8
+constexpr uint32_t kEmitWarpsPerUnit = kParseWarps / kEmitUnitsPerTile;          // K1a warps (2 KiB each) per unit: 2
+
 template <bool STORE>
-__device__ __forceinline__ int32_t emit_tile(uint32_t w0, uint32_t w1, uint32_t q, uint32_t rel0, uint64_t tile0,
+__device__ __forceinline__ int32_t emit_unit(uint32_t (&w)[2 * kEmitMasks], uint32_t q, uint32_t rel0, uint64_t unit0,
                                              uint64_t* __restrict__ ps, uint64_t* __restrict__ pe)
 {
     int32_t d = 0;                              // sum over sequence ends of rel - sum over sequence starts of rel
-    while (w0 | w1) {                           // one trip per newline of the busiest lane
-        const bool lo = w0 != 0;
-        const uint32_t w = lo ? w0 : w1;
-        const uint32_t rel = rel0 + (lo ? 0u : 32u) + (uint32_t)__ffs(w) - 1u;
-        const uint32_t cleared = w & (w - 1);
-        if (lo) w0 = cleared; else w1 = cleared;
+    uint32_t any = 0;
+#pragma unroll
+    for (int i = 0; i < 2 * kEmitMasks; ++i) any |= w[i];
+    while (any) {                               // one trip per newline of the busiest lane
+        // lowest set bit over the words, in text order
+        uint32_t cur = 0, base = 0;
+        int which = -1;
+#pragma unroll
+        for (int i = 2 * kEmitMasks - 1; i >= 0; --i)
+            if (w[i]) { cur = w[i]; base = 32u * i; which = i; }
+        const uint32_t rel = rel0 + base + (uint32_t)__ffs(cur) - 1u;
+        const uint32_t cleared = cur & (cur - 1);
+        any = 0;
+#pragma unroll
+        for (int i = 0; i < 2 * kEmitMasks; ++i) {
+            if (i == which) w[i] = cleared;
+            any |= w[i];
+        }
         const uint32_t ph = q & 3u, rr = q >> 2;
         if (ph == 0) {                          // header line ends: the sequence line starts at the next byte
             d -= (int32_t)(rel + 1);
-            VK_ASSERT(rel < 2048u && rr < 2048u);
-            if (STORE) ps[rr] = tile0 + rel + 1;
+            VK_ASSERT(rel < kEmitUnitBytes && rr < kEmitUnitBytes);
+            if (STORE) ps[rr] = unit0 + rel + 1;
         } else if (ph == 1) {                   // sequence line ends
             d += (int32_t)rel;
-            if (STORE) pe[rr] = tile0 + rel;
+            if (STORE) pe[rr] = unit0 + rel;
         }
         ++q;
     }
@@ -164,27 +182,29 @@ parse_emit_kernel(const uint64_t* __restrict__ masks, const uint64_t* __restrict
 {
     pdl_wait();
     const uint32_t lane = threadIdx.x & 31;
-    const uint64_t n_wt = (uint64_t)n_tiles * kParseWarps;                 // warp-tiles
+    const uint64_t n_units = (uint64_t)n_tiles * kEmitUnitsPerTile;
     const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    const uint64_t per = (n_wt + n_warps - 1) / n_warps;
+    const uint64_t per = (n_units + n_warps - 1) / n_warps;
     const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const uint64_t g0 = wid * per, g1 = g0 + per < n_wt ? g0 + per : n_wt;
+    const uint64_t g0 = wid * per, g1 = g0 + per < n_units ? g0 + per : n_units;
     int64_t diff = 0;
     uint32_t overflow = 0;
     if (g0 < g1) {
-        // line index of the first newline of warp-tile g0
-        const uint32_t tile = (uint32_t)(g0 / kParseWarps), wit = (uint32_t)(g0 % kParseWarps);
+        // line index of the first newline of unit g0: tile prefix + the K1a warps of the tile in front of the unit
+        const uint32_t tile = (uint32_t)(g0 / kEmitUnitsPerTile);
+        const uint32_t wit = (uint32_t)(g0 % kEmitUnitsPerTile) * kEmitWarpsPerUnit;
         const uint32_t wc = lane < wit ? warp_count[(uint64_t)tile * kParseWarps + lane] : 0u;
         uint64_t line_base = tile_prefix[tile] + __reduce_add_sync(0xffffffffu, wc);
-        const uint64_t* mp = masks + g0 * 32 + lane;
-        uint64_t m_nx = *mp;
-        const uint32_t rel0 = lane * 64u;
+        // lane l owns masks 2l, 2l+1 of the unit: one 16-byte load
+        const ulonglong2* mp = reinterpret_cast<const ulonglong2*>(masks) + g0 * 32 + lane;
+        ulonglong2 m_nx = *mp;
+        const uint32_t rel0 = lane * (64u * kEmitMasks);
         for (uint64_t g = g0; g < g1; ++g) {
-            const uint64_t m = m_nx;
+            const ulonglong2 m = m_nx;
             mp += 32;
-            if (g + 1 < g1) m_nx = *mp;                                   // next tile's masks in flight while this one is decoded
-            const uint32_t w0 = (uint32_t)m, w1 = (uint32_t)(m >> 32);
-            const uint32_t cnt = __popc(w0) + __popc(w1);
+            if (g + 1 < g1) m_nx = *mp;                                   // next unit's masks in flight while this one is decoded
+            uint32_t w[4] = {(uint32_t)m.x, (uint32_t)(m.x >> 32), (uint32_t)m.y, (uint32_t)(m.y >> 32)};
+            const uint32_t cnt = __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
             uint32_t incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -195,14 +215,14 @@ parse_emit_kernel(const uint64_t* __restrict__ masks, const uint64_t* __restrict
             const uint32_t lb = (uint32_t)line_base & 3u;
             const uint64_t r_base = line_base >> 2;
             const uint32_t q = lb + (incl - cnt);                          // (line index of this lane's first newline) - 4 r_base
-            const uint64_t tile0 = byte_base + g * 2048;
+            const uint64_t unit0 = byte_base + g * kEmitUnitBytes;
             const bool fits = r_base + ((lb + total) >> 2) < cap_reads;    // warp-uniform
             int32_t d;
-            if (fits) d = emit_tile<true>(w0, w1, q, rel0, tile0, starts + r_base, ends + r_base);
-            else { d = emit_tile<false>(w0, w1, q, rel0, tile0, nullptr, nullptr); overflow = 1; }
-            // + tile0 * (#ends - #starts), - #starts for the "+1"s already taken above via rel + 1
+            if (fits) d = emit_unit<true>(w, q, rel0, unit0, starts + r_base, ends + r_base);
+            else { d = emit_unit<false>(w, q, rel0, unit0, nullptr, nullptr); overflow = 1; }
+            // + unit0 * (#ends - #starts); the "+1" of every start is already in d
             const int32_t dn = (int32_t)count_phase(q, cnt, 1) - (int32_t)count_phase(q, cnt, 0);
-            diff += (int64_t)d + (int64_t)dn * (int64_t)tile0;
+            diff += (int64_t)d + (int64_t)dn * (int64_t)unit0;
             line_base += total;
         }
     }
