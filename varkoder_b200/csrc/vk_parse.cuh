@@ -133,7 +133,7 @@ __device__ __forceinline__ uint32_t count_phase(uint32_t q0, uint32_t cnt, uint3
 }
 
 // One lane decodes kEmitMasks consecutive 64-byte masks (128 bytes of text); a warp-unit is 4 KiB.
-constexpr int kEmitMasks = 2;
+constexpr int kEmitMasks = 2;      // 4 measured slower (339 vs 332 us per step): longer divergent loops
 constexpr uint32_t kEmitUnitBytes = 32u * 64u * kEmitMasks;                      // 4 KiB
 constexpr uint32_t kEmitUnitsPerTile = kParseTileBytes / kEmitUnitBytes;         // 8
 constexpr uint32_t kEmitWarpsPerUnit = kParseWarps / kEmitUnitsPerTile;          // K1a warps (2 KiB each) per unit: 2
@@ -195,16 +195,31 @@ parse_emit_kernel(const uint64_t* __restrict__ masks, const uint64_t* __restrict
         const uint32_t wit = (uint32_t)(g0 % kEmitUnitsPerTile) * kEmitWarpsPerUnit;
         const uint32_t wc = lane < wit ? warp_count[(uint64_t)tile * kParseWarps + lane] : 0u;
         uint64_t line_base = tile_prefix[tile] + __reduce_add_sync(0xffffffffu, wc);
-        // lane l owns masks 2l, 2l+1 of the unit: one 16-byte load
-        const ulonglong2* mp = reinterpret_cast<const ulonglong2*>(masks) + g0 * 32 + lane;
-        ulonglong2 m_nx = *mp;
+        // lane l owns masks kEmitMasks * l .. of the unit: 16-byte loads
+        constexpr int kLd = kEmitMasks / 2;
+        const ulonglong2* mp = reinterpret_cast<const ulonglong2*>(masks) + (g0 * 32 + lane) * kLd;
+        ulonglong2 m_nx[kLd];
+#pragma unroll
+        for (int i = 0; i < kLd; ++i) m_nx[i] = mp[i];
         const uint32_t rel0 = lane * (64u * kEmitMasks);
         for (uint64_t g = g0; g < g1; ++g) {
-            const ulonglong2 m = m_nx;
-            mp += 32;
-            if (g + 1 < g1) m_nx = *mp;                                   // next unit's masks in flight while this one is decoded
-            uint32_t w[4] = {(uint32_t)m.x, (uint32_t)(m.x >> 32), (uint32_t)m.y, (uint32_t)(m.y >> 32)};
-            const uint32_t cnt = __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
+            ulonglong2 m[kLd];
+#pragma unroll
+            for (int i = 0; i < kLd; ++i) m[i] = m_nx[i];
+            mp += 32 * kLd;
+            if (g + 1 < g1) {                                             // next unit's masks in flight while this one is decoded
+#pragma unroll
+                for (int i = 0; i < kLd; ++i) m_nx[i] = mp[i];
+            }
+            uint32_t w[2 * kEmitMasks];
+#pragma unroll
+            for (int i = 0; i < kLd; ++i) {
+                w[4 * i] = (uint32_t)m[i].x; w[4 * i + 1] = (uint32_t)(m[i].x >> 32);
+                w[4 * i + 2] = (uint32_t)m[i].y; w[4 * i + 3] = (uint32_t)(m[i].y >> 32);
+            }
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int i = 0; i < 2 * kEmitMasks; ++i) cnt += __popc(w[i]);
             uint32_t incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
