@@ -557,3 +557,38 @@ def test_very_long_reads_and_limits(engine, k):
     engine.parse()
     with pytest.raises(VkError, match="longer than 2\\^24-1"):
         engine.count(Params(k=k, min_bp=0, max_bp=None, is_query=True))
+
+
+def test_concurrent_contexts_are_independent():
+    """several samples in flight on one GPU (one context per host thread, as stages.images_for_samples does with
+    gpu_workers > 1): every thread gets exactly the result of a serial run"""
+    import threading
+    from varkoder_b200.engine import Engine
+    table = get_kmer_mapping(7, "cgr")
+    bufs = [synth.fixed(300_000 + 50_000 * i, 150, seed=60 + i).tobytes() for i in range(4)]
+    params = [Params(k=7, min_bp=50_000, max_bp=None, seed=100 + i) for i in range(4)]
+    ref_eng = Engine(0)
+    want = [ref_eng.reads_to_images(b, p, table, want_canon=True) for b, p in zip(bufs, params)]
+    ref_eng.close()
+    got = [None] * 4
+    errs = []
+
+    def work(i):
+        try:
+            e = Engine(0)
+            for _ in range(20):                                # keep the GPU busy with overlapping steps
+                r = e.reads_to_images(bufs[i], params[i], table, want_canon=True)
+            got[i] = r
+            e.close()
+        except Exception as ex:                                # pragma: no cover
+            errs.append(ex)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for i in range(4):
+        assert got[i].levels == want[i].levels and got[i].level_bases == want[i].level_bases
+        assert (got[i].canon == want[i].canon).all() and (got[i].pixels == want[i].pixels).all()
