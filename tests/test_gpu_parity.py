@@ -592,3 +592,16 @@ def test_concurrent_contexts_are_independent():
     for i in range(4):
         assert got[i].levels == want[i].levels and got[i].level_bases == want[i].level_bases
         assert (got[i].canon == want[i].canon).all() and (got[i].pixels == want[i].pixels).all()
+
+
+def test_more_levels_than_the_caller_guessed(engine):
+    """vk_reads_to_images renders max_levels_out levels speculatively; a ladder with more levels takes a second render"""
+    buf = synth.fixed(700_000, 150, seed=88).tobytes()
+    table = get_kmer_mapping(6, "varKode")
+    params = Params(k=6, min_bp=20_000, max_bp=None, seed=2)
+    few = engine.reads_to_images(buf, params, table, max_levels=2, want_canon=True)
+    many = engine.reads_to_images(buf, params, table, max_levels=16, want_canon=True)
+    assert len(few.levels) == len(many.levels) == 6
+    assert (few.pixels == many.pixels).all() and (few.canon == many.canon).all()
+    dev = engine.device_pixels()
+    assert tuple(dev.shape) == (6, 46, 46) and (dev.cpu().numpy() == many.pixels).all()
