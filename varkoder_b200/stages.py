@@ -15,7 +15,6 @@ What differs, by design (DESIGN.md "Boundary"):
   * the sub-sample of each level is the seeded nested rule of this project, not BBTools' RNG.
 All compute is in the CUDA library; nothing here falls back to a CPU implementation of it.
 """
-import gzip
 import hashlib
 import json
 import os
@@ -49,16 +48,19 @@ def default_engine(device=None):
     return _ENGINES[key]
 
 
+_PINNED = {}
+
+
 def read_clean_fastq(path):
-    """bytes of a cleaned FASTQ (``.fq.gz`` as written by clean_reads, image.py:529-540, or plain text)."""
-    path = str(path)
-    with open(path, "rb") as f:
-        magic = f.read(2)
-    if magic == b"\x1f\x8b":
-        with gzip.open(path, "rb") as f:
-            return f.read()
-    with open(path, "rb") as f:
-        return f.read()
+    """bytes of a cleaned FASTQ (``.fq.gz`` as written by clean_reads, image.py:529-540, or plain text) as a uint8
+    view of a page-locked buffer that this process reuses from call to call (the view is valid until the next call):
+    the H2D copy of a pinned buffer runs at PCIe speed, a pageable one at a fraction of it."""
+    from .feed import PinnedBuffer, inflate_into
+    buf = _PINNED.get(os.getpid())
+    if buf is None:
+        buf = _PINNED[os.getpid()] = PinnedBuffer(0, pinned=True)
+    n = inflate_into(path, buf)
+    return buf.array[:n]
 
 
 def _strip_suffixes(p):
