@@ -139,6 +139,7 @@ struct Chunk {
     uint32_t j;        // chunk number inside its read (0: no bases to the left)
     uint32_t rlen;     // length of the read (break points)
     int32_t q0;        // read position of byte 0 of the chunk (negative in a read's first chunk)
+    uint32_t last;     // last lane of the window that holds a chunk (warp-uniform; 31 except where units run out)
 };
 
 struct ChunkStream {
@@ -146,28 +147,54 @@ struct ChunkStream {
     const uint64_t* seg_sorted;
     unsigned long long* seg_counter;
     uint32_t seg_len, lane;
+    uint32_t n_warps, last_base;   // warps serving the segment; counter value seen by the last claim
     uint64_t text_words;   // 16-byte words of the text buffer (VK_ASSERT only)
     Unit A, B;         // A is being consumed, B follows it in the chunk stream
     uint64_t entC;     // the unit after B, on its way from memory
     uint32_t pos;      // stream position of lane 0, in A's chunk numbering
     uint32_t own, own_j;   // owner (0..31: lane of A, 32..63: lane of B) and chunk number of the last chunk of the previous window
 
+    // Guided self-scheduling: a unit is 32 reads while the segment has plenty left, 16 / 8 / 4 towards its end, so that
+    // the warps of a segment finish within a few reads of each other (a full unit is ~5 iterations = ~16 us of a warp's
+    // time when 32 warps share the SM; with fixed units that was the kernel's tail).  The chunk stream runs across
+    // units, so small units do not leave lanes idle.
     __device__ __forceinline__ uint64_t claim()
     {
+        const uint32_t left = last_base < seg_len ? seg_len - last_base : 0u;
+        const uint32_t per_warp = left / n_warps;                    // reads still unclaimed per warp, roughly
+        const uint32_t size = per_warp >= 96u ? 32u : per_warp >= 32u ? 16u : per_warp >= 8u ? 8u : 4u;
         unsigned long long r0 = 0;
-        if (lane == 0) r0 = atomicAdd(seg_counter, 32ull);
+        if (lane == 0) r0 = atomicAdd(seg_counter, (unsigned long long)size);
         const uint32_t base = (uint32_t)__shfl_sync(0xffffffffu, r0, 0);
-        return (base < seg_len && base + lane < seg_len) ? seg_sorted[base + lane] : 0ull;
+        last_base = base;
+        return (lane < size && base < seg_len && base + lane < seg_len) ? seg_sorted[base + lane] : 0ull;
     }
+    // n_warps_seg: warps that serve this segment (all CTAs of it)
     __device__ __forceinline__ void init(const uint4* t, const uint64_t* ss, uint32_t sl, unsigned long long* sc, uint32_t ln,
-                                         uint64_t n_bytes)
+                                         uint64_t n_bytes, uint32_t n_warps_seg)
     {
         text16 = t; seg_sorted = ss; seg_len = sl; seg_counter = sc; lane = ln;
         text_words = (n_bytes + 15) >> 4;
-        A = make_unit(claim(), lane);
-        B = make_unit(claim(), lane);
-        entC = claim();
         pos = 0; own = 0; own_j = 0;
+        n_warps = n_warps_seg ? n_warps_seg : 1u;
+        last_base = 0;
+        if ((uint64_t)seg_len >= 192ull * n_warps) {
+            // plenty of reads per warp: the first three units with ONE round trip to the counter and three independent
+            // loads (three dependent claims cost ~5 us of start-up latency in every warp)
+            unsigned long long r0 = 0;
+            if (lane == 0) r0 = atomicAdd(seg_counter, 96ull);
+            const uint32_t base = (uint32_t)__shfl_sync(0xffffffffu, r0, 0);
+            last_base = base + 64;
+            const uint64_t ea = (base < seg_len && base + lane < seg_len) ? seg_sorted[base + lane] : 0ull;
+            const uint64_t eb = (base + 32 < seg_len && base + 32 + lane < seg_len) ? seg_sorted[base + 32 + lane] : 0ull;
+            entC = (base + 64 < seg_len && base + 64 + lane < seg_len) ? seg_sorted[base + 64 + lane] : 0ull;
+            A = make_unit(ea, lane);
+            B = make_unit(eb, lane);
+        } else {                                                        // small segment: unit by unit keeps the warps balanced
+            A = make_unit(claim(), lane);
+            B = make_unit(claim(), lane);
+            entC = claim();
+        }
     }
     __device__ __forceinline__ Chunk fetch()
     {
@@ -180,8 +207,11 @@ struct ChunkStream {
             entC = claim();
         }
         Chunk c;
-        const uint32_t f = pos + lane;
-        const bool act = f < A.total + B.total;
+        const uint32_t endAB = A.total + B.total;
+        // chunks available to this window: 32 except where A and B together hold fewer (small units towards the end of
+        // the segment); the window after this one starts right behind the last chunk taken
+        const uint32_t nact = endAB > pos ? (endAB - pos < 32u ? endAB - pos : 32u) : 0u;
+        const bool act = lane < nact;
         // one bit per read whose first chunk lies in the window [pos, pos + 32)
         const uint32_t sa = A.excl - pos, sb = A.total + B.excl - pos;
         const bool hasA = (uint32_t)(A.ent & kEntryLenMask) != 0, hasB = (uint32_t)(B.ent & kEntryLenMask) != 0;
@@ -198,8 +228,9 @@ struct ChunkStream {
             o = ord < A.nz ? ord : ord - A.nz + 32;
             j = lane - hb;
         }
-        own = __shfl_sync(FULL, o, 31);
-        own_j = __shfl_sync(FULL, j, 31);
+        const int last = nact ? (int)nact - 1 : 31;
+        own = __shfl_sync(FULL, o, last);
+        own_j = __shfl_sync(FULL, j, last);
         uint64_t e = __shfl_sync(FULL, A.ent, (int)(o & 31u));
         if (pos + 32u > A.total) {                                  // warp-uniform: the window reaches into B
             const uint64_t eb = __shfl_sync(FULL, B.ent, (int)(o & 31u));
@@ -223,7 +254,8 @@ struct ChunkStream {
         c.j = j;
         c.rlen = rlen;
         c.q0 = (int32_t)(32u * j) - (int32_t)rlo;
-        pos += 32;
+        c.last = (uint32_t)last;
+        pos += nact ? nact : 32u;
         return c;
     }
 };
@@ -252,7 +284,7 @@ __device__ __forceinline__ Decoded decode_chunk(const Chunk& cur, uint32_t& carr
     uint32_t hist = __shfl_up_sync(FULL, tail, 1);
     if (lane == 0) hist = carry;
     if (cur.j == 0) hist = 0;
-    carry = __shfl_sync(FULL, tail, 31);
+    carry = __shfl_sync(FULL, tail, (int)cur.last);
     d.Cc = hist & 0xFFFFu;
     const uint32_t Vc = hist >> 16;
     const uint64_t VW = (uint64_t)Vc | ((uint64_t)V << KM1);        // bit i <-> base i - (K-1) of the chunk
@@ -344,7 +376,8 @@ count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sort
     }
 
     ChunkStream cs;
-    cs.init(text16, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane, plan->n_bytes);
+    cs.init(text16, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane, plan->n_bytes,
+            (plan->seg_cta_begin[seg + 1] - plan->seg_cta_begin[seg]) * (blockDim.x >> 5));
     uint32_t carry = 0;                                             // tail of lane 31 of the previous iteration
     Chunk cur = cs.fetch();
     while (__ballot_sync(FULL, cur.range != 0) != 0) {
@@ -459,7 +492,8 @@ count16_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ so
     __syncthreads();
 
     ChunkStream cs;
-    cs.init(text16, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane, plan->n_bytes);
+    cs.init(text16, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane, plan->n_bytes,
+            (plan->seg_cta_begin[seg + 1] - plan->seg_cta_begin[seg]) * (blockDim.x >> 5));
     uint32_t carry = 0;
     Chunk cur = cs.fetch();
     while (__ballot_sync(FULL, cur.range != 0) != 0) {
