@@ -28,8 +28,9 @@
 //
 // Three ways to count (template MODE):
 //   kSmem32   k <= 7: 4^k x u32 bins in shared memory, one ATOMS.POPC.INC per base.  Lanes without a k-mer
-//             increment a per-lane trash word: ptxas cannot predicate ATOMS.POPC.INC (it branches around it) and a
-//             sparsely populated ATOMS costs as much as a full one (profiles/microbench_atomics_r01.txt).
+//             increment one common trash word (POPC.INC folds lanes with the same address, so they add a single bank
+//             access; per-lane trash words measured 142.5 us against 139.3 us): ptxas cannot predicate ATOMS.POPC.INC
+//             (it branches around it) and a sparsely populated ATOMS costs as much as a full one.
 //   kSmem16   k = 7, 8: 4^8 16-bit bins (two per 32-bit word, 128 KiB).  k = 8 counts every 8-mer; k = 7 counts
 //             PAIRS: the 8-mer that ends at an odd chunk position stands for the two 7-mers it contains, so a base
 //             pair costs one shared-memory operation instead of two (the kernel is bound by the shared-memory data
@@ -356,7 +357,7 @@ count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sort
     constexpr uint32_t NK = 1u << (2 * K);
     constexpr int KM1 = K - 1;
     constexpr uint32_t FULL = 0xffffffffu;
-    extern __shared__ uint32_t s_raw[];           // kSmem32: [pad to a 64 KiB shared address][NK bins][32 trash words]
+    extern __shared__ uint32_t s_raw[];           // kSmem32: [pad to a 64 KiB shared address][NK bins][trash word]
     const uint32_t tid = threadIdx.x, lane = tid & 31;
 
     const int seg = cta_segment(plan, lane);
@@ -369,7 +370,7 @@ count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sort
     const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(s_raw);
     const uint32_t hist_addr = MODE == kSmem32 ? (raw_addr + 0xFFFFu) & ~0xFFFFu : 0u;
     uint32_t* const s_hist = s_raw + ((hist_addr - raw_addr) >> 2);
-    const uint32_t trash_addr = hist_addr + (NK + lane) * 4u;
+    const uint32_t trash_addr = hist_addr + NK * 4u;
     if (MODE == kSmem32) {
         for (uint32_t i = tid; i < NK + 32; i += blockDim.x) s_hist[i] = 0;
         __syncthreads();
