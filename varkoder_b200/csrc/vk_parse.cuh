@@ -182,27 +182,34 @@ parse_emit_kernel(const uint64_t* __restrict__ masks, const uint64_t* __restrict
 {
     pdl_wait();
     const uint32_t lane = threadIdx.x & 31;
-    const uint64_t n_units = (uint64_t)n_tiles * kEmitUnitsPerTile;
-    const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    const uint64_t per = (n_units + n_warps - 1) / n_warps;
-    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const uint64_t g0 = wid * per, g1 = g0 + per < n_units ? g0 + per : n_units;
+    // 32-bit unit arithmetic: the text is shorter than 2^40 bytes, so there are fewer than 2^28 units
+    const uint32_t n_units = n_tiles * kEmitUnitsPerTile;
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t per = (n_units + n_warps - 1) / n_warps;
+    const uint32_t wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t g0_64 = (uint64_t)wid * per;
+    const uint32_t g0 = g0_64 < n_units ? (uint32_t)g0_64 : n_units, g1 = n_units - g0 < per ? n_units : g0 + per;
     int64_t diff = 0;
     uint32_t overflow = 0;
     if (g0 < g1) {
         // line index of the first newline of unit g0: tile prefix + the K1a warps of the tile in front of the unit
-        const uint32_t tile = (uint32_t)(g0 / kEmitUnitsPerTile);
-        const uint32_t wit = (uint32_t)(g0 % kEmitUnitsPerTile) * kEmitWarpsPerUnit;
+        const uint32_t tile = g0 / kEmitUnitsPerTile;
+        const uint32_t wit = (g0 % kEmitUnitsPerTile) * kEmitWarpsPerUnit;
         const uint32_t wc = lane < wit ? warp_count[(uint64_t)tile * kParseWarps + lane] : 0u;
         uint64_t line_base = tile_prefix[tile] + __reduce_add_sync(0xffffffffu, wc);
         // lane l owns masks kEmitMasks * l .. of the unit: 16-byte loads
         constexpr int kLd = kEmitMasks / 2;
-        const ulonglong2* mp = reinterpret_cast<const ulonglong2*>(masks) + (g0 * 32 + lane) * kLd;
+        const ulonglong2* mp = reinterpret_cast<const ulonglong2*>(masks) + ((uint64_t)g0 * 32 + lane) * kLd;
         ulonglong2 m_nx[kLd];
 #pragma unroll
         for (int i = 0; i < kLd; ++i) m_nx[i] = mp[i];
         const uint32_t rel0 = lane * (64u * kEmitMasks);
-        for (uint64_t g = g0; g < g1; ++g) {
+        // nsites pieces, relative to the warp's first unit: d_sum = sum of the in-unit parts, dn_sum = #ends - #starts,
+        // dn_units = sum of (#ends - #starts) x (unit - g0); put together once after the loop
+        int64_t d_sum = 0;
+        int32_t dn_sum = 0;
+        int64_t dn_units = 0;
+        for (uint32_t g = g0; g < g1; ++g) {
             ulonglong2 m[kLd];
 #pragma unroll
             for (int i = 0; i < kLd; ++i) m[i] = m_nx[i];
@@ -230,16 +237,20 @@ parse_emit_kernel(const uint64_t* __restrict__ masks, const uint64_t* __restrict
             const uint32_t lb = (uint32_t)line_base & 3u;
             const uint64_t r_base = line_base >> 2;
             const uint32_t q = lb + (incl - cnt);                          // (line index of this lane's first newline) - 4 r_base
-            const uint64_t unit0 = byte_base + g * kEmitUnitBytes;
+            const uint64_t unit0 = byte_base + (uint64_t)g * kEmitUnitBytes;
             const bool fits = r_base + ((lb + total) >> 2) < cap_reads;    // warp-uniform
             int32_t d;
             if (fits) d = emit_unit<true>(w, q, rel0, unit0, starts + r_base, ends + r_base);
             else { d = emit_unit<false>(w, q, rel0, unit0, nullptr, nullptr); overflow = 1; }
-            // + unit0 * (#ends - #starts); the "+1" of every start is already in d
+            // the "+1" of every start is already in d
             const int32_t dn = (int32_t)count_phase(q, cnt, 1) - (int32_t)count_phase(q, cnt, 0);
-            diff += (int64_t)d + (int64_t)dn * (int64_t)unit0;
+            d_sum += d;
+            dn_sum += dn;                                                  // |dn| <= 32 per unit and lane
+            dn_units += (int32_t)(dn * (int32_t)(g - g0));
             line_base += total;
         }
+        diff = d_sum + dn_units * (int64_t)kEmitUnitBytes
+             + (int64_t)dn_sum * (int64_t)(byte_base + (uint64_t)g0 * kEmitUnitBytes);
     }
     uint64_t sum = (uint64_t)diff;
 #pragma unroll
