@@ -159,6 +159,15 @@ int vk_device_pixels(vk_ctx* ctx, const uint8_t** dev_pixels, int32_t* n_levels,
 int vk_remap(vk_ctx* ctx, int n_images, uint32_t n_in_pixels, uint32_t n_out_pixels, const uint8_t* in_host,
              const int32_t* src0, const int32_t* src1, const uint8_t* mult, int sum_rc, uint8_t* out_host);
 
+/* Per-position base content of the framed reads of the current text -- the numbers fastp's "content_curves" are made
+ * of, which the reference reads back from the fastp report to set varkoderBaseFreqSd / varkoderLowQualityFlag
+ * (get_basefrequency_sd, varKoder/commands/image.py:49-88; used at :1093-1096).
+ * counts_host[(p - pos_begin) * 5 + j], pos_begin <= p < pos_end (at most 64 positions per call):
+ *   j = 0..3  reads whose base at position p is A, T, C, G (fastp's classes: byte & 7 == 1, 4, 3, 7),
+ *   j = 4     reads that have a position p at all (the curve's denominator; N and anything else only count here).
+ * Needs framing: after vk_parse, vk_count or vk_reads_to_images on the current text.  Synchronises. */
+int vk_base_content(vk_ctx* ctx, int32_t pos_begin, int32_t pos_end, uint64_t* counts_host);
+
 /* Device time of the last vk_reads_to_images / stage call, per kernel group, in milliseconds (CUDA events on
  * the context stream): [0] upload (H2D), [1] parse, [2] plan+bucket, [3] count kernel, [4] slab reduce+fold,
  * [5] render, [6] read-back (D2H), [7] total. */

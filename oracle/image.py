@@ -233,3 +233,20 @@ def remap_exact(img, lut_in, lut_out, k, in_is_cgr, out_is_cgr, sum_rc=False):
     with np.errstate(all="ignore"):
         out = np.uint8((new - np.uint8(mn)) / np.uint8(mx) * 255) if mx else np.zeros_like(new)
     return out.reshape(np.asarray(lut_out).shape)
+
+
+# ---- quality flag ---------------------------------------------------------------------------
+def base_content(buf, starts, lens, pos_begin=5, pos_end=40):
+    """numpy restatement of what fastp accumulates for its content curves (per cycle: bases by ``byte & 7`` and the
+    number of reads that reach the cycle), over the framed reads: -> uint64 [pos_end - pos_begin, 5] (A, T, C, G, reach).
+    The reference consumes the curves in get_basefrequency_sd (varKoder/commands/image.py:49-88)."""
+    a = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+    starts = np.asarray(starts, dtype=np.int64)
+    lens = np.asarray(lens, dtype=np.int64)
+    out = np.zeros((pos_end - pos_begin, 5), dtype=np.uint64)
+    for i, p in enumerate(range(pos_begin, pos_end)):
+        sel = lens > p
+        b = a[starts[sel] + p] & 7
+        out[i] = [np.count_nonzero(b == 1), np.count_nonzero(b == 4), np.count_nonzero(b == 3),
+                  np.count_nonzero(b == 7), b.size]
+    return out

@@ -605,3 +605,56 @@ def test_more_levels_than_the_caller_guessed(engine):
     assert (few.pixels == many.pixels).all() and (few.canon == many.canon).all()
     dev = engine.device_pixels()
     assert tuple(dev.shape) == (6, 46, 46) and (dev.cpu().numpy() == many.pixels).all()
+
+
+# ------------------------------------------------------------------------------------- quality flag (N4)
+def test_base_content_matches_reference_goldens(engine, golden_dir):
+    """vk_base_content == the counts behind the golden fastp curves; the host tail then gives the value the imported
+    reference returned (tests/golden/base_sd.json, oracle/make_golden_quality.py)."""
+    from oracle.make_golden_quality import fastq_case
+    from varkoder_b200 import quality
+    for c in json.load(open(os.path.join(golden_dir, "base_sd.json"))):
+        buf = fastq_case(c["seed"], c["n_reads"], c["len_lo"], c["len_hi"], c["bias"])
+        engine.upload(buf)
+        engine.parse()
+        counts = engine.base_content()
+        assert counts.astype(int).tolist() == c["counts_5_40"], c["name"]
+        with np.errstate(all="ignore"):
+            sd = quality.base_frequency_sd(counts)
+        assert (np.isnan(sd) and c["base_sd"] is None) or float(sd).hex() == c["base_sd_hex"], c["name"]
+
+
+def test_base_content_large_and_after_fused_call(engine, tmp_path):
+    """20 Mbp of ragged reads (Bembidion-shaped): counts for cycles 0..63 equal the oracle's; the fused host call with base_sd=None writes
+    the measured value into the PNG keys the reference writes (image.py:920-930) and into the stats key of :1096."""
+    from PIL import Image
+    from varkoder_b200 import quality, stages
+    buf = synth.variable(120_000, seed=77).tobytes()          # lengths 60..280, 1 % shorter than k (incl. empty)
+    p = dsk.parse_fastq(buf)
+    table = get_kmer_mapping(7, "cgr")
+    engine.reads_to_images(buf, Params(k=7, min_bp=500_000, max_bp=None, seed=3), table)
+    assert (engine.base_content(0, 64) == oimg.base_content(buf, p["starts"], p["lens"], 0, 64)).all()
+    assert (engine.base_content(30, 40) == oimg.base_content(buf, p["starts"], p["lens"], 30, 40)).all()
+    st = stages.reads_to_images(None, "q", tmp_path, table, k=7, mapping_code="cgr", min_bp=500_000, max_bp=1_000_000,
+                                seed=1, base_sd=None, engine=engine, fastq_bytes=buf)
+    want = quality.base_frequency_sd(oimg.base_content(buf, p["starts"], p["lens"], 5, 40))
+    assert st["base_frequencies_sd"] == want
+    im = Image.open(sorted(tmp_path.glob("q@*.png"))[0])
+    assert im.info["varkoderBaseFreqSd"] == str(want) and im.info["varkoderLowQualityFlag"] == str(want > 0.01)
+
+
+def test_base_content_argument_and_state_errors():
+    from varkoder_b200.engine import Engine, VkError
+    e = Engine(0)
+    try:
+        with pytest.raises(VkError):
+            e.base_content()                       # nothing framed yet
+        e.upload(fastq(["ACGTACGTACGT"]))
+        e.parse()
+        with pytest.raises(VkError):
+            e.base_content(10, 10)
+        with pytest.raises(VkError):
+            e.base_content(0, 65)
+        assert e.base_content(0, 12)[:, 4].tolist() == [1] * 12
+    finally:
+        e.close()

@@ -152,3 +152,25 @@ def test_remap_golden(golden_dir, k):
         src, dst = d.split("_to_")
         got = oimg.remap_exact(z[key + "__in"], luts[src], luts[dst], k, src == "cgr", dst == "cgr", mode == "sum")
         assert (got == z[key + "__out"]).all(), key
+
+
+def test_quality_flag_golden(golden_dir):
+    """get_basefrequency_sd (image.py:49-88) run on fastp-shaped reports built from the oracle's counts
+    (oracle/make_golden_quality.py): the numpy restatement of the counts and the host arithmetic of
+    varkoder_b200.quality reproduce the stored counts and the reference's float64 value bit for bit."""
+    from oracle.make_golden_quality import fastq_case
+    from varkoder_b200 import quality
+    cases = json.load(open(os.path.join(golden_dir, "base_sd.json")))
+    assert len(cases) >= 5
+    for c in cases:
+        buf = fastq_case(c["seed"], c["n_reads"], c["len_lo"], c["len_hi"], c["bias"])
+        p = dsk.parse_fastq(buf)
+        counts = oimg.base_content(buf, p["starts"], p["lens"], 5, 40)
+        assert counts.astype(int).tolist() == c["counts_5_40"], c["name"]
+        with np.errstate(all="ignore"):
+            sd = quality.base_frequency_sd(counts)
+        if c["base_sd"] is None:
+            assert np.isnan(sd), c["name"]
+        else:
+            assert float(sd).hex() == c["base_sd_hex"], c["name"]
+        assert quality.low_quality_flag(sd) == (c["base_sd"] is not None and c["base_sd"] > 0.01)

@@ -17,6 +17,7 @@ VK_LADDER_LESS_THAN_MIN = 1
 SYMBOLS = [
     "vk_abi_version", "vk_last_error", "vk_ctx_create", "vk_ctx_destroy", "vk_set_mapping", "vk_upload",
     "vk_attach", "vk_parse", "vk_count", "vk_render", "vk_render_counts", "vk_reads_to_images", "vk_device_pixels", "vk_remap",
+    "vk_base_content",
     "vk_last_timings", "vk_set_fine_timing", "vk_launch_count", "vk_bucket_retries", "vk_synth_fastq",
 ]
 
@@ -71,6 +72,7 @@ def load():
                                      C.POINTER(VkResult), vp, vp]
     L.vk_device_pixels.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.vk_remap.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, vp, vp, vp, vp, C.c_int, vp]
+    L.vk_base_content.argtypes = [vp, C.c_int32, C.c_int32, vp]
     L.vk_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.vk_set_fine_timing.argtypes = [vp, C.c_int]
     L.vk_launch_count.argtypes = [vp]

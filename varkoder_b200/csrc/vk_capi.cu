@@ -11,6 +11,7 @@
 #include "vk_count.cuh"
 #include "vk_image.cuh"
 #include "vk_parse.cuh"
+#include "vk_quality.cuh"
 #include "vk_synth.cuh"
 
 namespace {
@@ -106,6 +107,7 @@ struct vk_ctx {
     DevBuf<unsigned long long> seg_hist, canon, vals, bins;
     DevBuf<uint8_t> remap_in, remap_out, remap_mult;
     DevBuf<int32_t> remap_src;
+    DevBuf<unsigned long long> content;
     Mapping maps[4];
 
     bool fine_timing = true;        // vk_set_fine_timing: events between the kernel groups (they serialise the stream)
@@ -721,6 +723,32 @@ int vk_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, int on_dev
             CU(cudaMemcpyAsync(canon_host, c->canon.p, (size_t)nl * nk * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
         }
+    });
+}
+
+int vk_base_content(vk_ctx* c, int32_t pos_begin, int32_t pos_end, uint64_t* counts_host)
+{
+    return guarded([&] {
+        if (!c || !counts_host) throw ApiError{VK_EINVAL, "NULL argument"};
+        if (pos_begin < 0 || pos_end <= pos_begin || pos_end - pos_begin > vk::kContentMaxPos)
+            throw ApiError{VK_EINVAL, "positions must satisfy 0 <= begin < end <= begin + 64"};
+        if (!c->have_text || !c->parsed) throw ApiError{VK_ESTATE, "vk_base_content needs framed reads: call vk_parse, vk_count or vk_reads_to_images first"};
+        set_device(c);
+        const uint32_t n_pos = (uint32_t)(pos_end - pos_begin);
+        const size_t n = (size_t)n_pos * 5;
+        c->content.ensure(n);
+        CU(cudaMemsetAsync(c->content.p, 0, n * sizeof(unsigned long long), c->stream));
+        const uint64_t n_reads = c->plan_h->n_reads;
+        if (n_reads) {
+            const unsigned grid = (unsigned)std::min<uint64_t>((n_reads + vk::kContentThreads - 1) / vk::kContentThreads,
+                                                               (uint64_t)c->n_sms * 8);
+            launch(c, vk::base_content_kernel, dim3(grid), dim3(vk::kContentThreads), 0, c->text, (const uint64_t*)c->starts.p,
+                   (const uint64_t*)c->ends.p, (const vk::Plan*)c->plan_d, (uint32_t)pos_begin, n_pos, c->content.p);
+            CU(cudaGetLastError());
+            ++c->launches;
+        }
+        CU(cudaMemcpyAsync(counts_host, c->content.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
     });
 }
 

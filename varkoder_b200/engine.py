@@ -207,6 +207,13 @@ class Engine:
                                      mult.ctypes.data, 1 if sum_rc else 0, out.ctypes.data))
         return out
 
+    def base_content(self, pos_begin=5, pos_end=40):
+        """per-position base content of the framed reads: uint64 [pos_end - pos_begin, 5], columns A, T, C, G, reads
+        reaching the position (vk_base_content; the input of quality.base_frequency_sd)"""
+        out = np.zeros((int(pos_end) - int(pos_begin), 5), dtype=np.uint64)
+        self._check(self._L.vk_base_content(self._ctx, int(pos_begin), int(pos_end), out.ctypes.data))
+        return out
+
     def device_pixels(self):
         """the images of the last render as a torch uint8 CUDA tensor [levels, side, side] that ALIASES the context's
         buffer (valid until the next render): the hand-off to a classifier that stays on the GPU (query.py:283-314)."""

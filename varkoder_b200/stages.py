@@ -28,6 +28,7 @@ import numpy as np
 from .engine import Engine, Params
 from .ladder import (BP_KMER_SEP, LABELS_SEP, QUAL_THRESH, SAMPLE_BP_SEP, LessThanMinimumData, image_name,
                      ladder, level_tag)
+from . import quality
 from .mapping import as_pixel_table
 
 _ENGINES = {}
@@ -114,6 +115,9 @@ def reads_to_images(infile, sample, outfolder, kmer_mapping, k=7, mapping_code="
         eprint("Post-cleaning input file " + str(infile) + " has less than " + str(min_bp)
                + "bp, decrease --min_bp if you want to produce an image.")
         raise LessThanMinimumData()
+    measured_sd = None
+    if base_sd is None:                 # no fastp report: the quality flag from the reads themselves (quality.py)
+        measured_sd = base_sd = quality.base_frequency_sd(eng.base_content())
     t1 = time.perf_counter()
     written = []
     for lvl, bp in enumerate(res.levels):
@@ -131,6 +135,8 @@ def reads_to_images(infile, sample, outfolder, kmer_mapping, k=7, mapping_code="
     stats["splitting_bp_per_file"] = ",".join(str(x) for x in res.levels)
     stats[str(k) + "mer_counting_time"] = (tm["count"] + tm["reduce_fold"]) / 1e3
     stats["k" + str(k) + "_img_time"] = tm["render"] / 1e3 + (t2 - t1)
+    if measured_sd is not None:
+        stats["base_frequencies_sd"] = measured_sd          # the key run_clean2img sets (image.py:1096)
     if verbose:
         eprint(f"varkoder_b200: {sample}: {res.nsites} bp, levels {res.levels}, "
                f"read+gpu {t1 - t0:.3f}s, png {t2 - t1:.3f}s")
@@ -248,7 +254,9 @@ def images_for_samples(samples, outfolder, kmer_mapping, k=7, mapping_code="varK
     sample is a chain of short dependent kernels and three or four samples in flight fill the gaps (600 -> 766
     Gbases/s on 200 Mbp samples, 68 -> 180 on 10 Mbp ones, profiles/r01_notes.md).
 
-    ``samples``: iterable of dicts ``{"sample": name, "path": clean .fq(.gz), "labels": [...], "base_sd": float}``.
+    ``samples``: iterable of dicts ``{"sample": name, "path": clean .fq(.gz), "labels": [...], "base_sd": float}``;
+    ``"base_sd": None`` measures the quality flag from the reads on the GPU (quality.py) instead of taking it from a
+    fastp report.
     ``seeds``: per-sample seeds (default: the sample's position).  ``engine``: use this one context only.
     Returns ``{sample: stats}`` (submission order) with the reference's stats keys; a sample with too little data gets
     ``{"failed_step": "split"}`` exactly as run_clean2img records it (image.py:1020-1027), and ``on_error(sample,
@@ -280,14 +288,17 @@ def images_for_samples(samples, outfolder, kmer_mapping, k=7, mapping_code="varK
         try:
             res = eng.reads_to_images(buf.array[:n], params, table)
             tm = eng.timings()
+            sd = s.get("base_sd", 0)
+            if sd is None:              # no fastp report for this sample: measure it (quality.py)
+                sd = quality.base_frequency_sd(eng.base_content())
         finally:
             feeder.release(buf)
-        return res, tm, time.perf_counter() - t0
+        return res, tm, time.perf_counter() - t0, sd
 
     all_stats = OrderedDict()
     png_jobs = []
 
-    def finish(s, res, tm, dt, feeder):
+    def finish(s, res, tm, dt, sd, feeder):
         name = str(s["sample"])
         if res.status != 0:
             if on_error is not None:
@@ -299,6 +310,8 @@ def images_for_samples(samples, outfolder, kmer_mapping, k=7, mapping_code="varK
         stats["splitting_bp_per_file"] = ",".join(str(x) for x in res.levels)
         stats[str(k) + "mer_counting_time"] = (tm["count"] + tm["reduce_fold"]) / 1e3
         stats["k" + str(k) + "_img_time"] = dt
+        if s.get("base_sd", 0) is None:
+            stats["base_frequencies_sd"] = sd
         all_stats[name] = stats
         for lvl, bp in enumerate(res.levels):
             outfile = image_name(name, bp, mapping_code, k)
@@ -306,7 +319,7 @@ def images_for_samples(samples, outfolder, kmer_mapping, k=7, mapping_code="varK
             if not overwrite and (folder / outfile).is_file():
                 continue
             png_jobs.append(feeder.pool.submit(write_png, res.pixels[lvl].copy(), folder / outfile,
-                                               s.get("labels", ()), s.get("base_sd", 0), QUAL_THRESH, mapping_code))
+                                               s.get("labels", ()), sd, QUAL_THRESH, mapping_code))
 
     gpu_pool = ThreadPoolExecutor(max_workers=max(1, int(gpu_workers)), thread_name_prefix="vk-gpu")
     try:
