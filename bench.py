@@ -440,7 +440,7 @@ def main():
         barrier()
         sh_ms = 1e3 * (time.perf_counter() - t0) / s_steps
         sharded = {"workload": f"one sample of {world}x{n_bases} bases read-sharded over {world} GPUs, k={K} {MAPPING}, "
-                               f"{len(rs.levels)} levels, all_gather(2 scalars) + NCCL all_reduce(int64 x {seg.numel()})",
+                               f"{len(rs.levels)} levels, all_gather(2 scalars) + ONE NCCL all_reduce(int64 x {len(rs.levels) * 4 ** K + 128})",
                    "steps": s_steps, "ms_per_step_wall": sh_ms, "value": world * n_bases / (sh_ms * 1e-3) / 1e9,
                    "unit": "Gbases/s"}
 

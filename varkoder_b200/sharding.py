@@ -75,9 +75,10 @@ def _exchange_shard_stats(n_reads, nsites, group=None):
     rank = dist.get_rank(group)
     dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
     mine = torch.tensor([int(n_reads), int(nsites)], dtype=torch.int64, device=dev)
-    allv = [torch.zeros_like(mine) for _ in range(world)]
-    dist.all_gather(allv, mine, group=group)
-    per_rank = [(int(v[0]), int(v[1])) for v in (t.cpu() for t in allv)]
+    allv = torch.empty(2 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allv, mine, group=group)
+    flat = allv.cpu().tolist()                                   # one read-back for all ranks
+    per_rank = [(flat[2 * r], flat[2 * r + 1]) for r in range(world)]
     base = sum(r for r, _ in per_rank[:rank])
     total = sum(s for _, s in per_rank)
     return base, total, per_rank
@@ -99,23 +100,31 @@ def sharded_count(engine, shard_bytes, params: Params, seg_hist, group=None):
     base, total, per_rank = _exchange_shard_stats(st["n_reads"], st["nsites"], group)
     p = replace(params, read_index_base=base, nsites_override=total)      # 0 bases in total: every shard is empty too
     res = engine.count(p, seg_hist.data_ptr())
-    # the one exchange step of the path; every rank derives the same ladder, so only its levels are exchanged
-    n_words = max(len(res.levels), 1) * nk
-    dist.all_reduce(seg_hist.view(torch.int64)[:n_words], op=dist.ReduceOp.SUM, group=group)
-    # realised reads / bases per level, summed over shards (same reduction, tiny)
+    # the one exchange step of the path; every rank derives the same ladder, so only its levels are exchanged.  The
+    # realised reads / bases per level ride along in the first unused row of the table (same reduction, one collective)
     nl = len(res.levels)
-    dev = seg_hist.device
-    tot = torch.zeros(2 * _lib.VK_MAX_LEVELS, dtype=torch.int64, device=dev)
+    M = _lib.VK_MAX_LEVELS
+    words = seg_hist.view(torch.int64)
+    mine = torch.zeros(2 * M, dtype=torch.int64)
     if nl:
-        tot[:nl] = torch.tensor(res.level_reads, dtype=torch.int64, device=dev)
-        tot[_lib.VK_MAX_LEVELS:_lib.VK_MAX_LEVELS + nl] = torch.tensor(res.level_bases, dtype=torch.int64, device=dev)
-    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
-    tot = tot.cpu()
+        mine[:nl] = torch.tensor(res.level_reads, dtype=torch.int64)
+        mine[M:M + nl] = torch.tensor(res.level_bases, dtype=torch.int64)
+    if nl < M and nk >= 2 * M:
+        tail = words[nl * nk:nl * nk + 2 * M]
+        tail.copy_(mine)
+        dist.all_reduce(words[:nl * nk + 2 * M], op=dist.ReduceOp.SUM, group=group)
+        tot = tail.to("cpu", copy=True)            # copy: on a CPU tensor .cpu() would alias the row zeroed next
+        tail.zero_()
+    else:
+        dist.all_reduce(words[:max(nl, 1) * nk], op=dist.ReduceOp.SUM, group=group)
+        tot = mine.to(seg_hist.device)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+        tot = tot.cpu()
     n_reads = sum(r for r, _ in per_rank)
     return Result(n_bytes=st["n_bytes"], n_lines=st["n_lines"], n_reads=n_reads, nsites=total,
                   nsites_true=st["nsites_true"], status=res.status, levels=res.levels,
                   level_reads=[int(x) for x in tot[:nl]],
-                  level_bases=[int(x) for x in tot[_lib.VK_MAX_LEVELS:_lib.VK_MAX_LEVELS + nl]])
+                  level_bases=[int(x) for x in tot[M:M + nl]])
 
 
 def sharded_reads_to_images(engine, shard_bytes, params: Params, table, seg_hist=None, group=None,
