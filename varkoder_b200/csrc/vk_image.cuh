@@ -75,20 +75,48 @@ image_kernel_cluster(const unsigned long long* __restrict__ canon, const int32_t
         own[i] = p < n_pix ? (pixel_value(canon_l, lut, p) << kImgIdxBits) | p : ~0ull;
     }
     __syncthreads();
-    // ---- bitonic sort of the slice, ascending; comparators of stride < 32 stay inside one warp's 64 elements
-    for (uint32_t size = 2; size <= S; size <<= 1) {
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t t = tid; t < (S >> 1); t += nthr) {
-                const uint32_t lo = 2 * t - (t & (stride - 1));
+    // ---- bitonic sort of the slice, ascending.  blockDim.x = S / 2: a thread owns elements e0 = 64 warp + lane and
+    // e0 + 32, so every comparator of stride <= 32 stays inside a warp: stride 32 inside the thread, strides 16..1 by
+    // shuffle, all in registers.  Only the strides >= 64 of the sizes >= 128 go through shared memory (15 steps with a
+    // block barrier for S = 2048, instead of 66 shared-memory steps).
+    {
+        constexpr uint32_t FULL = 0xffffffffu;
+        VK_ASSERT(2 * nthr == S);
+        const uint32_t e0 = 64u * (tid >> 5) + (tid & 31u), e1 = e0 + 32u;
+        unsigned long long a = own[e0], b = own[e1];
+        auto low_strides = [&](const uint32_t size, uint32_t stride) {            // strides stride..1 (stride <= 32)
+            if (stride == 32u) {
+                const bool up = (e0 & size) == 0;
+                if ((a > b) == up) { const unsigned long long t = a; a = b; b = t; }
+                stride = 16u;
+            }
+            for (; stride > 0; stride >>= 1) {
+                const unsigned long long oa = __shfl_xor_sync(FULL, a, stride), ob = __shfl_xor_sync(FULL, b, stride);
+                // keep the smaller key iff (this is the lower partner) == (the run is ascending)
+                const bool lower = (e0 & stride) == 0;                              // same for e1 (stride < 32)
+                const bool keep_min_a = lower == ((e0 & size) == 0), keep_min_b = lower == ((e1 & size) == 0);
+                a = (oa < a) == keep_min_a ? oa : a;
+                b = (ob < b) == keep_min_b ? ob : b;
+            }
+        };
+        for (uint32_t size = 2; size <= 64u && size <= S; size <<= 1) low_strides(size, size >> 1);
+        for (uint32_t size = 128; size <= S; size <<= 1) {
+            own[e0] = a; own[e1] = b;
+            __syncthreads();
+            for (uint32_t stride = size >> 1; stride >= 64u; stride >>= 1) {
+                const uint32_t lo = 2 * tid - (tid & (stride - 1));
                 const uint32_t hi = lo + stride;
                 const bool up = (lo & size) == 0;
-                const unsigned long long a = own[lo], b = own[hi];
-                if ((a > b) == up) { own[lo] = b; own[hi] = a; }
+                const unsigned long long x = own[lo], y = own[hi];
+                if ((x > y) == up) { own[lo] = y; own[hi] = x; }
+                __syncthreads();
             }
-            if (stride > 16) __syncthreads(); else __syncwarp();
+            a = own[e0]; b = own[e1];
+            low_strides(size, 32u);
         }
-        __syncthreads();
+        own[e0] = a; own[e1] = b;         // (a thread's pair was last read by the thread itself)
     }
+    __syncthreads();
     // ---- all-gather of the sorted slices over distributed shared memory (all remote loads of a thread in flight at once)
     cluster.sync();
     for (uint32_t i = tid; i < S; i += nthr) {
