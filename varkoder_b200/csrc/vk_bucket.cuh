@@ -69,9 +69,15 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
                 if (len > kEntryLenMask) atomicAdd(&s_long, 1u);
                 else if (len >= (uint64_t)k) {
                     const uint64_t h = prio64(seed, read_index_base + r);
-                    int c = 0;
-                    while (c < nl && (s_all[c] || h < s_thr[c])) ++c;
-                    seg[i] = c - 1;
+                    // number of levels the read is in: membership is monotone in the level (levels are nested: the
+                    // "all reads" levels come first, thresholds never increase), so a binary search with a
+                    // warp-uniform trip count replaces the divergent walk down the ladder
+                    int lo = 0, hi = nl;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_all[mid] || h < s_thr[mid]) lo = mid + 1; else hi = mid;
+                    }
+                    seg[i] = lo - 1;
                     if (seg[i] >= 0) {
                         len32 = (uint32_t)len;
                         entry[i] = ((st[i] - text_base) << kEntryLenBits) | len;
