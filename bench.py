@@ -4,16 +4,21 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...   # the reference-equivalent CPU path (oracle port)
 
-Workload (BASELINE.json configs[1]): one synthetic 200 Mbp cleaned FASTQ per GPU (read length 150,
-SURVEY.md section 8d shape), k=7, CGR mapping, full sub-sample ladder 200M..500K (9 levels) from ONE pass.
+Workload (BASELINE.json configs[1]): synthetic 200 Mbp cleaned FASTQ samples (read length 150, SURVEY.md
+section 8d shape), k=7, CGR mapping, full sub-sample ladder 200M..500K (9 levels) from ONE pass.
 A step = the whole hot path over one sample: FASTQ framing -> ladder -> seeded sub-sampling -> k-mer
 counting of all levels -> canonical fold -> 9 images (uint8) read back to the host.
 
-value   device-resident: text already in HBM, CUDA events on the library's stream around each step
-        (the 423 MB input is larger than the 126 MB L2, so nothing is served from cache between steps).
-e2e     same call with the text in pinned HOST memory: H2D copy + kernels + read-back, wall clock.
-N > 1   one process per GPU (torchrun), each with its own sample (sharded by sample, no data-path
-        collective): value = N * bases / max-over-ranks time; scaling "weak".
+value   device-resident: the texts are already in HBM.  EXACTLY K steps are dealt to `--in-flight` contexts
+        (default 4, one host thread each: the path of one sample is a chain of short dependent kernels, several
+        samples in flight fill its gaps -- how stages.images_for_samples runs a batch).  The region is bracketed
+        by barrier + device synchronize on both sides and timed by two CUDA events recorded at those idle points,
+        so every gap between steps is inside it.  Every context alternates two samples of its own (423 MB each,
+        larger than the 126 MB L2; no two contexts read the same bytes).  `one_context` reports a single
+        context's per-sample device interval and wall time beside it.
+e2e     same call with the text in pinned HOST memory: H2D copy + kernels + read-back, wall clock, two contexts.
+N > 1   one process per GPU (torchrun), each with its own samples (sharded by sample, no data-path
+        collective): value = N * K * bases / max-over-ranks time; scaling "weak".
 """
 import argparse
 import json
@@ -254,15 +259,15 @@ def run_reference_arm(args):
 
 def workload_config():
     if K == 9:
-        return {"workload": "configs[2]: single 1 Gbp synthetic sample per GPU, read length 150, k=9, varKode mapping, "
+        return {"workload": "configs[2]: 1 Gbp synthetic samples, one per step (the GPU arm keeps `in_flight` of them in flight per GPU), read length 150, k=9, varKode mapping, "
                             "-M 0, ladder 1G..500K (11 levels) from one pass; histogram 4^9 in L2 (global atomics)",
                 "bases_per_step_per_gpu": N_BASES, "bytes_per_base": round(BYTES_PER_BASE, 4), "k": K, "mapping": MAPPING,
                 "levels": len(LEVELS), "l2_policy": "input (2.1 GB) larger than L2 (126 MB); no flush needed",
                 "parallelism": "by-sample, one process per GPU, no collective"}
-    return {"workload": "configs[1]: single 200 Mbp synthetic sample per GPU, read length 150, k=7, cgr mapping, "
+    return {"workload": "configs[1]: 200 Mbp synthetic samples, one per step (the GPU arm keeps `in_flight` of them in flight per GPU), read length 150, k=7, cgr mapping, "
                         "full subsample ladder 200M..500K (9 levels) from one pass",
             "bases_per_step_per_gpu": N_BASES, "bytes_per_base": round(BYTES_PER_BASE, 4), "k": K, "mapping": MAPPING,
-            "levels": len(LEVELS), "l2_policy": "input (423 MB) larger than L2 (126 MB), and consecutive steps read two different samples alternately",
+            "levels": len(LEVELS), "l2_policy": "input (423 MB per sample) larger than L2 (126 MB); every context alternates two samples of its own and no two contexts read the same bytes",
             "parallelism": "by-sample, one process per GPU, no collective"}
 
 
@@ -273,9 +278,11 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-concurrent", action="store_true", help="skip the several-samples-in-flight side measurement")
+    ap.add_argument("--in-flight", type=int, default=4,
+                    help="samples in flight per GPU in the timed region: one context + host thread each (1 = one stream)")
+    ap.add_argument("--no-concurrent", action="store_true", help="same as --in-flight 1")
     ap.add_argument("--bases", type=int, default=None, help="debug: smaller sample (invalidates the bench line)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
                     help="c2 = BASELINE configs[1] (the bench line); c3 = configs[2]: 1 Gbp, k=9 varKode, -M 0 (side measurement)")
@@ -308,26 +315,36 @@ def main():
     W = max(3, args.warmup)
     n_bases = args.bases
 
-    eng = Engine(local)
+    import threading
+    T = 1 if args.no_concurrent else max(1, args.in_flight)
+    engs = [Engine(local) for _ in range(T)]
+    eng = engs[0]
     table = get_kmer_mapping(K, MAPPING)
     params = Params(k=K, min_bp=MIN_BP, max_bp=MAX_BP, seed=1 + rank)
     total = synth.fixed_total_bytes(n_bases, READ_LEN)
-    # two different samples per rank, used alternately: whatever one step leaves in the 126 MB L2 (the tail of a
-    # 423 MB text) is of no use to the next step, which reads the other sample
+    # Every context owns TWO different samples and alternates them: whatever one step leaves in the 126 MB L2 (the tail
+    # of a 423 MB text) is of no use to the next step of that context, and no two contexts ever read the same bytes.
     n_reads_sample = (n_bases + READ_LEN - 1) // READ_LEN
-    devs = []
-    for j in range(2):
-        d = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
-        first_read = (2 * rank + j) * n_reads_sample                      # every rank gets its own samples
-        assert eng.synth_fastq(d.data_ptr(), d.numel(), n_bases, READ_LEN, seed=20260118 + 2000, first_read=first_read) == total
-        devs.append(d)
+    samples = []
+    for t in range(T):
+        pair = []
+        for j in range(2):
+            d = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+            first_read = ((rank * T + t) * 2 + j) * n_reads_sample            # distinct reads everywhere
+            assert eng.synth_fastq(d.data_ptr(), d.numel(), n_bases, READ_LEN, seed=20260118 + 2000, first_read=first_read) == total
+            pair.append(d)
+        samples.append(pair)
+    devs = samples[0]
     dev = devs[0]
     step_no = [0]
 
+    def run_step(t, i):
+        return engs[t].reads_to_images(samples[t][i & 1].data_ptr(), params, table, on_device=True, n_bytes=total,
+                                       max_levels=len(LEVELS))
+
     def step_device():
-        d = devs[step_no[0] & 1]
+        r = run_step(0, step_no[0])
         step_no[0] += 1
-        r = eng.reads_to_images(d.data_ptr(), params, table, on_device=True, n_bytes=total, max_levels=len(LEVELS))
         return r, eng.timings()
 
     def barrier():
@@ -335,30 +352,75 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(W):
-        res, _ = step_device()
-    assert res.nsites == n_bases and (n_bases != N_BASES or res.levels == LEVELS)
-    assert res.pixels.shape == (len(res.levels), table.side, table.side) and int(res.pixels.max()) == 255
+    for t in range(T):
+        for i in range(W):
+            res = run_step(t, i)
+        assert res.nsites == n_bases and (n_bases != N_BASES or res.levels == LEVELS)
+        assert res.pixels.shape == (len(res.levels), table.side, table.side) and int(res.pixels.max()) == 255
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # ---- timed region: K whole steps, device-resident text.  Only the first and last CUDA event of a step are recorded
-    # (events between kernels would serialise the stream and defeat the dependent-launch overlap the library uses)
-    eng.set_fine_timing(False)
-    for _ in range(2):
-        step_device()
-    launches0 = eng.launch_count()
+
+    # ---- timed region: EXACTLY K steps (one step = one sample through the whole path, device-resident text), dealt to
+    # the T contexts; a barrier + device synchronize on both sides; elapsed time from two CUDA events recorded at those
+    # two idle points (so it includes every gap between the steps), and the wall clock next to it.  Inside a step only
+    # its first and last event are recorded (events between kernels would serialise the stream and defeat the
+    # dependent-launch overlap the library uses).
+    for e in engs:
+        e.set_fine_timing(False)
+    for t in range(T):
+        for i in range(2):
+            run_step(t, i)
+    share = [args.steps // T + (1 if t < args.steps % T else 0) for t in range(T)]
+    errors = []
+
+    def work(t):
+        try:
+            for i in range(share[t]):
+                run_step(t, i)
+        except Exception as exc:          # surfaced after the join
+            errors.append(exc)
+
+    launches0 = sum(e.launch_count() for e in engs)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    threads_ = [threading.Thread(target=work, args=(t,)) for t in range(T)]
     barrier()
+    ev0.record()
     t_wall0 = time.perf_counter()
-    dev_ms = 0.0
-    for _ in range(args.steps):
-        res, tm = step_device()
-        dev_ms += tm["total"]
-    barrier()
+    if T == 1:
+        work(0)
+    else:
+        for th in threads_:
+            th.start()
+        for th in threads_:
+            th.join()
+    torch.cuda.synchronize()
+    ev1.record()
+    ev1.synchronize()
     wall_ms = 1e3 * (time.perf_counter() - t_wall0)
-    launches = eng.launch_count() - launches0
+    dev_ms = ev0.elapsed_time(ev1)
+    barrier()
+    if errors:
+        raise errors[0]
+    launches = sum(e.launch_count() for e in engs) - launches0
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- one context alone (sample latency): sum of the per-step device intervals (first to last CUDA event of a step
+    # on the library's stream) and the wall clock of the same loop, which adds the host gaps between dependent steps
+    one_steps = max(3, min(args.steps, 200))
+    one_dev = 0.0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(one_steps):
+        _, tm = step_device()
+        one_dev += tm["total"]
+    torch.cuda.synchronize()
+    one_wall = 1e3 * (time.perf_counter() - t0)
+    one_stream = {"steps": one_steps, "ms_per_step_device": one_dev / one_steps, "ms_per_step_wall": one_wall / one_steps,
+                  "value_device": n_bases * one_steps / (one_dev * 1e-3) / 1e9, "unit": "Gbases/s",
+                  "note": "one context, one sample at a time: device interval of a step (its first to last CUDA event) "
+                          "and wall clock per step including the host gap between two synchronous calls; rank-local"}
 
     # ---- per-kernel split of a step (CUDA events between the kernel groups, on the library's stream): gives the
     # count kernel's own duration for the roofline.  Not part of `value`.
@@ -374,51 +436,48 @@ def main():
     per_kernel = {k2: v / split_steps for k2, v in per_kernel.items()}
     torch.cuda.synchronize()
 
-    # ---- end to end: pinned host text -> images on the host, wall clock
-    host = torch.empty(total, dtype=torch.uint8).pin_memory()
-    host.copy_(dev[:total])
+    # ---- end to end: pinned host text -> vk_reads_to_images (H2D copy, whole path, D2H of the images) -> pixels on the
+    # host, wall clock.  Two contexts on two host threads so that one sample's upload overlaps the other's kernels; the
+    # PCIe link is the limit either way.
+    Te = min(T, 2)
+    hosts = []
+    for t in range(Te):
+        h = torch.empty(total, dtype=torch.uint8).pin_memory()
+        h.copy_(samples[t][0][:total])
+        hosts.append(h)
+    host = hosts[0]
     torch.cuda.synchronize()
-    for _ in range(2):
-        eng.reads_to_images(host, params, table, max_levels=len(LEVELS))
+    r2s = [None] * Te
+    for t in range(Te):
+        for _ in range(2):
+            r2s[t] = engs[t].reads_to_images(hosts[t], params, table, max_levels=len(LEVELS))
+    e_share = [args.e2e_steps // Te + (1 if t < args.e2e_steps % Te else 0) for t in range(Te)]
+
+    def e2e_work(t):
+        try:
+            for _ in range(e_share[t]):
+                r2s[t] = engs[t].reads_to_images(hosts[t], params, table, max_levels=len(LEVELS))
+        except Exception as exc:
+            errors.append(exc)
+
+    e_threads = [threading.Thread(target=e2e_work, args=(t,)) for t in range(Te)]
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        r2 = eng.reads_to_images(host, params, table, max_levels=len(LEVELS))
+    if Te == 1:
+        e2e_work(0)
+    else:
+        for th in e_threads:
+            th.start()
+        for th in e_threads:
+            th.join()
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
+    if errors:
+        raise errors[0]
+    r2 = r2s[0]
     res0 = eng.reads_to_images(devs[0].data_ptr(), params, table, on_device=True, n_bytes=total, max_levels=len(LEVELS))
     assert (r2.pixels == res0.pixels).all()                # host-buffer path == device-resident path, same sample
     d2h = int(res.pixels.size) + 4096
-
-    # ---- several samples in flight on one GPU (the by-sample batch regime, BASELINE configs[3]): T host threads, each
-    # with its own context, push the same resident sample through the path concurrently.  Not the bench line.
-    conc = None
-    if not args.no_concurrent:
-        T = 4
-        c_steps = max(5, min(args.steps, 100))
-        engs = [Engine(local) for _ in range(T)]
-        for e in engs:
-            e.set_fine_timing(False)
-            e.reads_to_images(dev.data_ptr(), params, table, on_device=True, n_bytes=total, max_levels=len(LEVELS))
-
-        def work(e):
-            for _ in range(c_steps):
-                e.reads_to_images(dev.data_ptr(), params, table, on_device=True, n_bytes=total, max_levels=len(LEVELS))
-
-        th = [threading.Thread(target=work, args=(e,)) for e in engs]
-        barrier()
-        t0 = time.perf_counter()
-        for x in th:
-            x.start()
-        for x in th:
-            x.join()
-        torch.cuda.synchronize()
-        c_ms = 1e3 * (time.perf_counter() - t0)
-        for e in engs:
-            e.close()
-        conc = {"contexts": T, "steps_per_context": c_steps, "ms_per_sample_wall": c_ms / (T * c_steps),
-                "value_this_rank": n_bases * T * c_steps / (c_ms * 1e-3) / 1e9, "unit": "Gbases/s",
-                "note": "same 200 Mbp resident sample through 4 contexts at once (host threads); wall clock; rank-local"}
 
     # ---- N > 1 only: ONE sample of N x 200 Mbp read-sharded over the ranks (BASELINE configs[4] shape): every rank
     # frames and counts its shard, one NCCL all-reduce sums the per-segment histograms, every rank renders.
@@ -468,7 +527,9 @@ def main():
             "e2e": {"value": world * n_bases * args.e2e_steps / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s",
                     "h2d_bytes_per_step": total, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
                     "ms_per_step": e2e_ms / args.e2e_steps,
-                    "note": "uncompressed FASTQ in pinned host memory -> vk_reads_to_images -> pixels on host; wall clock"},
+                    "contexts": Te,
+                    "note": "uncompressed FASTQ in pinned host memory -> vk_reads_to_images -> pixels on host; wall clock; "
+                            "two contexts so that uploads overlap kernels"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "count_kernel<7,smem>" if K <= 7 else f"count_kernel<{K},global>", "achieved": achieved, "peak": peak,
@@ -477,6 +538,7 @@ def main():
                          "kernel_ms": count_s * 1e3,
                          "whole_step_frac": (n_bases * BYTES_PER_BASE / (dev_ms * 1e-3 / steps) / 1e9) / peak},
             "ms_per_step_wall": wall_ms / steps,
+            "in_flight": T,
             "kernel_ms_per_step": per_kernel,
             "kernel_split_note": f"mean of {split_steps} separate steps with CUDA events between the kernel groups; "
                                  "those events serialise the stream, so the groups sum to more than ms_per_step",
@@ -484,8 +546,7 @@ def main():
         }
         if sharded is not None:
             out["read_sharded"] = sharded
-        if conc is not None:
-            out["samples_in_flight"] = conc
+        out["one_context"] = one_stream
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = run_cpu_baseline(host.numpy())
         print(json.dumps(out), flush=True)

@@ -3,7 +3,7 @@
 # usage: tools/profile_gpu.sh <tag>      outputs under gpurun_out/
 set -u
 TAG=${1:-r01}
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --in-flight 1"
 mkdir -p gpurun_out
 python bench.py --steps 500 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err || exit 1
 $CMD > gpurun_out/plain_${TAG}.log 2>&1 || exit 1
