@@ -490,6 +490,53 @@ def test_full_size_properties_config3(engine):
     assert (r2.canon[0] == dsk.canonical_counts(head, k, threads=0)).all()
 
 
+def test_text_beyond_4_gib(engine):
+    """One buffer of 4.65 GB (2.2 Gbp): byte offsets pass 2^32 inside the framing, the read table and the count
+    kernel's chunk addresses.  The whole sample equals the sum of three read shards that each stay below 4 GiB, the
+    TAIL of the buffer (where the offsets are largest) equals the CPU oracle, and the quality-flag kernel reads past
+    2^32 too."""
+    import torch
+    k, L, n_bases = 7, 150, 2_200_000_000
+    table = get_kmer_mapping(k, "cgr")
+    total = synth.fixed_total_bytes(n_bases, L)
+    assert total > 2 ** 32
+    dev = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+    assert engine.synth_fastq(dev.data_ptr(), dev.numel(), n_bases, L, seed=4242) == total
+    params = Params(k=k, min_bp=100_000_000, max_bp=None, seed=5)
+    res = engine.reads_to_images(dev.data_ptr(), params, table, on_device=True, n_bytes=total, want_canon=True)
+    assert res.nsites == n_bases and res.levels == [2_200_000_000, 2_000_000_000, 1_000_000_000, 500_000_000,
+                                                    200_000_000, 100_000_000]
+    assert res.level_bases[0] == n_bases and res.level_reads[0] == res.n_reads == (n_bases + L - 1) // L
+    content = engine.base_content(0, 8)
+    assert (content[:, 4] == res.n_reads).all()
+    rec = synth.record_size(L)
+    cuts = [0, (res.n_reads // 3) & ~15, (2 * res.n_reads // 3) & ~15, res.n_reads]
+    nk = 4 ** k
+    both = torch.zeros(64 * nk, dtype=torch.int64, device="cuda")
+    content_sum = np.zeros_like(content)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        off, nb = a * rec, (b * rec if b < res.n_reads else total) - a * rec
+        assert nb < 2 ** 32
+        engine.attach(dev.data_ptr() + off, nb)
+        engine.parse()
+        seg = torch.zeros(64 * nk, dtype=torch.int64, device="cuda")
+        r = engine.count(Params(k=k, min_bp=100_000_000, max_bp=None, seed=5, read_index_base=a, nsites_override=n_bases),
+                         seg.data_ptr())
+        assert r.levels == res.levels
+        content_sum += engine.base_content(0, 8)
+        both += seg
+    torch.cuda.synchronize()
+    canon2, _ = engine.render(None, k, len(res.levels), both.data_ptr())
+    assert (canon2 == res.canon).all()
+    assert (content_sum == content).all()
+    # the last 2000 records, by the CPU oracle: same counts as the GPU gets when it is handed only that tail
+    tail_off = (res.n_reads - 2000) * rec
+    tail = dev[tail_off:total].cpu().numpy().tobytes()
+    r_tail = engine.reads_to_images(tail, Params(k=k, min_bp=0, max_bp=None, is_query=True), table, want_canon=True)
+    assert (r_tail.canon[0] == dsk.canonical_counts(tail, k, threads=0)).all()
+    del dev
+
+
 def test_query_mode_device_handoff(engine):
     """`varKoder query` (image.py:1028-1048): one level of min(nsites, max_bp), no min_bp check -- and the images can be
     handed to a GPU consumer without leaving the device (vk_device_pixels)."""
