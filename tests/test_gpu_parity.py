@@ -409,7 +409,8 @@ def test_batch_of_bembidion_shaped_samples(engine, tmp_path):
         p = tmp_path / f"S{i}.fq.gz"
         with gzip.open(p, "wb", compresslevel=1) as f:
             f.write(buf)
-        samples.append(dict(sample=f"S{i}", path=str(p), labels=[f"sp{i % 2}", "genus"], base_sd=0.002 * i))
+        # S3 has no fastp report: its quality flag is measured from the reads on the GPU (base_sd=None)
+        samples.append(dict(sample=f"S{i}", path=str(p), labels=[f"sp{i % 2}", "genus"], base_sd=None if i == 3 else 0.002 * i))
         bufs[f"S{i}"] = buf
     owner, loads = sharding.assign_samples([len(bufs[s["sample"]]) for s in samples], 2)
     assert sorted(set(owner)) == [0, 1] and abs(loads[0] - loads[1]) <= max(loads) // 2
@@ -430,6 +431,12 @@ def test_batch_of_bembidion_shaped_samples(engine, tmp_path):
             img = Image.open(f)
             assert img.mode == "L" and (np.asarray(img) == pix[lvl]).all()
             assert img.info["varkoderKeywords"] == ";".join(s["labels"]) and img.info["varkoderMapping"] == "varKode"
+            sd = s["base_sd"]
+            if sd is None:
+                from varkoder_b200 import quality
+                sd = quality.base_frequency_sd(oimg.base_content(buf, p["starts"], p["lens"], 5, 40))
+                assert stats[s["sample"]]["base_frequencies_sd"] == sd
+            assert img.info["varkoderBaseFreqSd"] == str(sd) and img.info["varkoderLowQualityFlag"] == str(sd > 0.01)
     # a sample below min_bp is recorded the way run_clean2img records a split failure
     small = dict(sample="tiny", path=samples[4]["path"])
     st = stages.images_for_samples([small], out, table, k=7, min_bp=10**9, max_bp=10**10, engine=engine)
