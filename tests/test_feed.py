@@ -72,3 +72,100 @@ def test_sample_feeder_propagates_errors(tmp_path):
     with feed.SampleFeeder([bad], threads=1, pinned=False) as fd:
         with pytest.raises(Exception):
             list(fd)
+
+
+# ---------------------------------------------------------------------------------- libvk_feed.so (csrc/vk_inflate.c)
+def _deflate(raw, level, strategy):
+    import zlib
+    c = zlib.compressobj(level, zlib.DEFLATED, 31, 9, strategy)
+    return c.compress(raw) + c.flush()
+
+
+def _corpus():
+    rng = np.random.default_rng(11)
+    from varkoder_b200 import synth
+    return {
+        "fastq_fixed": synth.fixed(400_000, 150, seed=3).tobytes(),
+        "fastq_ragged": synth.variable(3000, seed=4).tobytes(),
+        "random": rng.integers(0, 256, 120_000, dtype=np.uint8).tobytes(),          # stored blocks / long codes
+        "zeros": bytes(300_000),                                                    # distance 1, maximal matches
+        "text": b"the quick brown fox jumps over the lazy dog. " * 8000,
+        "four_symbols": rng.integers(0, 4, 200_000, dtype=np.uint8).tobytes(),
+        "skewed": (rng.geometric(0.02, 150_000) % 256).astype(np.uint8).tobytes(),  # code lengths up to 15: sub-tables
+        "empty": b"",
+        "one_byte": b"A",
+        "tiny": b"ACGT\n" * 3,
+    }
+
+
+def test_feed_library_is_built_and_used():
+    assert feed.feed_lib() is not None, "libvk_feed.so missing: run make -C varkoder_b200/csrc"
+
+
+def test_gunzip_equals_zlib_on_every_block_type():
+    """stored / fixed / dynamic blocks, every zlib strategy and level, exact-size and roomy output buffers"""
+    import zlib
+    for name, raw in _corpus().items():
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+                comp = _deflate(raw, level, strategy)
+                for slack in (0, 1000):
+                    buf = feed.PinnedBuffer(0, pinned=False)
+                    n = feed.gunzip_into(comp, buf, size_hint=len(raw) + slack)
+                    assert n == len(raw) and buf.array[:n].tobytes() == raw, (name, level, strategy, slack)
+
+
+def test_gunzip_multi_member_padding_and_growth():
+    raw = _corpus()["fastq_fixed"]
+    comp = gzip.compress(raw[:100_000], 6) + gzip.compress(b"", 6) + gzip.compress(raw[100_000:250_000], 1) + bytes(37)
+    buf = feed.PinnedBuffer(0, pinned=False)
+    n = feed.gunzip_into(comp, buf, size_hint=0)                 # no hint: the buffer grows until the text fits
+    assert n == 250_000 and buf.array[:n].tobytes() == raw[:250_000]
+    # header fields: FEXTRA, FNAME, FCOMMENT, FHCRC
+    body = gzip.compress(raw[:5000], 6)
+    hdr = bytes([0x1f, 0x8b, 8, 2 | 4 | 8 | 16]) + body[4:10] + b"\x03\x00abc" + b"name\x00" + b"comment\x00" + b"\x12\x34"
+    n = feed.gunzip_into(hdr + body[10:], buf, size_hint=5000)
+    assert n == 5000 and buf.array[:n].tobytes() == raw[:5000]
+
+
+def test_gunzip_rejects_damage():
+    """truncation anywhere and single bit flips: never accepted, never a crash (CRC-32 + ISIZE are checked)"""
+    rng = np.random.default_rng(5)
+    raw = _corpus()["fastq_ragged"]
+    comp = gzip.compress(raw, 6)
+    buf = feed.PinnedBuffer(len(raw) + 64, pinned=False)
+    for cut in (0, 5, 17, 100, len(comp) // 2, len(comp) - 9, len(comp) - 1):
+        assert feed.gunzip_into(comp[:cut], buf, size_hint=len(raw)) is None, cut
+    for _ in range(400):
+        b = bytearray(comp)
+        b[int(rng.integers(10, len(comp)))] ^= 1 << int(rng.integers(0, 8))
+        got = feed.gunzip_into(bytes(b), buf, size_hint=len(raw))
+        assert got is None or buf.array[:got].tobytes() == raw           # a flip in a don't-care header bit may pass
+    assert feed.gunzip_into(b"not gzip at all, just text", buf) is None
+
+
+def test_crc32_equals_zlib():
+    import ctypes
+    import zlib
+    L = feed.feed_lib()
+    rng = np.random.default_rng(0)
+    for n in list(range(0, 200)) + [1000, 4096, 65537, (1 << 20) + 13]:
+        a = rng.integers(0, 256, n + 3, dtype=np.uint8)
+        for off in (0, 1, 3):
+            b = a[off:off + n]
+            assert L.vkf_crc32(0, ctypes.c_void_p(b.ctypes.data), n) == zlib.crc32(b.tobytes()), (n, off)
+        h = n // 2
+        run = L.vkf_crc32(L.vkf_crc32(0, ctypes.c_void_p(a.ctypes.data), h), ctypes.c_void_p(a[h:].ctypes.data), n - h)
+        assert run == zlib.crc32(a[:n].tobytes())
+
+
+def test_inflate_falls_back_to_zlib(tmp_path, monkeypatch):
+    """without the library (or when it declines a file) the zlib path gives the same bytes"""
+    data = fastq(rand_reads(np.random.default_rng(8), 500, 0, 120))
+    p = tmp_path / "x.fq.gz"
+    p.write_bytes(gzip.compress(data))
+    monkeypatch.setattr(feed, "_feed_lib", False)
+    assert feed.feed_lib() is None
+    buf = feed.PinnedBuffer(0, pinned=False)
+    n = feed.inflate_into(p, buf)
+    assert buf.array[:n].tobytes() == data
