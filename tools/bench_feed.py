@@ -1,6 +1,6 @@
 """End to end FROM GZIP FILES: N synthetic cleaned .fq.gz samples -> threaded inflate into pinned buffers -> GPU -> PNGs on
 disk, through stages.images_for_samples (the batch entry point).  Side measurement, not the bench line: it is bound by
-zlib inflate on the host cores (one gzip member cannot be split; parallelism is across samples).
+gzip inflate on the host cores (one gzip member cannot be split; parallelism is across samples).
 usage: python tools/bench_feed.py [n_samples] [bases_per_sample]"""
 import gzip
 import os
@@ -42,15 +42,18 @@ try:
           f"{n_samples * total / 1e6:.0f} MB text, {time.perf_counter() - t0:.1f} s", flush=True)
     table = get_kmer_mapping(7, "varKode")
     threads = len(os.sched_getaffinity(0))
-    for workers in (1, 3):
-        out = os.path.join(tmp, f"images_{workers}")
+    from varkoder_b200 import feed
+    lib = feed.feed_lib()
+    for decoder, workers in (("zlib", 1), ("libvk_feed", 1), ("libvk_feed", 3)):
+        feed._feed_lib = False if decoder == "zlib" else lib
+        out = os.path.join(tmp, f"images_{decoder}_{workers}")
         t0 = time.perf_counter()
         st = stages.images_for_samples(samples, out, table, k=7, mapping_code="varKode", min_bp=500_000,
                                        max_bp=200_000_000, threads=threads, gpu_workers=workers)
         dt = time.perf_counter() - t0
         n_png = sum(len(files) for _, _, files in os.walk(out))
         assert len(st) == n_samples and all("failed_step" not in v for v in st.values())
-        print(f"gpu_workers={workers} inflate_threads={threads}: {dt:.2f} s  {n_samples * n_bases / dt / 1e9:.2f} Gbases/s  "
+        print(f"decoder={decoder} gpu_workers={workers} inflate_threads={threads}: {dt:.2f} s  {n_samples * n_bases / dt / 1e9:.2f} Gbases/s  "
               f"{n_samples * total / dt / 1e9:.2f} GB/s of text  {n_png} PNGs", flush=True)
 finally:
     shutil.rmtree(tmp, ignore_errors=True)

@@ -249,7 +249,7 @@ def images_for_samples(samples, outfolder, kmer_mapping, k=7, mapping_code="varK
     """Steps C-E of run_clean2img for MANY samples (the loop of ImageCommand.process_samples, image.py:1265-1294) on
     one GPU: samples are inflated ahead by worker threads into pinned memory (varkoder_b200.feed), pushed through the
     GPU by ``gpu_workers`` threads that each own a context, and their PNGs are written by the inflate pool off the
-    critical path.  From gzip files the batch is bound by zlib on the host cores (0.6 Gbases/s with 16 threads,
+    critical path.  From gzip files the batch is bound by inflate on the host cores (2.0 Gbases/s with 16 threads,
     tools/bench_feed.py), so one GPU worker is the default; with inputs that are already in memory the path of one
     sample is a chain of short dependent kernels and three or four samples in flight fill the gaps (600 -> 766
     Gbases/s on 200 Mbp samples, 68 -> 180 on 10 Mbp ones, profiles/r01_notes.md).
