@@ -169,3 +169,86 @@ def test_inflate_falls_back_to_zlib(tmp_path, monkeypatch):
     buf = feed.PinnedBuffer(0, pinned=False)
     n = feed.inflate_into(p, buf)
     assert buf.array[:n].tobytes() == data
+
+
+# ------------------------------------------------------------------------ one gzip member on several threads
+def pigz_like(raw, level=6, block=128 * 1024, independent=False):
+    """the stream pigz writes (the reference's clean_reads output, image.py:534-540): ONE member; every block is
+    compressed on its own, primed with the previous 32 KiB unless -i, and ends with a sync flush (empty stored block)"""
+    import zlib
+    out = [b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03"]
+    for i in range(0, max(len(raw), 1), block):
+        zd = raw[max(0, i - 32768):i] if (i and not independent) else b""
+        c = (zlib.compressobj(level, zlib.DEFLATED, -15, 8, zlib.Z_DEFAULT_STRATEGY, zd) if zd
+             else zlib.compressobj(level, zlib.DEFLATED, -15, 8))
+        last = i + block >= len(raw)
+        out.append(c.compress(raw[i:i + block]) + c.flush(zlib.Z_FINISH if last else zlib.Z_SYNC_FLUSH))
+    out.append(zlib.crc32(raw).to_bytes(4, "little") + (len(raw) & 0xFFFFFFFF).to_bytes(4, "little"))
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("independent", [False, True])
+@pytest.mark.parametrize("block", [128 * 1024, 20_000])
+def test_parallel_member_equals_serial(independent, block):
+    """pieces cut behind pigz's sync points, decoded concurrently with placeholders for the unseen 32 KiB, resolved front
+    to back: byte-identical to the serial decode; blocks shorter than the window make placeholders chain through
+    several pieces"""
+    import zlib
+    from varkoder_b200 import synth
+    raw = synth.variable(9000, seed=21).tobytes() + b"ACGT" * 50_000 + synth.fixed(600_000, 150, seed=2).tobytes()
+    comp = pigz_like(raw, 6, block, independent)
+    assert zlib.decompress(comp, 31) == raw
+    buf = feed.PinnedBuffer(0, pinned=False)
+    for threads, min_piece in ((2, 1 << 16), (5, 1 << 14), (16, 4096)):
+        n = feed.gunzip_parallel(comp, buf, len(raw), threads, min_piece=min_piece)
+        assert n == len(raw) and buf.array[:n].tobytes() == raw, (threads, min_piece)
+
+
+def test_parallel_member_declines_what_it_cannot_prove(tmp_path):
+    import zlib
+    from varkoder_b200 import synth
+    raw = synth.fixed(900_000, 150, seed=8).tobytes()
+    buf = feed.PinnedBuffer(0, pinned=False)
+    # an ordinary gzip stream has no sync points
+    assert feed.gunzip_parallel(zlib.compress(raw, 6, 31), buf, len(raw), 8, min_piece=4096) is None
+    # two members: the last piece does not end in front of the file's trailer
+    two = pigz_like(raw[:500_000]) + pigz_like(raw[500_000:])
+    assert feed.gunzip_parallel(two, buf, len(raw), 8, min_piece=4096) is None
+    # stored data that CONTAINS the marker bytes: cuts at places that are no block starts -> pieces fail -> declined
+    fake = (b"\x00\x00\xff\xff" + bytes(range(256))) * 8000
+    c = zlib.compressobj(0, zlib.DEFLATED, 31)
+    comp = c.compress(fake) + c.flush()
+    assert feed.gunzip_parallel(comp, buf, len(fake), 8, min_piece=4096) is None
+    # damaged CRC
+    good = pigz_like(raw)
+    bad = good[:-8] + bytes([good[-8] ^ 1]) + good[-7:]
+    assert feed.gunzip_parallel(good, buf, len(raw), 4, min_piece=1 << 15) == len(raw)
+    assert feed.gunzip_parallel(bad, buf, len(raw), 4, min_piece=1 << 15) is None
+    # end to end through inflate_into: every one of them still comes out right (serial decoder / zlib take over)
+    for name, blob, want in (("a", two, raw), ("b", comp, fake), ("c", good, raw)):
+        p = tmp_path / f"{name}.fq.gz"
+        p.write_bytes(blob)
+        n = feed.inflate_into(p, buf, threads=8)
+        assert buf.array[:n].tobytes() == want
+
+
+def test_crc32_combine():
+    import zlib
+    L = feed.feed_lib()
+    rng = np.random.default_rng(4)
+    for la, lb in ((0, 0), (1, 0), (0, 5), (7, 9), (1000, 1), (65536, 100_003), (3, 1 << 20)):
+        a = rng.integers(0, 256, la, dtype=np.uint8).tobytes()
+        b = rng.integers(0, 256, lb, dtype=np.uint8).tobytes()
+        assert L.vkf_crc32_combine(zlib.crc32(a), zlib.crc32(b), lb) == zlib.crc32(a + b)
+
+
+def test_feeder_splits_members_when_samples_are_few(tmp_path):
+    from varkoder_b200 import synth
+    raw = synth.fixed(3_000_000, 150, seed=12).tobytes()
+    p = tmp_path / "big.fq.gz"
+    p.write_bytes(pigz_like(raw, 1))
+    with feed.SampleFeeder([str(p)], threads=8, pinned=False) as fd:
+        assert fd.piece_threads == 8
+        for i, it, buf, n in fd:
+            assert buf.array[:n].tobytes() == raw
+            fd.release(buf)

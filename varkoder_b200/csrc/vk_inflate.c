@@ -234,225 +234,20 @@ static uint32_t crc32_bytes(uint32_t crc, const uint8_t* p, size_t n)
 #define BITS(n) ((uint32_t)bitbuf & ((1u << (n)) - 1u))
 #define DROP(n) do { bitbuf >>= (n); bitcnt -= (n); } while (0)
 
-/* one raw DEFLATE stream: in -> out.  Returns VKF_*; *in_used and *out_used are always set. */
-static int inflate_raw(tables_t* T, const uint8_t* const in_begin, const uint8_t* const in_end, uint8_t* const out_begin,
-                       uint8_t* const out_end, size_t* in_used, size_t* out_used)
-{
-    const uint8_t* in = in_begin;
-    uint8_t* out = out_begin;
-    uint64_t bitbuf = 0;
-    unsigned bitcnt = 0;
-    int rc = VKF_OK, final = 0;
-
-    while (!final) {
-        REFILL_SAFE();
-        if (bitcnt < 3) { rc = VKF_ETRUNC; goto done; }
-        final = (int)BITS(1);
-        const unsigned type = (unsigned)(bitbuf >> 1) & 3u;
-        DROP(3);
-        if (type == 0) {
-            /* stored: back to a byte boundary, hand the accounted bytes back, then LEN / NLEN / raw bytes */
-            DROP(bitcnt & 7u);
-            in -= bitcnt >> 3;
-            bitbuf = 0;
-            bitcnt = 0;
-            if (in_end - in < 4) { rc = VKF_ETRUNC; goto done; }
-            const unsigned len = in[0] | (in[1] << 8), nlen = in[2] | (in[3] << 8);
-            in += 4;
-            if ((len ^ nlen) != 0xFFFFu) { rc = VKF_EFORMAT; goto done; }
-            if ((size_t)(in_end - in) < len) { rc = VKF_ETRUNC; goto done; }
-            if ((size_t)(out_end - out) < len) { rc = VKF_ESPACE; goto done; }
-            memcpy(out, in, len);
-            in += len;
-            out += len;
-            continue;
-        }
-        if (type == 3) { rc = VKF_EFORMAT; goto done; }
-        if (type == 1) {
-            uint8_t* l = T->lens;
-            for (unsigned i = 0; i < 144; ++i) l[i] = 8;
-            for (unsigned i = 144; i < 256; ++i) l[i] = 9;
-            for (unsigned i = 256; i < 280; ++i) l[i] = 7;
-            for (unsigned i = 280; i < 288; ++i) l[i] = 8;
-            for (unsigned i = 0; i < 32; ++i) l[288 + i] = 5;
-            if (build_table(T->lt, LT_BITS, LT_CAP, l, 288, 0) || build_table(T->dt, DT_BITS, DT_CAP, l + 288, 32, 1)) { rc = VKF_EFORMAT; goto done; }
-        } else {
-            REFILL_SAFE();
-            if (bitcnt < 14) { rc = VKF_ETRUNC; goto done; }
-            const unsigned hlit = BITS(5) + 257; DROP(5);
-            const unsigned hdist = BITS(5) + 1; DROP(5);
-            const unsigned hclen = BITS(4) + 4; DROP(4);
-            if (hlit > 286 || hdist > 30) { rc = VKF_EFORMAT; goto done; }
-            uint8_t pl[19] = {0};
-            for (unsigned i = 0; i < hclen; ++i) {
-                REFILL_SAFE();
-                if (bitcnt < 3) { rc = VKF_ETRUNC; goto done; }
-                pl[kPrecodeOrder[i]] = (uint8_t)BITS(3);
-                DROP(3);
-            }
-            if (build_table(T->pt, PT_BITS, PT_CAP, pl, 19, 2)) { rc = VKF_EFORMAT; goto done; }
-            uint8_t* l = T->lens;
-            unsigned n = 0;
-            const unsigned total = hlit + hdist;
-            while (n < total) {
-                REFILL_SAFE();
-                const uint32_t e = T->pt[BITS(PT_BITS)];
-                const unsigned cl = e & 63u;
-                if (cl == 0) { rc = VKF_EFORMAT; goto done; }
-                if (cl + 7 > bitcnt) { rc = VKF_ETRUNC; goto done; }
-                DROP(cl);
-                const unsigned sym = e >> 16;
-                if (sym < 16) { l[n++] = (uint8_t)sym; continue; }
-                unsigned rep, val = 0;
-                if (sym == 16) {
-                    if (n == 0) { rc = VKF_EFORMAT; goto done; }
-                    val = l[n - 1];
-                    rep = 3 + BITS(2); DROP(2);
-                } else if (sym == 17) { rep = 3 + BITS(3); DROP(3); }
-                else { rep = 11 + BITS(7); DROP(7); }
-                if (n + rep > total) { rc = VKF_EFORMAT; goto done; }
-                memset(l + n, (int)val, rep);
-                n += rep;
-            }
-            if (l[256] == 0) { rc = VKF_EFORMAT; goto done; }
-            uint8_t dl[32];
-            memcpy(dl, l + hlit, hdist);
-            memset(dl + hdist, 0, 32 - hdist);
-            memset(l + hlit, 0, 288 - hlit);
-            if (build_table(T->lt, LT_BITS, LT_CAP, l, 288, 0) || build_table(T->dt, DT_BITS, DT_CAP, dl, 32, 1)) { rc = VKF_EFORMAT; goto done; }
-        }
-
-        /* ---- symbols of the block */
-        for (;;) {
-            uint32_t e;
-            /* fast loop: enough input for every refill and enough room for the longest match plus the copy overshoot */
-            while (in_end - in >= 16 && out_end - out >= 320) {
-                REFILL_FAST();
-                e = T->lt[BITS(LT_BITS)];
-                if (e & F_LIT) {                                   /* up to three literals on one refill (3 x 15 bits) */
-                    DROP(e & 63u);
-                    *out++ = (uint8_t)(e >> 16);
-                    e = T->lt[BITS(LT_BITS)];
-                    if (e & F_LIT) {
-                        DROP(e & 63u);
-                        *out++ = (uint8_t)(e >> 16);
-                        e = T->lt[BITS(LT_BITS)];
-                        if (e & F_LIT) {
-                            DROP(e & 63u);
-                            *out++ = (uint8_t)(e >> 16);
-                            continue;
-                        }
-                    }
-                    REFILL_FAST();
-                }
-                if (e & F_SUB) {
-                    DROP(LT_BITS);
-                    e = T->lt[(e >> 16) + BITS((e >> 8) & 31u)];
-                    if (e & F_LIT) {
-                        DROP(e & 63u);
-                        *out++ = (uint8_t)(e >> 16);
-                        continue;
-                    }
-                }
-                if (e & F_EOB) { DROP(e & 63u); goto block_done; }
-                unsigned len = e >> 16;
-                if (len == 0) { rc = VKF_EFORMAT; goto done; }
-                DROP(e & 63u);
-                const unsigned lx = (e >> 8) & 31u;
-                len += BITS(lx);
-                DROP(lx);
-                /* at least 56 - 15 - 15 - 5 = 21 bits left; a distance needs up to 15 + 13 */
-                if (bitcnt < 28) REFILL_FAST();
-                uint32_t d = T->dt[BITS(DT_BITS)];
-                if (d & F_SUB) {
-                    DROP(DT_BITS);
-                    d = T->dt[(d >> 16) + BITS((d >> 8) & 31u)];
-                }
-                unsigned dist = d >> 16;
-                if (dist == 0) { rc = VKF_EFORMAT; goto done; }
-                DROP(d & 63u);
-                const unsigned dx = (d >> 8) & 31u;
-                dist += BITS(dx);
-                DROP(dx);
-                if (dist > (size_t)(out - out_begin)) { rc = VKF_EFORMAT; goto done; }
-                const uint8_t* src = out - dist;
-                uint8_t* const end = out + len;
-                if (dist >= 8) {
-                    copy64(out, src);
-                    copy64(out + 8, src + 8);
-                    copy64(out + 16, src + 16);
-                    if (len > 24) {
-                        out += 24; src += 24;
-                        do { copy64(out, src); out += 8; src += 8; } while (out < end);
-                    }
-                } else if (dist == 1) {
-                    memset(out, *src, len);
-                } else {
-                    do { *out++ = *src++; } while (out < end);
-                }
-                out = end;
-            }
-            /* careful loop: one symbol at a time with every bound checked */
-            REFILL_SAFE();
-            e = T->lt[BITS(LT_BITS)];
-            unsigned used = e & 63u;
-            if (e & F_SUB) {
-                if (bitcnt < LT_BITS) { rc = VKF_ETRUNC; goto done; }
-                DROP(LT_BITS);
-                e = T->lt[(e >> 16) + BITS((e >> 8) & 31u)];
-                used = e & 63u;
-            }
-            if (used == 0) { rc = bitcnt < 15 && in >= in_end ? VKF_ETRUNC : VKF_EFORMAT; goto done; }
-            if (used > bitcnt) { rc = VKF_ETRUNC; goto done; }
-            DROP(used);
-            if (e & F_LIT) {
-                if (out >= out_end) { rc = VKF_ESPACE; goto done; }
-                *out++ = (uint8_t)(e >> 16);
-                continue;
-            }
-            if (e & F_EOB) goto block_done;
-            unsigned len = e >> 16;
-            const unsigned lx = (e >> 8) & 31u;
-            if (len == 0) { rc = VKF_EFORMAT; goto done; }
-            if (lx > bitcnt) { rc = VKF_ETRUNC; goto done; }
-            len += BITS(lx);
-            DROP(lx);
-            REFILL_SAFE();
-            uint32_t d = T->dt[BITS(DT_BITS)];
-            if (d & F_SUB) {
-                if (bitcnt < DT_BITS) { rc = VKF_ETRUNC; goto done; }
-                DROP(DT_BITS);
-                d = T->dt[(d >> 16) + BITS((d >> 8) & 31u)];
-            }
-            unsigned dist = d >> 16;
-            const unsigned dx = (d >> 8) & 31u, du = d & 63u;
-            if (dist == 0 || du == 0) { rc = bitcnt < 15 && in >= in_end ? VKF_ETRUNC : VKF_EFORMAT; goto done; }
-            if (du + dx > bitcnt) { rc = VKF_ETRUNC; goto done; }
-            DROP(du);
-            dist += BITS(dx);
-            DROP(dx);
-            if (dist > (size_t)(out - out_begin)) { rc = VKF_EFORMAT; goto done; }
-            if ((size_t)(out_end - out) < len) {
-                /* fill what fits so that the caller can grow the buffer and see how far the stream got */
-                rc = VKF_ESPACE;
-                goto done;
-            }
-            const uint8_t* src = out - dist;
-            for (unsigned i = 0; i < len; ++i) out[i] = src[i];
-            out += len;
-        }
-    block_done:;
-    }
-    /* final block done: back to a byte boundary, return the bytes that were accounted but not used */
-    bitbuf &= bitcnt < 64 ? (((uint64_t)1 << bitcnt) - 1) : ~(uint64_t)0;
-    DROP(bitcnt & 7u);
-    in -= bitcnt >> 3;
-done:
-    if (in > in_end) in = in_end;
-    *in_used = (size_t)(in - in_begin);
-    *out_used = (size_t)(out - out_begin);
-    return rc;
-}
+#define FN_NAME inflate_raw
+#define OUT_T uint8_t
+#define SYMBOLIC 0
+#include "vk_inflate_body.inc"
+#undef FN_NAME
+#undef OUT_T
+#undef SYMBOLIC
+#define FN_NAME inflate_raw16
+#define OUT_T uint16_t
+#define SYMBOLIC 1
+#include "vk_inflate_body.inc"
+#undef FN_NAME
+#undef OUT_T
+#undef SYMBOLIC
 
 /* gzip file (one or more members, RFC 1952) -> out.  *out_len = bytes produced; returns VKF_OK or a negative VKF_E*.
  * With VKF_ESPACE, *out_len is the number of bytes produced before the buffer ran out (grow it and call again). */
@@ -485,7 +280,8 @@ int vkf_gunzip(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, s
         if (flg & 2) p += 2;
         if (p >= in_len) return VKF_ETRUNC;
         size_t used = 0, made = 0;
-        const int rc = inflate_raw(&T, in + p, in + in_len, out + op, out + out_cap, &used, &made);
+        int fin = 0;
+        const int rc = inflate_raw(&T, in + p, in + in_len, NULL, out + op, out + out_cap, &used, &made, &fin);
         if (rc != VKF_OK) { *out_len = op + made; return rc; }
         p += used;
         if (in_len - p < 8) { *out_len = op + made; return VKF_ETRUNC; }
@@ -502,4 +298,125 @@ int vkf_gunzip(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, s
 }
 
 uint32_t vkf_crc32(uint32_t crc, const uint8_t* p, size_t n) { return crc32_bytes(crc, p, n); }
+
+/* ---- one gzip member on several threads ---------------------------------------------------------------------------
+ * pigz (what the reference's clean_reads step writes, image.py:534-540) ends every 128 KiB chunk with an empty stored
+ * block, so the compressed stream has byte-aligned block starts every few tens of KiB, recognisable by the bytes
+ * 00 00 FF FF in front of them.  feed.py cuts the stream at such points, decodes the pieces concurrently -- the first
+ * one as bytes, the others as 16-bit symbols with placeholders for the 32 KiB they cannot see (pigz primes every chunk
+ * with the previous one) -- and resolves the placeholders piece by piece once the bytes in front are final.  A cut at
+ * a 00 00 FF FF that was not a block boundary makes its piece fail or end in the wrong place, and the CRC-32 of the
+ * whole member is checked at the end: any doubt sends the file to the serial decoder. */
+
+/* length of the gzip header at in[0..n), or 0 */
+size_t vkf_gzip_header_len(const uint8_t* in, size_t n)
+{
+    if (n < 18 || in[0] != 0x1f || in[1] != 0x8b || in[2] != 8 || (in[3] & 0xE0)) return 0;
+    const unsigned flg = in[3];
+    size_t p = 10;
+    if (flg & 4) {
+        if (n - p < 2) return 0;
+        const size_t xl = in[p] | (in[p + 1] << 8);
+        p += 2;
+        if (n - p < xl) return 0;
+        p += xl;
+    }
+    for (int f = 8; f <= 16; f <<= 1) {
+        if (!(flg & f)) continue;
+        while (p < n && in[p]) ++p;
+        if (p >= n) return 0;
+        ++p;
+    }
+    if (flg & 2) p += 2;
+    return p < n ? p : 0;
+}
+
+/* offset just behind the first 00 00 FF FF at or after `from` (a candidate block start), or n when there is none */
+size_t vkf_next_sync(const uint8_t* in, size_t n, size_t from)
+{
+    if (n < 4) return n;
+    for (size_t i = from; i + 4 <= n; ++i) {
+        if (in[i + 3] != 0xFF) continue;                 /* rare byte first */
+        if (in[i + 2] == 0xFF && in[i + 1] == 0 && in[i] == 0) return i + 4;
+    }
+    return n;
+}
+
+/* One piece of a raw DEFLATE stream.  in[0..in_len): from a block start to the cut behind an empty stored block
+ * (last = 0) or to the end of the file (last = 1: runs up to the final block).  symbolic = 0: out is uint8_t[out_cap];
+ * symbolic = 1: out is uint16_t[out_cap].  Returns VKF_OK only if the piece ended where it had to. */
+int vkf_inflate_piece(const uint8_t* in, size_t in_len, int last, int symbolic, void* out, size_t out_cap, size_t* out_len,
+                      size_t* in_used)
+{
+    tables_t T;
+    int fin = 0, rc;
+    const uint8_t* stop = last ? NULL : in + in_len;
+    if (symbolic) rc = inflate_raw16(&T, in, in + in_len, stop, (uint16_t*)out, (uint16_t*)out + out_cap, in_used, out_len, &fin);
+    else rc = inflate_raw(&T, in, in + in_len, stop, (uint8_t*)out, (uint8_t*)out + out_cap, in_used, out_len, &fin);
+    if (rc != VKF_OK) return rc;
+    if (last ? !fin : (fin || *in_used != in_len)) return VKF_EFORMAT;
+    return VKF_OK;
+}
+
+/* symbols -> bytes.  window = the 32768 bytes in front of the piece (window[32767] is the byte just before it).
+ * Returns the number of placeholders that pointed in front of `valid_from` (window offsets below it hold no data:
+ * the stream is younger than 32 KiB there) -- must be 0. */
+size_t vkf_resolve16(const uint16_t* sym, size_t n, const uint8_t* window, size_t valid_from, uint8_t* out)
+{
+    size_t bad = 0, i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t a, b;
+        memcpy(&a, sym + i, 8);
+        memcpy(&b, sym + i + 4, 8);
+        if (((a | b) & 0xFF00FF00FF00FF00ull) == 0) {           /* eight plain bytes */
+            out[i] = (uint8_t)a; out[i + 1] = (uint8_t)(a >> 16); out[i + 2] = (uint8_t)(a >> 32); out[i + 3] = (uint8_t)(a >> 48);
+            out[i + 4] = (uint8_t)b; out[i + 5] = (uint8_t)(b >> 16); out[i + 6] = (uint8_t)(b >> 32); out[i + 7] = (uint8_t)(b >> 48);
+            continue;
+        }
+        for (size_t j = i; j < i + 8; ++j) {
+            const unsigned v = sym[j];
+            if (v & 0x8000u) { bad += (v & 0x7FFFu) < valid_from; out[j] = window[v & 0x7FFFu]; }
+            else out[j] = (uint8_t)v;
+        }
+    }
+    for (; i < n; ++i) {
+        const unsigned v = sym[i];
+        if (v & 0x8000u) { bad += (v & 0x7FFFu) < valid_from; out[i] = window[v & 0x7FFFu]; }
+        else out[i] = (uint8_t)v;
+    }
+    return bad;
+}
+
+/* CRC-32 of A || B from crc(A), crc(B) and len(B): multiply crc(A) by x^(8 len) modulo the polynomial (GF(2) matrix
+ * squaring), then add crc(B). */
+static uint32_t gf2_times(const uint32_t* mat, uint32_t vec)
+{
+    uint32_t sum = 0;
+    for (; vec; vec >>= 1, ++mat)
+        if (vec & 1u) sum ^= *mat;
+    return sum;
+}
+static void gf2_square(uint32_t* sq, const uint32_t* mat)
+{
+    for (int i = 0; i < 32; ++i) sq[i] = gf2_times(mat, mat[i]);
+}
+uint32_t vkf_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2)
+{
+    uint32_t even[32], odd[32];
+    if (len2 == 0) return crc1;
+    odd[0] = 0xEDB88320u;                       /* operator for one zero bit */
+    for (int i = 1; i < 32; ++i) odd[i] = 1u << (i - 1);
+    gf2_square(even, odd);                      /* two bits */
+    gf2_square(odd, even);                      /* four bits */
+    do {                                        /* first square gives the operator for one zero byte */
+        gf2_square(even, odd);
+        if (len2 & 1) crc1 = gf2_times(even, crc1);
+        len2 >>= 1;
+        if (!len2) break;
+        gf2_square(odd, even);
+        if (len2 & 1) crc1 = gf2_times(odd, crc1);
+        len2 >>= 1;
+    } while (len2);
+    return crc1 ^ crc2;
+}
 int vkf_abi_version(void) { return 1; }

@@ -81,6 +81,17 @@ def feed_lib():
             L.vkf_gunzip.restype = C.c_int
             L.vkf_crc32.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t]
             L.vkf_crc32.restype = C.c_uint32
+            L.vkf_gzip_header_len.argtypes = [C.c_void_p, C.c_size_t]
+            L.vkf_gzip_header_len.restype = C.c_size_t
+            L.vkf_next_sync.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t]
+            L.vkf_next_sync.restype = C.c_size_t
+            L.vkf_inflate_piece.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                            C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+            L.vkf_inflate_piece.restype = C.c_int
+            L.vkf_resolve16.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+            L.vkf_resolve16.restype = C.c_size_t
+            L.vkf_crc32_combine.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
+            L.vkf_crc32_combine.restype = C.c_uint32
             _feed_lib = L
         except OSError:
             _feed_lib = False
@@ -108,8 +119,118 @@ def gunzip_into(comp, buf: "PinnedBuffer", size_hint=0, verify_crc=True):
         cap = max(2 * buf.array.size, cap + (1 << 32 if size_hint else 0))
 
 
-def inflate_into(path, buf: PinnedBuffer):
-    """Read a FASTQ file (gzip, possibly multi-member, or plain text) into ``buf``; returns the number of bytes."""
+_piece_pool = None
+_piece_pool_lock = threading.Lock()
+WINDOW = 32768
+
+
+def piece_pool():
+    """threads that decode the pieces of ONE gzip member (leaf tasks only; separate from a feeder's per-sample pool)"""
+    global _piece_pool
+    with _piece_pool_lock:
+        if _piece_pool is None:
+            _piece_pool = ThreadPoolExecutor(max_workers=max(2, len(os.sched_getaffinity(0))), thread_name_prefix="vk-piece")
+    return _piece_pool
+
+
+def gunzip_parallel(comp, buf: "PinnedBuffer", size_hint, threads, verify_crc=True, min_piece=1 << 20):
+    """One single-member gzip file on several threads (see ``csrc/vk_inflate.c``, "one gzip member on several threads"):
+    cut the stream behind the empty stored blocks pigz leaves after every chunk, decode the pieces concurrently (the
+    first as bytes in place, the others as 16-bit symbols with placeholders for the 32 KiB in front of them), resolve
+    the placeholders front to back, check ISIZE and the CRC-32 of the whole member.  Returns the number of bytes, or
+    None when the file is not of that shape or anything does not add up (the caller then decodes it serially)."""
+    L = feed_lib()
+    if L is None or threads < 2 or size_hint <= 0:
+        return None
+    a = np.frombuffer(comp, dtype=np.uint8) if not isinstance(comp, np.ndarray) else comp
+    n, base = a.size, a.ctypes.data
+    hl = L.vkf_gzip_header_len(base, n)
+    if hl == 0 or n - hl - 8 < 2 * min_piece or size_hint < n // 2:
+        return None
+    want = int(min(threads * 3, (n - hl - 8) // min_piece))
+    step = (n - hl - 8) // want
+    cuts = [hl]
+    for k in range(1, want):
+        pos = L.vkf_next_sync(base, n - 8, hl + k * step)
+        if pos >= n - 8:
+            break
+        if pos > cuts[-1]:
+            cuts.append(int(pos))
+    P = len(cuts)
+    if P < 2:
+        return None
+    ratio = size_hint / float(n - hl)
+    buf.reserve(size_hint + 64)
+    out_base = buf.array.ctypes.data
+
+    def decode(i):
+        start = cuts[i]
+        last = i + 1 == P
+        ln = (n - start) if last else (cuts[i + 1] - start)
+        got, used = C.c_size_t(), C.c_size_t()
+        if i == 0:
+            rc = L.vkf_inflate_piece(base + start, ln, 0, 0, out_base, size_hint, C.byref(got), C.byref(used))
+            return rc, None, int(got.value), int(used.value), ln
+        cap = int(ln * ratio * 1.25) + (1 << 16)
+        while True:
+            sym = np.empty(cap, dtype=np.uint16)
+            rc = L.vkf_inflate_piece(base + start, ln, 1 if last else 0, 1, sym.ctypes.data, cap, C.byref(got), C.byref(used))
+            if rc != VKF_ESPACE or cap > 64 * ln + (1 << 20):
+                return rc, sym, int(got.value), int(used.value), ln
+            cap *= 2
+
+    pool = piece_pool()
+    res = list(pool.map(decode, range(P)))
+    if any(r[0] != VKF_OK for r in res):
+        return None
+    if res[-1][3] != res[-1][4] - 8:                       # the final block must end right in front of the trailer
+        return None
+    lens = [r[2] for r in res]
+    offs = [0]
+    for x in lens:
+        offs.append(offs[-1] + x)
+    total = offs[-1]
+    trailer = a[n - 8:].tobytes()
+    if (total & 0xFFFFFFFF) != int.from_bytes(trailer[4:], "little") or total > size_hint:
+        return None
+
+    def window_of(off):
+        if off >= WINDOW:
+            return buf.array[off - WINDOW:off], 0
+        w = np.zeros(WINDOW, dtype=np.uint8)
+        w[WINDOW - off:] = buf.array[:off]
+        return w, WINDOW - off
+
+    # front to back: the last 32 KiB of every piece (the window of the next one), then everything else concurrently
+    bad = 0
+    for i in range(1, P):
+        t0 = max(0, lens[i] - WINDOW)
+        w, valid_from = window_of(offs[i])
+        bad += L.vkf_resolve16(res[i][1].ctypes.data + 2 * t0, lens[i] - t0, w.ctypes.data, valid_from, out_base + offs[i] + t0)
+
+    def head(i):
+        t0 = max(0, lens[i] - WINDOW)
+        if t0 == 0:
+            return 0
+        w, valid_from = window_of(offs[i])
+        return L.vkf_resolve16(res[i][1].ctypes.data, t0, w.ctypes.data, valid_from, out_base + offs[i])
+
+    bad += sum(pool.map(head, range(1, P)))
+    if bad:
+        return None
+    if verify_crc:
+        crcs = list(pool.map(lambda i: L.vkf_crc32(0, out_base + offs[i], lens[i]), range(P)))
+        crc = crcs[0]
+        for i in range(1, P):
+            crc = L.vkf_crc32_combine(crc, crcs[i], lens[i])
+        if crc != int.from_bytes(trailer[:4], "little"):
+            return None
+    return total
+
+
+def inflate_into(path, buf: PinnedBuffer, threads=1):
+    """Read a FASTQ file (gzip, possibly multi-member, or plain text) into ``buf``; returns the number of bytes.
+    ``threads`` > 1 lets one pigz-written member be decoded by several threads (``gunzip_parallel``)."""
     path = str(path)
     with open(path, "rb") as f:
         magic = f.read(2)
@@ -123,7 +244,9 @@ def inflate_into(path, buf: PinnedBuffer):
         if feed_lib() is not None:
             comp = np.empty(os.fstat(f.fileno()).st_size, dtype=np.uint8)
             f.readinto(memoryview(comp))
-            got = gunzip_into(comp, buf, hint)
+            got = gunzip_parallel(comp, buf, hint, threads) if threads > 1 else None
+            if got is None:
+                got = gunzip_into(comp, buf, hint)
             if got is not None:
                 return got
             f.seek(0)                                  # let zlib have the last word (and raise its own error)
@@ -164,6 +287,8 @@ class SampleFeeder:
         self.path_of = path_of
         self.threads = threads or max(1, min(len(os.sched_getaffinity(0)), 16))
         self.depth = depth or self.threads + 1
+        # fewer samples than threads: the spare threads split single gzip members (pigz-written files) into pieces
+        self.piece_threads = max(1, self.threads // max(1, min(len(self.items), self.threads)))
         self.pinned = pinned
         self._free = deque()
         self._lock = threading.Lock()
@@ -174,7 +299,7 @@ class SampleFeeder:
             buf = self._free.popleft() if self._free else None
         if buf is None:
             buf = PinnedBuffer(0, self.pinned)
-        n = inflate_into(self.path_of(it), buf)
+        n = inflate_into(self.path_of(it), buf, self.piece_threads)
         return buf, n
 
     def release(self, buf):
