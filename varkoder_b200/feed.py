@@ -278,6 +278,29 @@ def inflate_into(path, buf: PinnedBuffer, threads=1):
         return n
 
 
+# Page-locking memory is slow (the driver pins every page), so buffers outlive a feeder: the next batch of the
+# process starts with the pinned buffers of the previous one.
+_buffer_cache = {True: deque(), False: deque()}
+_buffer_cache_lock = threading.Lock()
+_BUFFER_CACHE_MAX = 64
+
+
+def _cached_buffer(pinned):
+    with _buffer_cache_lock:
+        q = _buffer_cache[bool(pinned)]
+        if q:
+            return q.popleft()
+    return PinnedBuffer(0, pinned)
+
+
+def _return_buffers(bufs):
+    with _buffer_cache_lock:
+        for b in bufs:
+            q = _buffer_cache[bool(b.pinned)]
+            if len(q) < _BUFFER_CACHE_MAX:
+                q.append(b)
+
+
 class SampleFeeder:
     """Iterate ``(index, item, PinnedBuffer, n_bytes)`` over samples in submission order, inflating up to ``depth``
     samples ahead on ``threads`` worker threads.  Buffers are recycled: hand one back with :meth:`release`."""
@@ -298,7 +321,7 @@ class SampleFeeder:
         with self._lock:
             buf = self._free.popleft() if self._free else None
         if buf is None:
-            buf = PinnedBuffer(0, self.pinned)
+            buf = _cached_buffer(self.pinned)
         n = inflate_into(self.path_of(it), buf, self.piece_threads)
         return buf, n
 
@@ -323,6 +346,9 @@ class SampleFeeder:
 
     def close(self):
         self.pool.shutdown(wait=True, cancel_futures=True)
+        with self._lock:
+            free, self._free = list(self._free), deque()
+        _return_buffers(free)
 
     def __enter__(self):
         return self
