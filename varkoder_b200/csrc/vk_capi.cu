@@ -176,6 +176,7 @@ void enqueue_parse(vk_ctx* c, const vk_params* params, bool rescan = true)
     a.cap_reads = cap;
     a.cap_sorted = c->sorted.cap;
     a.n_count_ctas = (uint32_t)(c->n_sms * c->count_ctas_per_sm);
+    if (params && params->k == 9 && c->use_count16) a.n_count_ctas /= 2;      // k = 9 counts in CTA pairs (count9h_kernel)
     a.exact_layout = c->exact_layout ? 1u : 0u;
     a.test_tight = c->test_tight ? 1u : 0u;
     launch(c, plan_kernel, dim3(1), dim3(64), 0, c->text, c->starts.p, c->ends.p, a, c->plan_d);
@@ -222,6 +223,21 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist, int breaklen)
             return;
         }
     }
+    if constexpr (K == 9) {
+        if (c->use_count16) {
+            // canonical classes in two halves, one per CTA of a pair (vk_count.cuh)
+            const unsigned pairs = (unsigned)(c->n_sms * c->count_ctas_per_sm) / 2;
+            const size_t smem = (size_t)32768 * sizeof(uint32_t) + 2048;      // + padding to a 2 KiB shared address
+            CU(cudaFuncSetAttribute(count9h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            launch(c, count9h_kernel, dim3(2 * pairs), block, smem, reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d,
+                   c->slabs.p, breaklen);
+            ++c->launches;
+            c->mark(EV_COUNT);
+            launch(c, reduce_slabs9h_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, seg_hist);
+            ++c->launches;
+            return;
+        }
+    }
     if constexpr (K <= 7) {
         // the histogram sits at a 64 KiB-aligned shared address (vk_count.cuh): up to 64 KiB of padding in front
         const size_t smem = 0x10000 + (size_t)(NK + 32) * sizeof(uint32_t);
@@ -249,6 +265,7 @@ void enqueue_count(vk_ctx* c, const vk_params* p, unsigned long long* seg_hist, 
     const int k = p->k;
     const uint32_t nk = 1u << (2 * k);
     if (k <= 7 || (k == 8 && c->use_count16)) c->slabs.ensure((size_t)c->n_sms * c->count_ctas_per_sm * nk);
+    if (k == 9 && c->use_count16) c->slabs.ensure((size_t)c->n_sms * c->count_ctas_per_sm * 65536u);
     const int bgrid = (int)std::min<uint64_t>((n_reads_bound + kBucketThreads * kBucketItems - 1) / (kBucketThreads * kBucketItems) + 1,
                                              (uint64_t)c->n_sms * 8);
     launch(c, bucket_scatter_kernel, dim3(bgrid), dim3(kBucketThreads), 0, c->starts.p, c->ends.p, k, p->seed, p->read_index_base, 0,

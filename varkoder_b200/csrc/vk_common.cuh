@@ -48,6 +48,7 @@ struct Plan {
     uint32_t long_reads;                         // reads longer than 2^24-1 bases (unsupported)
     uint32_t bucket_overflow;                    // a segment received more reads than its region holds (retry, exact layout)
     uint64_t seg_cap[kMaxLevels];                // entries each segment's region of the sorted array can hold
+    unsigned long long seg_next2[kMaxLevels];    // second set of unit counters (k = 9: the other half of every CTA pair)
 };
 
 // splitmix64 finaliser over (seed, global read index): the seeded per-read priority (DESIGN.md "Sub-sampling").

@@ -314,13 +314,15 @@ __device__ __forceinline__ Decoded decode_chunk(const Chunk& cur, uint32_t& carr
 }
 
 // which segment does this CTA serve?  (-1: none)
-__device__ __forceinline__ int cta_segment(const Plan* __restrict__ plan, uint32_t lane)
+__device__ __forceinline__ int cta_segment(const Plan* __restrict__ plan, uint32_t lane, uint32_t cta);
+__device__ __forceinline__ int cta_segment(const Plan* __restrict__ plan, uint32_t lane) { return cta_segment(plan, lane, blockIdx.x); }
+__device__ __forceinline__ int cta_segment(const Plan* __restrict__ plan, uint32_t lane, const uint32_t cta)
 {
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t b0 = plan->seg_cta_begin[lane], b1 = plan->seg_cta_begin[lane + 1];
     const uint32_t b2 = plan->seg_cta_begin[lane + 32], b3 = plan->seg_cta_begin[lane + 33];
-    const uint32_t m0 = __ballot_sync(FULL, blockIdx.x >= b0 && blockIdx.x < b1);
-    const uint32_t m1 = __ballot_sync(FULL, blockIdx.x >= b2 && blockIdx.x < b3);
+    const uint32_t m0 = __ballot_sync(FULL, cta >= b0 && cta < b1);
+    const uint32_t m1 = __ballot_sync(FULL, cta >= b2 && cta < b3);
     if (m0) return __ffs(m0) - 1;
     if (m1) return 32 + __ffs(m1) - 1;
     return -1;
@@ -562,6 +564,158 @@ count16_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ so
     }
     __syncthreads();
     count16_flush<K>(h8, h7, slab, tid, nthr);
+}
+
+// ------------------------------------------------------------------------------------------ k = 9: canonical halves
+// 4^9 forward bins do not fit shared memory even at 16 bits (512 KiB).  The 2 x 4^8 CANONICAL classes of an odd k do,
+// as two tables of 4^8 16-bit bins: CTAs work in PAIRS, both CTAs of a pair stream the same reads (the second read of
+// a text line is an L2 hit while the two stay close), and each counts the classes of its half with the exact
+// returning-add / drain scheme of count16_kernel<8>.
+//
+// The class of a 9-mer needs no comparison: a k-mer and its reverse complement have complementary MIDDLE bases, and
+// under the code A0 C1 T2 G3 the complement is XOR 2, so exactly one of the two has bit 9 (the high bit of base 4)
+// clear -- that one is the representative x, and dropping the zero bit gives a dense 17-bit class id:
+//     id = x[0..8] | x[10..17] << 9,   bin = id & 0xFFFF (word id & 0x7FFF, upper bin iff id bit 15),   half = id bit 16.
+// The reverse-complement index comes from a second window: the stream with its 2-bit groups reversed and complemented
+// (two BREV per 16 positions), in which the reverse complement of the 9-mer ending at position j is again a contiguous
+// field.  reduce_slabs9h_kernel writes a class total to seg_hist[x] and 0 to seg_hist[rc x]; fold_kernel's
+// fwd[i] + fwd[rc i] then yields the canonical abundance for both, unchanged.
+__device__ __forceinline__ uint64_t revcomp_groups64(uint64_t s)
+{
+    uint32_t a = __brev((uint32_t)(s >> 32)), b = __brev((uint32_t)s);          // a: new low word, b: new high word
+    a = ((a & 0x55555555u) << 1) | ((a >> 1) & 0x55555555u);                   // bit order inside each group back
+    b = ((b & 0x55555555u) << 1) | ((b >> 1) & 0x55555555u);
+    return (uint64_t)(a ^ 0xAAAAAAAAu) | ((uint64_t)(b ^ 0xAAAAAAAAu) << 32);   // complement = XOR 2 per group
+}
+// x << 2 of the representative of the 9-mer that ends at window position j (garbage above bit 19)
+template <int J>
+__device__ __forceinline__ uint32_t rep9_x4(uint32_t Wl, uint32_t Wh, uint32_t Rl, uint32_t Rh)
+{
+    const uint32_t f4 = __funnelshift_r(Wl, Wh, 2 * J);
+    const uint32_t r4 = J == 0 ? Rh : __funnelshift_r(Rl, Rh, 32 - 2 * J);
+    return (f4 & 0x800u) ? r4 : f4;
+}
+__device__ __forceinline__ uint32_t rep9_offset(uint32_t x4) { return (x4 & 0x7FCu) + ((x4 >> 1) & 0x1F800u); }
+__device__ __forceinline__ uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// The kernel is bound by the ALU pipe (97 % busy in the first version, FMA pipe 5 %), so everything that can be a
+// multiply-add is one: the multipliers are powers of two held in registers the compiler cannot see through
+// (Opaque), which keeps ptxas from turning the IMADs back into shifts.
+struct Opaque9 {
+    uint32_t two31;      // x * 2^31 >> 32 = x >> 1
+    uint32_t two11;      // x * 2^11
+    uint32_t h_addr;     // table base, 2 KiB aligned: (x4 & 0x7FC) | h_addr is one LOP3
+    uint32_t other19;    // (1 - half) << 19: (x4 ^ other19) & 0x80000 is 2^19 for a k-mer of this CTA's half, else 0
+};
+
+template <int J>
+__device__ __forceinline__ void count9_steps(uint32_t Wl, uint32_t Wh, uint32_t Rl, uint32_t Rh, uint32_t E, const Opaque9& q,
+                                             uint32_t& acc)
+{
+    if constexpr (J < 16) {
+        const uint32_t x4 = rep9_x4<J>(Wl, Wh, Rl, Rh);
+        // address: bits 2..10 stay, bits 12..17 move down by one (the hole is the representative's zero bit)
+        const uint32_t addr = mad_hi(x4 & 0x3F000u, q.two31, and_or(x4, 0x7FCu, q.h_addr));
+        // increment << 13: 1 (lower bin of the word) or 0x10001 (upper bin, bit 18), then x 2^-13 if the half is ours
+        const uint32_t inc13 = mad_lo(x4 & 0x40000u, q.two11, 0x2000u);
+        uint32_t mine;                                                           // (x4 ^ other19) & 0x80000
+        asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(mine) : "r"(x4), "r"(q.other19), "r"(0x80000u));
+        const uint32_t inc = mad_hi(mine, inc13, 0u);
+        acc |= smem_add_ret(addr, (E >> J) & 1u ? inc : 0u);
+        count9_steps<J + 1>(Wl, Wh, Rl, Rh, E, q, acc);
+    }
+}
+template <int J>
+__device__ __forceinline__ void drain9_steps(uint32_t Wl, uint32_t Wh, uint32_t Rl, uint32_t Rh, uint32_t* h8, uint32_t* slab)
+{
+    if constexpr (J < 16) {
+        drain16<8>(h8, slab, rep9_offset(rep9_x4<J>(Wl, Wh, Rl, Rh)) >> 2);
+        drain9_steps<J + 1>(Wl, Wh, Rl, Rh, h8, slab);
+    }
+}
+
+__global__ void __launch_bounds__(kCountThreads)
+count9h_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sorted, Plan* __restrict__ plan,
+               uint32_t* __restrict__ slabs, int breaklen)
+{
+    pdl_wait();
+    constexpr int K = 9;
+    constexpr uint32_t NB = 65536u;               // bins of one half
+    constexpr uint32_t FULL = 0xffffffffu;
+    extern __shared__ uint32_t s_raw9[];          // [pad to a 2 KiB shared address][32768 words: two 16-bit bins each]
+    const uint32_t tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
+    const uint32_t pair = blockIdx.x >> 1, half = blockIdx.x & 1u;
+    const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(s_raw9);
+    const uint32_t h_addr = (raw_addr + 2047u) & ~2047u;
+    uint32_t* const s_raw = s_raw9 + ((h_addr - raw_addr) >> 2);
+
+    uint32_t* const slab = slabs + (size_t)blockIdx.x * NB;
+    for (uint32_t i = tid; i < NB; i += nthr) slab[i] = 0;             // also for CTAs without a segment (reduce reads all)
+    const int seg = cta_segment(plan, lane, pair);
+    if (seg < 0) return;
+    const uint32_t seg_len = (uint32_t)(plan->seg_reads[seg] < plan->seg_cap[seg] ? plan->seg_reads[seg] : plan->seg_cap[seg]);
+    uint32_t* const h8 = s_raw;
+    for (uint32_t i = tid; i < 32768u; i += nthr) s_raw[i] = 0;
+    __syncthreads();
+
+    ChunkStream cs;
+    cs.init(text16, sorted + plan->seg_begin[seg], seg_len, half ? &plan->seg_next2[seg] : &plan->seg_next[seg], lane,
+            plan->n_bytes, (plan->seg_cta_begin[seg + 1] - plan->seg_cta_begin[seg]) * (blockDim.x >> 5));
+    const uint32_t zero = blockDim.x >> 31;                                  // 0, but not to the compiler
+    const Opaque9 q = {0x80000000u >> zero, 2048u >> zero, h_addr, (1u - half) << 19};
+    uint32_t carry = 0;
+    Chunk cur = cs.fetch();
+    while (__ballot_sync(FULL, cur.range != 0) != 0) {
+        const Chunk nxt = cs.fetch();
+        const Decoded d = decode_chunk<K>(cur, carry, lane, breaklen);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            // 24 bases: the 9-mers that end at chunk positions 16h .. 16h+15 (8 bases in front of the first one)
+            const uint64_t W = h ? (uint64_t)(d.Plo >> 16) | ((uint64_t)d.Phi << 16) : (uint64_t)d.Cc | ((uint64_t)d.Plo << 16);
+            const uint64_t W4 = W << 2;
+            const uint64_t R4 = (revcomp_groups64(W) >> 14) << 2;      // rc of the 9-mer ending at j: R4 >> (32 - 2j)
+            const uint32_t Wl = (uint32_t)W4, Wh = (uint32_t)(W4 >> 32), Rl = (uint32_t)R4, Rh = (uint32_t)(R4 >> 32);
+            const uint32_t E = h ? d.E >> 16 : d.E & 0xFFFFu;
+            uint32_t acc = 0;
+            count9_steps<0>(Wl, Wh, Rl, Rh, E, q, acc);
+            if (__ballot_sync(FULL, (acc & 0xC000u) != 0) != 0) {          // rare: some word is running hot
+                if (acc & 0xC000u) drain9_steps<0>(Wl, Wh, Rl, Rh, h8, slab);
+            }
+        }
+        cur = nxt;
+    }
+    __syncthreads();
+    count16_flush<8>(h8, nullptr, slab, tid, nthr);
+}
+
+// segment histograms of the k = 9 pairs: class totals at the representative's forward index, 0 at its reverse complement
+__global__ void __launch_bounds__(256)
+reduce_slabs9h_kernel(const uint32_t* __restrict__ slabs, const Plan* __restrict__ plan, unsigned long long* __restrict__ seg_hist)
+{
+    pdl_wait();
+    constexpr uint32_t NK = 1u << 18;
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (uint64_t)kMaxLevels * NK) return;
+    const uint32_t s = (uint32_t)(g / NK), x = (uint32_t)(g % NK);
+    unsigned long long sum = 0;
+    if ((x & 0x200u) == 0) {
+        const uint32_t id = (x & 0x1FFu) | ((x >> 10) << 9);
+        const uint32_t half = id >> 16, bin = id & 0xFFFFu;
+        const uint32_t c0 = plan->seg_cta_begin[s], c1 = plan->seg_cta_begin[s + 1];
+        for (uint32_t c = c0; c < c1; ++c) sum += slabs[(size_t)(2 * c + half) * 65536u + bin];
+    }
+    seg_hist[g] = sum;
 }
 
 // K3: per-segment histograms (uint64) = sum of the slabs of the CTAs that served the segment.

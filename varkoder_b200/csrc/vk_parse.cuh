@@ -365,6 +365,7 @@ plan_kernel(const uint8_t* __restrict__ text, uint64_t* __restrict__ starts, uin
         plan->seg_reads[l] = 0;
         plan->seg_bases[l] = 0;
         plan->seg_next[l] = 0;
+        plan->seg_next2[l] = 0;
         s_frac[l] = all ? 1.0 : (double)thr * 5.421010862427522e-20;      // thr / 2^64
     }
     __syncthreads();
