@@ -616,7 +616,7 @@ struct Opaque9 {
     uint32_t two31;      // x * 2^31 >> 32 = x >> 1
     uint32_t two11;      // x * 2^11
     uint32_t h_addr;     // table base, 2 KiB aligned: (x4 & 0x7FC) | h_addr is one LOP3
-    uint32_t other19;    // (1 - half) << 19: (x4 ^ other19) & 0x80000 is 2^19 for a k-mer of this CTA's half, else 0
+    uint32_t other19;    // (1 - half) << 19: bit 19 of x4 ^ other19 is set for a k-mer of this CTA's half
 };
 
 template <int J>
@@ -629,10 +629,11 @@ __device__ __forceinline__ void count9_steps(uint32_t Wl, uint32_t Wh, uint32_t 
         const uint32_t addr = mad_hi(x4 & 0x3F000u, q.two31, and_or(x4, 0x7FCu, q.h_addr));
         // increment << 13: 1 (lower bin of the word) or 0x10001 (upper bin, bit 18), then x 2^-13 if the half is ours
         const uint32_t inc13 = mad_lo(x4 & 0x40000u, q.two11, 0x2000u);
-        uint32_t mine;                                                           // (x4 ^ other19) & 0x80000
-        asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(mine) : "r"(x4), "r"(q.other19), "r"(0x80000u));
-        const uint32_t inc = mad_hi(mine, inc13, 0u);
-        acc |= smem_add_ret(addr, (E >> J) & 1u ? inc : 0u);
+        // 2^19 iff the k-mer is countable (bit J of E) AND of this CTA's half: (x4 ^ other19) & (E bit J moved to bit 19)
+        const uint32_t ej = (E << (19 - J)) & 0x80000u;
+        uint32_t mine;
+        asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(mine) : "r"(x4), "r"(q.other19), "r"(ej));
+        acc |= smem_add_ret(addr, mad_hi(mine, inc13, 0u));
         count9_steps<J + 1>(Wl, Wh, Rl, Rh, E, q, acc);
     }
 }
@@ -672,7 +673,7 @@ count9h_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ so
     ChunkStream cs;
     cs.init(text16, sorted + plan->seg_begin[seg], seg_len, half ? &plan->seg_next2[seg] : &plan->seg_next[seg], lane,
             plan->n_bytes, (plan->seg_cta_begin[seg + 1] - plan->seg_cta_begin[seg]) * (blockDim.x >> 5));
-    const uint32_t zero = blockDim.x >> 31;                                  // 0, but not to the compiler
+    const uint32_t zero = (uint32_t)(plan->n_bytes >> 63);                   // 0 (texts are shorter than 2^40), but not to ptxas
     const Opaque9 q = {0x80000000u >> zero, 2048u >> zero, h_addr, (1u - half) << 19};
     uint32_t carry = 0;
     Chunk cur = cs.fetch();
