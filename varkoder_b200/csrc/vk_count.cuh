@@ -26,7 +26,7 @@
 // previous K-1 codes in 64-bit windows, so each k-mer is one funnel shift + mask; validity is a bit mask whose
 // K-long runs give the 32-bit "a k-mer ends here" mask E.
 //
-// Three ways to count (template MODE):
+// Four ways to count:
 //   kSmem32   k <= 7: 4^k x u32 bins in shared memory, one ATOMS.POPC.INC per base.  Lanes without a k-mer
 //             increment one common trash word (POPC.INC folds lanes with the same address, so they add a single bank
 //             access; per-lane trash words measured 142.5 us against 139.3 us): ptxas cannot predicate ATOMS.POPC.INC
@@ -37,7 +37,9 @@
 //             pipe: 3.5 wavefronts per 32 random banks, profiles/r01_notes.md); 7-mers whose pair partner is not
 //             countable (read ends, N, break points) go to a 4^7 x u32 table.  16-bit bins are kept exact by
 //             watching the values the atomics return and draining hot words to the slab (see count16_kernel).
-//   kGlobal   k = 9: increments go straight to the global (L2-resident) segment histogram.
+//   pairs/9   k = 9 (count9h_kernel): the 2 x 4^8 canonical classes of the odd k as two such 16-bit tables, one per CTA
+//             of a pair that streams the same reads; the class falls out of the middle base without a comparison.
+//   kGlobal   k = 8, 9 behind VK_COUNT16=0: increments go straight to the global (L2-resident) segment histogram.
 #pragma once
 #include "vk_common.cuh"
 
