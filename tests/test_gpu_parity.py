@@ -341,17 +341,18 @@ def test_bucket_overflow_retry_is_exact(monkeypatch):
         eng.close()
 
 
-@pytest.mark.parametrize("k", [7, 8])
+@pytest.mark.parametrize("k", [7, 8, 9])
 def test_low_complexity_flood_16bit_bins(monkeypatch, k):
-    """k = 8 (default) and k = 7 in pair mode (VK_COUNT_PAIRS=1) count in 16-bit shared-memory bins; floods of one k-mer
-    (poly-A, poly-G, dinucleotide repeats) push bins past 2^16 many times per CTA and must come out exact
-    (rendezvous + fold, vk_count.cuh)."""
+    """k = 8 and k = 9 (default kernels) and k = 7 in pair mode (VK_COUNT_PAIRS=1) count in 16-bit shared-memory bins;
+    floods of one k-mer (poly-A, poly-G, dinucleotide repeats: for k = 9 both halves of the canonical classes, forward
+    and reverse-complement representatives) push bins past 2^16 many times per CTA and must come out exact
+    (returning adds + drains, vk_count.cuh)."""
     from varkoder_b200.engine import Engine
     monkeypatch.setenv("VK_COUNT_PAIRS", "1")
     engine = Engine(0)
     rng = np.random.default_rng(900 + k)
     reads = (["A" * 150] * 6000 + ["G" * 151] * 5000 + ["AC" * 75] * 3000 + ["ACGTN" * 30] * 500
-             + rand_reads(rng, 3000, 0, 200, p_n=0.01) + ["T" * 1200] * 50)
+             + rand_reads(rng, 3000, 0, 200, p_n=0.01) + ["T" * 1200] * 50 + ["C" * 149] * 2500 + ["GT" * 70] * 1500)
     order = rng.permutation(len(reads))
     buf = fastq([reads[i] for i in order])
     _, res, canon, _ = gpu_counts(engine, buf, Params(k=k, min_bp=0, max_bp=None, is_query=True))
