@@ -251,7 +251,7 @@ def images_for_samples(samples, outfolder, kmer_mapping, k=7, mapping_code="varK
     GPU by ``gpu_workers`` threads that each own a context, and their PNGs are written by the inflate pool off the
     critical path.  From gzip files the batch is bound by inflate on the host cores (2.0 Gbases/s with 16 threads,
     tools/bench_feed.py), so one GPU worker is the default; with inputs that are already in memory the path of one
-    sample is a chain of short dependent kernels and three or four samples in flight fill the gaps (600 -> 766
+    sample is a chain of short dependent kernels and three or four samples in flight fill the gaps (580 -> 778
     Gbases/s on 200 Mbp samples, 68 -> 180 on 10 Mbp ones, profiles/r01_notes.md).
 
     ``samples``: iterable of dicts ``{"sample": name, "path": clean .fq(.gz), "labels": [...], "base_sd": float}``;
