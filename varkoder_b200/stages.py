@@ -60,7 +60,8 @@ def read_clean_fastq(path):
     buf = _PINNED.get(os.getpid())
     if buf is None:
         buf = _PINNED[os.getpid()] = PinnedBuffer(0, pinned=True)
-    n = inflate_into(path, buf)
+    # one sample at a time: every host thread may work on this file (a pigz-written member is decoded in pieces)
+    n = inflate_into(path, buf, threads=len(os.sched_getaffinity(0)))
     return buf.array[:n]
 
 
