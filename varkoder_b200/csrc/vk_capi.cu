@@ -76,6 +76,12 @@ struct vk_ctx {
     bool ev_valid[EV_N] = {};
     uint64_t launches = 0;
     int count_threads = 1024, count_ctas_per_sm = 1;      // count-kernel launch shape (VK_COUNT_THREADS / VK_COUNT_CTAS)
+    int count_extra = 0;            // k <= 8: CTAs launched beyond the resident ones (VK_COUNT_EXTRA); they start when the
+                                    // CTAs of the small segments have finished and level the tail of the big ones.
+                                    // Measured at k = 7: 0 -> 139.0 us, 1 -> 138.4, 2 -> 139.3, 3 and more -> 155+: off.
+    int count_extra9 = 6;           // k = 9: extra PAIRS (VK_COUNT_EXTRA9).  74 pairs over 11 segments leave six pairs with
+                                    // 1.5 % of the work; 2.76 ms (0) -> 2.64 (2) -> 2.59 (6) -> 2.66 (10) per Gbp
+    int count_grid() const { return n_sms * count_ctas_per_sm + count_extra; }
 
     // "outbox": [Plan, padded to kPlanPad bytes][pixels of every level] contiguous on the device and mirrored in pinned
     // host memory, so that the fused path reads everything back with ONE device-to-host copy
@@ -175,8 +181,9 @@ void enqueue_parse(vk_ctx* c, const vk_params* params, bool rescan = true)
     a.n_bytes = n;
     a.cap_reads = cap;
     a.cap_sorted = c->sorted.cap;
-    a.n_count_ctas = (uint32_t)(c->n_sms * c->count_ctas_per_sm);
-    if (params && params->k == 9 && c->use_count16) a.n_count_ctas /= 2;      // k = 9 counts in CTA pairs (count9h_kernel)
+    a.n_count_ctas = (uint32_t)c->count_grid();
+    if (params && params->k == 9 && c->use_count16)                             // k = 9 counts in CTA pairs (count9h_kernel)
+        a.n_count_ctas = (uint32_t)(c->n_sms * c->count_ctas_per_sm / 2 + c->count_extra9);
     a.exact_layout = c->exact_layout ? 1u : 0u;
     a.test_tight = c->test_tight ? 1u : 0u;
     launch(c, plan_kernel, dim3(1), dim3(64), 0, c->text, c->starts.p, c->ends.p, a, c->plan_d);
@@ -207,7 +214,7 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist, int breaklen)
 {
     using namespace vk;
     constexpr uint32_t NK = 1u << (2 * K);
-    const dim3 grid(c->n_sms * c->count_ctas_per_sm), block(c->count_threads);
+    const dim3 grid(c->count_grid()), block(c->count_threads);
     const uint64_t total = (uint64_t)kMaxLevels * NK;
     if constexpr (K == 7 || K == 8) {
         if (K == 8 ? c->use_count16 : c->use_pairs) {
@@ -226,7 +233,7 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist, int breaklen)
     if constexpr (K == 9) {
         if (c->use_count16) {
             // canonical classes in two halves, one per CTA of a pair (vk_count.cuh)
-            const unsigned pairs = (unsigned)(c->n_sms * c->count_ctas_per_sm) / 2;
+            const unsigned pairs = (unsigned)(c->n_sms * c->count_ctas_per_sm / 2 + c->count_extra9);
             const size_t smem = (size_t)32768 * sizeof(uint32_t) + 2048;      // + padding to a 2 KiB shared address
             CU(cudaFuncSetAttribute(count9h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             launch(c, count9h_kernel, dim3(2 * pairs), block, smem, reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d,
@@ -264,8 +271,8 @@ void enqueue_count(vk_ctx* c, const vk_params* p, unsigned long long* seg_hist, 
     using namespace vk;
     const int k = p->k;
     const uint32_t nk = 1u << (2 * k);
-    if (k <= 7 || (k == 8 && c->use_count16)) c->slabs.ensure((size_t)c->n_sms * c->count_ctas_per_sm * nk);
-    if (k == 9 && c->use_count16) c->slabs.ensure((size_t)c->n_sms * c->count_ctas_per_sm * 65536u);
+    if (k <= 7 || (k == 8 && c->use_count16)) c->slabs.ensure((size_t)c->count_grid() * nk);
+    if (k == 9 && c->use_count16) c->slabs.ensure((size_t)2 * (c->n_sms * c->count_ctas_per_sm / 2 + c->count_extra9) * 65536u);
     const int bgrid = (int)std::min<uint64_t>((n_reads_bound + kBucketThreads * kBucketItems - 1) / (kBucketThreads * kBucketItems) + 1,
                                              (uint64_t)c->n_sms * 8);
     launch(c, bucket_scatter_kernel, dim3(bgrid), dim3(kBucketThreads), 0, c->starts.p, c->ends.p, k, p->seed, p->read_index_base, 0,
@@ -490,6 +497,8 @@ int vk_ctx_create(int device, vk_ctx** out)
         c->n_sms = prop.multiProcessorCount;
         if (const char* e = getenv("VK_COUNT_THREADS")) c->count_threads = atoi(e);
         if (const char* e = getenv("VK_COUNT_CTAS")) c->count_ctas_per_sm = atoi(e);
+        if (const char* e = getenv("VK_COUNT_EXTRA")) c->count_extra = std::max(0, std::min(64, atoi(e)));
+        if (const char* e = getenv("VK_COUNT_EXTRA9")) c->count_extra9 = std::max(0, std::min(64, atoi(e)));
         if (const char* e = getenv("VK_TEST_TIGHT_BUCKETS")) c->test_tight = atoi(e) != 0;
         if (const char* e = getenv("VK_PDL")) c->use_pdl = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT16")) c->use_count16 = atoi(e) != 0;

@@ -317,7 +317,12 @@ __device__ __forceinline__ Decoded decode_chunk(const Chunk& cur, uint32_t& carr
 
 // which segment does this CTA serve?  (-1: none)
 __device__ __forceinline__ int cta_segment(const Plan* __restrict__ plan, uint32_t lane, uint32_t cta);
-__device__ __forceinline__ int cta_segment(const Plan* __restrict__ plan, uint32_t lane) { return cta_segment(plan, lane, blockIdx.x); }
+// CTAs are handed to the SMs in launch order and the plan puts the big segments first; the count kernels therefore
+// number themselves BACKWARDS, so that the small last segments run on the first CTAs and the few CTAs launched beyond
+// the SM count (vk_ctx::count_extra) join a big segment late, when a small one has finished: they take units off the
+// segment's shared counter and level the tail.
+__device__ __forceinline__ uint32_t logical_cta() { return gridDim.x - 1u - blockIdx.x; }
+__device__ __forceinline__ int cta_segment(const Plan* __restrict__ plan, uint32_t lane) { return cta_segment(plan, lane, logical_cta()); }
 __device__ __forceinline__ int cta_segment(const Plan* __restrict__ plan, uint32_t lane, const uint32_t cta)
 {
     constexpr uint32_t FULL = 0xffffffffu;
@@ -397,7 +402,7 @@ count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sort
 
     if (MODE == kSmem32) {
         __syncthreads();
-        uint32_t* slab = slabs + (size_t)blockIdx.x * NK;
+        uint32_t* slab = slabs + (size_t)logical_cta() * NK;
         for (uint32_t i = tid; i < NK; i += blockDim.x) slab[i] = s_hist[i];
     }
 }
@@ -491,7 +496,7 @@ count16_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ so
     constexpr uint32_t kWords = 32768u + (K == 7 ? 16384u : 0u);
     const uint32_t h8_addr = (uint32_t)__cvta_generic_to_shared(s_raw);
     const uint32_t h7_addr = h8_addr + 32768u * 4u;
-    uint32_t* const slab = slabs + (size_t)blockIdx.x * NK;
+    uint32_t* const slab = slabs + (size_t)logical_cta() * NK;
     for (uint32_t i = tid; i < kWords; i += nthr) s_raw[i] = 0;
     for (uint32_t i = tid; i < NK; i += nthr) slab[i] = 0;             // drains and the final fold ADD to the slab
     __syncthreads();
@@ -658,12 +663,12 @@ count9h_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ so
     constexpr uint32_t FULL = 0xffffffffu;
     extern __shared__ uint32_t s_raw9[];          // [pad to a 2 KiB shared address][32768 words: two 16-bit bins each]
     const uint32_t tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
-    const uint32_t pair = blockIdx.x >> 1, half = blockIdx.x & 1u;
+    const uint32_t pair = logical_cta() >> 1, half = logical_cta() & 1u;
     const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(s_raw9);
     const uint32_t h_addr = (raw_addr + 2047u) & ~2047u;
     uint32_t* const s_raw = s_raw9 + ((h_addr - raw_addr) >> 2);
 
-    uint32_t* const slab = slabs + (size_t)blockIdx.x * NB;
+    uint32_t* const slab = slabs + (size_t)logical_cta() * NB;
     for (uint32_t i = tid; i < NB; i += nthr) slab[i] = 0;             // also for CTAs without a segment (reduce reads all)
     const int seg = cta_segment(plan, lane, pair);
     if (seg < 0) return;
