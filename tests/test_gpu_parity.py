@@ -444,6 +444,31 @@ def test_batch_of_bembidion_shaped_samples(engine, tmp_path):
     assert st["tiny"] == {"failed_step": "split"}
 
 
+def test_single_pigz_member_through_the_batch_entry(engine, tmp_path):
+    """ONE sample in a file written the way pigz writes it (one member, sync point after every chunk, chunks primed with
+    the previous 32 KiB): the feeder's spare threads decode the member in pieces (feed.gunzip_parallel), and what reaches
+    the GPU is the same text -- pixels equal the oracle's."""
+    from PIL import Image
+    from tests.test_feed import pigz_like
+    from varkoder_b200 import feed, stages
+    from varkoder_b200.ladder import image_name, ladder
+    buf = synth.fixed(9_000_000, 150, seed=61).tobytes()
+    p = tmp_path / "P.fq.gz"
+    p.write_bytes(pigz_like(buf, 1))
+    probe = feed.PinnedBuffer(0, pinned=False)
+    assert feed.gunzip_parallel(np.fromfile(p, dtype=np.uint8), probe, len(buf), 8) == len(buf)      # the split path is taken
+    table = get_kmer_mapping(7, "cgr")
+    out = tmp_path / "img"
+    st = stages.images_for_samples([dict(sample="P", path=str(p), labels=["x"], base_sd=0.0)], out, table, k=7,
+                                   mapping_code="cgr", min_bp=2_000_000, max_bp=None, seeds=[5], threads=8, engine=engine)
+    parsed = dsk.parse_fastq(buf)
+    levels = ladder(parsed["nsites_ref"], 2_000_000, None)
+    assert st["P"]["splitting_bp_per_file"] == ",".join(str(x) for x in levels)
+    pix = oracle_images(oracle_levels(buf, 7, 5, levels, parsed["nsites_ref"]), table.lut)
+    for lvl, bp in enumerate(levels):
+        assert (np.asarray(Image.open(out / image_name("P", bp, "cgr", 7))) == pix[lvl]).all()
+
+
 def test_full_size_properties_config3(engine):
     """BASELINE config 3 shape (1 Gbp, k=9, varKode, -M 0: 11 levels; the 4^9 histogram lives in L2) on device-resident
     synthetic reads: ladder, nesting, reverse-complement symmetry, window conservation, rank-transform invariants, exact
