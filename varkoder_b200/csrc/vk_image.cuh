@@ -182,7 +182,11 @@ bitonic_global_step(unsigned long long* __restrict__ vals, uint32_t n_pad, uint3
     if ((a > b) == up) { v[lo] = b; v[hi] = a; }
 }
 
-// all steps with stride < TILE/2... handled in shared memory: TILE elements per CTA
+// Steps with stride < kSortTile of the global bitonic sort, one tile of kSortTile elements per CTA of 1024 threads.
+// A thread owns elements e0 = 128 warp + lane and e0 + 32, + 64, + 96, so every comparator of stride <= 64 stays inside
+// a warp: strides 64 and 32 inside the thread, 16..1 by shuffle, all in registers (as in image_kernel_cluster); only
+// the strides >= 128 go through shared memory with a block barrier (15 of the 78 steps of the first launch, 5 of the 12
+// of the later ones).
 constexpr uint32_t kSortTile = 4096;
 __global__ void __launch_bounds__(1024)
 bitonic_tile_kernel(unsigned long long* __restrict__ vals, uint32_t n_pad, uint32_t size_begin, uint32_t size_end,
@@ -190,26 +194,73 @@ bitonic_tile_kernel(unsigned long long* __restrict__ vals, uint32_t n_pad, uint3
 {
     pdl_wait();
     // runs, for size = size_begin .. size_end (doubling), the strides min(size/2, first_stride) .. 1 inside a tile
+    constexpr uint32_t FULL = 0xffffffffu;
     __shared__ unsigned long long s[kSortTile];
     unsigned long long* v = vals + (size_t)blockIdx.y * n_pad + (size_t)blockIdx.x * kSortTile;
     const uint32_t base = blockIdx.x * kSortTile;
-    for (uint32_t i = threadIdx.x; i < kSortTile; i += blockDim.x) s[i] = v[i];
+    const uint32_t tid = threadIdx.x;
+    VK_ASSERT(blockDim.x == 1024);
+    for (uint32_t i = tid; i < kSortTile; i += 1024) s[i] = v[i];
     __syncthreads();
+    const uint32_t e0 = 128u * (tid >> 5) + (tid & 31u);
+    unsigned long long a[4];
+    auto exchange = [&](unsigned long long& x, unsigned long long& y, bool up) {
+        if ((x > y) == up) { const unsigned long long t = x; x = y; y = t; }
+    };
+    // strides `stride` (<= 64) .. 1 of one size, on the registers
+    auto low_strides = [&](const uint32_t size, uint32_t stride) {
+        if (stride == 64u) {
+            exchange(a[0], a[2], ((base + e0) & size) == 0);
+            exchange(a[1], a[3], ((base + e0 + 32u) & size) == 0);
+            stride = 32u;
+        }
+        if (stride == 32u) {
+            exchange(a[0], a[1], ((base + e0) & size) == 0);
+            exchange(a[2], a[3], ((base + e0 + 64u) & size) == 0);
+            stride = 16u;
+        }
+        for (; stride > 0; stride >>= 1) {
+            const bool lower = (e0 & stride) == 0;                  // the same for the four elements (stride < 32)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const unsigned long long o = __shfl_xor_sync(FULL, a[r], stride);
+                const bool keep_min = lower == (((base + e0 + 32u * r) & size) == 0);
+                a[r] = (o < a[r]) == keep_min ? o : a[r];
+            }
+        }
+    };
+    bool in_regs = false;
     for (uint32_t size = size_begin; size <= size_end; size <<= 1) {
         uint32_t stride = size >> 1;
         if (stride > first_stride) stride = first_stride;
-        for (; stride > 0; stride >>= 1) {
-            for (uint32_t t = threadIdx.x; t < kSortTile / 2; t += blockDim.x) {
-                const uint32_t lo = 2 * t - (t & (stride - 1));
-                const uint32_t hi = lo + stride;
-                const bool up = ((base + lo) & size) == 0;
-                const unsigned long long a = s[lo], b = s[hi];
-                if ((a > b) == up) { s[lo] = b; s[hi] = a; }
+        if (stride >= 128u) {
+            if (in_regs) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) s[e0 + 32u * r] = a[r];
+                in_regs = false;
+                __syncthreads();
             }
-            __syncthreads();
+            for (; stride >= 128u; stride >>= 1) {
+                for (uint32_t t = tid; t < kSortTile / 2; t += 1024) {
+                    const uint32_t lo = 2 * t - (t & (stride - 1));
+                    const uint32_t hi = lo + stride;
+                    const bool up = ((base + lo) & size) == 0;
+                    const unsigned long long x = s[lo], y = s[hi];
+                    if ((x > y) == up) { s[lo] = y; s[hi] = x; }
+                }
+                __syncthreads();
+            }
         }
+        if (!in_regs) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a[r] = s[e0 + 32u * r];
+            in_regs = true;
+        }
+        low_strides(size, stride);
     }
-    for (uint32_t i = threadIdx.x; i < kSortTile; i += blockDim.x) v[i] = s[i];
+    // every thread last touched only its own four elements of s (or none): write them out from the registers
+#pragma unroll
+    for (int r = 0; r < 4; ++r) v[e0 + 32u * r] = a[r];
 }
 
 __global__ void __launch_bounds__(256)
