@@ -339,7 +339,14 @@ void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsign
         CU(cudaGetLastError());
         ++c->launches;
         for (uint32_t size = 2 * kSortTile; size <= n_pad; size <<= 1) {
-            for (uint32_t stride = size >> 1; stride >= kSortTile; stride >>= 1) {
+            uint32_t stride = size >> 1;
+            for (; (stride >> 1) >= kSortTile; stride >>= 2) {           // two strides per pass while both are global
+                dim3 gs((n_pad / 4 + 255) / 256, levels);
+                launch(c, bitonic_global_step2, dim3(gs), dim3(256), 0, c->vals.p, n_pad, size, stride);
+                CU(cudaGetLastError());
+                ++c->launches;
+            }
+            if (stride >= kSortTile) {
                 dim3 gs((n_pad / 2 + 255) / 256, levels);
                 launch(c, bitonic_global_step, dim3(gs), dim3(256), 0, c->vals.p, n_pad, size, stride);
                 CU(cudaGetLastError());

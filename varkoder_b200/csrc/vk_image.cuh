@@ -182,6 +182,27 @@ bitonic_global_step(unsigned long long* __restrict__ vals, uint32_t n_pad, uint3
     if ((a > b) == up) { v[lo] = b; v[hi] = a; }
 }
 
+// two consecutive steps (strides `stride` and `stride / 2`) in one pass: a thread owns the four elements they connect
+__global__ void __launch_bounds__(256)
+bitonic_global_step2(unsigned long long* __restrict__ vals, uint32_t n_pad, uint32_t size, uint32_t stride)
+{
+    pdl_wait();
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (n_pad >> 2)) return;
+    unsigned long long* v = vals + (size_t)blockIdx.y * n_pad;
+    const uint32_t h = stride >> 1;
+    const uint32_t low = q & (h - 1);
+    const uint32_t i = 4 * (q - low) + low;                    // bits log2(h) and log2(stride) of i are clear
+    const bool up = (i & size) == 0;                           // size > stride: the same for the four
+    unsigned long long x0 = v[i], x1 = v[i + h], x2 = v[i + stride], x3 = v[i + stride + h];
+    unsigned long long t;
+    if ((x0 > x2) == up) { t = x0; x0 = x2; x2 = t; }
+    if ((x1 > x3) == up) { t = x1; x1 = x3; x3 = t; }
+    if ((x0 > x1) == up) { t = x0; x0 = x1; x1 = t; }
+    if ((x2 > x3) == up) { t = x2; x2 = x3; x3 = t; }
+    v[i] = x0; v[i + h] = x1; v[i + stride] = x2; v[i + stride + h] = x3;
+}
+
 // Steps with stride < kSortTile of the global bitonic sort, one tile of kSortTile elements per CTA of 1024 threads.
 // A thread owns elements e0 = 128 warp + lane and e0 + 32, + 64, + 96, so every comparator of stride <= 64 stays inside
 // a warp: strides 64 and 32 inside the thread, 16..1 by shuffle, all in registers (as in image_kernel_cluster); only
