@@ -19,6 +19,8 @@ value   device-resident: the texts are already in HBM.  EXACTLY K steps are deal
 e2e     same call with the text in pinned HOST memory: H2D copy + kernels + read-back, wall clock, two contexts.
 N > 1   one process per GPU (torchrun), each with its own samples (sharded by sample, no data-path
         collective): value = N * K * bases / max-over-ranks time; scaling "weak".
+Side measurements: --workload c3 (configs[2]: 1 Gbp, k = 9) and --workload c5 (configs[4]: ONE 30 Gbp sample
+read-sharded over the ranks, one NCCL all-reduce of the histograms; scaling "strong").
 """
 import argparse
 import json
@@ -271,6 +273,74 @@ def workload_config():
             "parallelism": "by-sample, one process per GPU, no collective"}
 
 
+def run_c5(args, world, rank, local, torch, dist):
+    """BASELINE configs[4]: ONE sample of 30 Gbp (k = 7, CGR, -M 0: 16 levels), read-sharded over the ranks: every rank
+    frames and counts its contiguous shard of the records, two scalars are all-gathered (records, bases per shard: the
+    global read index base and the sample-wide nsites), ONE NCCL all-reduce sums the per-segment histograms and the
+    per-level totals, every rank renders.  Device-resident shards (generated on the device), wall clock between
+    barriers, max over ranks."""
+    import time as _t
+    from varkoder_b200 import sharding, synth
+    from varkoder_b200.engine import Engine, Params
+    from varkoder_b200.mapping import get_kmer_mapping
+    total_reads = (args.total_bases + READ_LEN - 1) // READ_LEN
+    first = total_reads * rank // world
+    last = total_reads * (rank + 1) // world
+    shard_bases = min((last - first) * READ_LEN, args.total_bases - first * READ_LEN)
+    eng = Engine(local)
+    table = get_kmer_mapping(7, "cgr")
+    nbytes = synth.fixed_total_bytes(shard_bases, READ_LEN)
+    dev = torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda")
+    assert eng.synth_fastq(dev.data_ptr(), dev.numel(), shard_bases, READ_LEN, seed=20260118 + 5000, first_read=first) == nbytes
+    seg = torch.zeros(64 * 4 ** 7, dtype=torch.int64, device="cuda")
+    sp = Params(k=7, min_bp=MIN_BP, max_bp=None, seed=11)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        eng.attach(dev.data_ptr(), nbytes)
+        if world > 1:
+            return sharding.sharded_reads_to_images(eng, None, sp, table, seg_hist=seg)
+        return eng.reads_to_images(dev.data_ptr(), sp, table, on_device=True, n_bytes=nbytes, max_levels=16)
+
+    for _ in range(max(2, min(args.warmup, 3))):
+        rs = step()
+    assert rs.nsites == args.total_bases and rs.levels[0] == args.total_bases and rs.level_bases[0] == args.total_bases
+    steps = max(1, min(args.steps, 20))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = _t.perf_counter()
+    for _ in range(steps):
+        rs = step()
+    barrier()
+    ms = 1e3 * (_t.perf_counter() - t0) / steps
+    clocks = sampler.stop() if rank == 0 else None
+    tm = eng.timings()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.cpu()[0])
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": args.total_bases / (ms * 1e-3) / 1e9, "unit": "Gbases/s", "n_gpus": world, "steps": steps,
+            "warmup": max(2, min(args.warmup, 3)), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"configs[4]: ONE sample of {args.total_bases} bases (read length 150), k=7, cgr, -M 0 "
+                                   f"({len(rs.levels)} levels), read-sharded over {world} GPU(s): shards of {shard_bases} bases "
+                                   f"({nbytes / 1e9:.1f} GB of text) resident per GPU, all_gather(2 scalars) + ONE NCCL "
+                                   f"all_reduce(int64 x {len(rs.levels) * 4 ** 7 + 128})",
+                       "bases_per_step": args.total_bases, "levels": len(rs.levels),
+                       "l2_policy": "shards are far larger than L2"},
+            "levels": rs.levels, "level_bases": rs.level_bases,
+            "kernel_ms_last_step_rank0": tm, "clocks": clocks}), flush=True)
+    eng.close()
+
+
 # ----------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -284,8 +354,10 @@ def main():
                     help="samples in flight per GPU in the timed region: one context + host thread each (1 = one stream)")
     ap.add_argument("--no-concurrent", action="store_true", help="same as --in-flight 1")
     ap.add_argument("--bases", type=int, default=None, help="debug: smaller sample (invalidates the bench line)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
-                    help="c2 = BASELINE configs[1] (the bench line); c3 = configs[2]: 1 Gbp, k=9 varKode, -M 0 (side measurement)")
+    ap.add_argument("--total-bases", type=int, default=30_000_000_000, help="c5: bases of the one read-sharded sample")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"],
+                    help="c2 = BASELINE configs[1] (the bench line); c3 = configs[2]: 1 Gbp, k=9 varKode, -M 0; c5 = configs[4]: ONE "
+                         "30 Gbp sample, k=7, read-sharded over the ranks with one NCCL all-reduce (side measurements)")
     args = ap.parse_args()
     global N_BASES, K, MAPPING, MAX_BP, LEVELS
     if args.workload == "c3":
@@ -314,6 +386,11 @@ def main():
     torch.cuda.set_device(local)
     W = max(3, args.warmup)
     n_bases = args.bases
+    if args.workload == "c5":
+        run_c5(args, world, rank, local, torch, dist)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     import threading
     T = 1 if args.no_concurrent else max(1, args.in_flight)
