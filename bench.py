@@ -273,6 +273,105 @@ def workload_config():
             "parallelism": "by-sample, one process per GPU, no collective"}
 
 
+def run_c4(args, world, rank, local, torch, dist):
+    """BASELINE configs[3]: a batch of 96 samples of 10-50 Mbp (k = 7, varKode, defaults: every ladder starts at the
+    sample's own nsites), dealt to the ranks by size (sharding.assign_samples, longest first), every rank pushes its
+    share through `--in-flight` contexts that take samples off a common queue.  Device-resident texts, wall clock
+    between barriers, max over ranks; reports the per-rank load."""
+    import threading as _th
+    import time as _t
+    import numpy as np
+    from varkoder_b200 import sharding, synth
+    from varkoder_b200.engine import Engine, Params
+    from varkoder_b200.mapping import get_kmer_mapping
+    rng = np.random.default_rng(20260118 + 4000)
+    sizes = [int(x) for x in rng.integers(10_000_000, 50_000_001, 96)]
+    owner, loads = sharding.assign_samples(sizes, world)
+    mine = sorted((i for i in range(len(sizes)) if owner[i] == rank), key=lambda i: -sizes[i])
+    T = 1 if args.no_concurrent else max(1, args.in_flight)
+    engs = [Engine(local) for _ in range(T)]
+    table = get_kmer_mapping(7, "varKode")
+    texts = {}
+    first = 0
+    starts = []
+    for n in sizes:
+        starts.append(first)
+        first += (n + READ_LEN - 1) // READ_LEN
+    for i in mine:
+        nb = synth.fixed_total_bytes(sizes[i], READ_LEN)
+        d = torch.empty(nb + 64, dtype=torch.uint8, device="cuda")
+        assert engs[0].synth_fastq(d.data_ptr(), d.numel(), sizes[i], READ_LEN, seed=20260118 + 4000, first_read=starts[i]) == nb
+        texts[i] = (d, nb)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lock = _th.Lock()
+    errors, levels_seen = [], []
+
+    def run_all():
+        queue = list(mine)
+
+        def work(t):
+            try:
+                while True:
+                    with lock:
+                        if not queue:
+                            return
+                        i = queue.pop(0)
+                    d, nb = texts[i]
+                    r = engs[t].reads_to_images(d.data_ptr(), Params(k=7, min_bp=MIN_BP, max_bp=None, seed=100 + i), table,
+                                                on_device=True, n_bytes=nb, max_levels=16)
+                    assert r.nsites == sizes[i] and r.status == 0
+                    levels_seen.append(len(r.levels))
+            except Exception as exc:
+                errors.append(exc)
+        th = [_th.Thread(target=work, args=(t,)) for t in range(T)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        torch.cuda.synchronize()
+        if errors:
+            raise errors[0]
+
+    for e in engs:
+        e.set_fine_timing(False)
+    run_all()                                            # warm-up: every buffer of every context at its final size
+    reps = max(1, min(args.steps, 5))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = _t.perf_counter()
+    for _ in range(reps):
+        run_all()
+    barrier()
+    ms = 1e3 * (_t.perf_counter() - t0) / reps
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.cpu()[0])
+    if rank == 0:
+        total = sum(sizes)
+        print(json.dumps({
+            "metric": METRIC, "value": total / (ms * 1e-3) / 1e9, "unit": "Gbases/s", "n_gpus": world, "steps": reps,
+            "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
+            "config": {"workload": f"configs[3]: one batch of 96 samples of 10-50 Mbp ({total} bases in all, read length 150), "
+                                   f"k=7, varKode, -m 500K, every ladder from the sample's own nsites "
+                                   f"({min(levels_seen)}-{max(levels_seen)} levels), dealt to {world} GPU(s) by size, {T} samples in "
+                                   "flight per GPU; a step = the whole batch",
+                       "bases_per_step": total, "samples": len(sizes), "in_flight": T,
+                       "l2_policy": "every sample is read once per step; the batch of a rank (0.8-6 GB) is larger than L2"},
+            "per_rank_bases": loads, "balance_max_over_mean": max(loads) / (sum(loads) / len(loads)), "clocks": clocks}), flush=True)
+    for e in engs:
+        e.close()
+
+
 def run_c5(args, world, rank, local, torch, dist):
     """BASELINE configs[4]: ONE sample of 30 Gbp (k = 7, CGR, -M 0: 16 levels), read-sharded over the ranks: every rank
     frames and counts its contiguous shard of the records, two scalars are all-gathered (records, bases per shard: the
@@ -355,9 +454,10 @@ def main():
     ap.add_argument("--no-concurrent", action="store_true", help="same as --in-flight 1")
     ap.add_argument("--bases", type=int, default=None, help="debug: smaller sample (invalidates the bench line)")
     ap.add_argument("--total-bases", type=int, default=30_000_000_000, help="c5: bases of the one read-sharded sample")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 = BASELINE configs[1] (the bench line); c3 = configs[2]: 1 Gbp, k=9 varKode, -M 0; c5 = configs[4]: ONE "
-                         "30 Gbp sample, k=7, read-sharded over the ranks with one NCCL all-reduce (side measurements)")
+                         "30 Gbp sample, k=7, read-sharded over the ranks with one NCCL all-reduce; c4 = configs[3]: 96 samples of "
+                         "10-50 Mbp dealt to the ranks by size (side measurements)")
     args = ap.parse_args()
     global N_BASES, K, MAPPING, MAX_BP, LEVELS
     if args.workload == "c3":
@@ -386,6 +486,11 @@ def main():
     torch.cuda.set_device(local)
     W = max(3, args.warmup)
     n_bases = args.bases
+    if args.workload == "c4":
+        run_c4(args, world, rank, local, torch, dist)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload == "c5":
         run_c5(args, world, rank, local, torch, dist)
         if world > 1:

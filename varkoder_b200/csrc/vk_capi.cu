@@ -81,6 +81,7 @@ struct vk_ctx {
                                     // Measured at k = 7: 0 -> 139.0 us, 1 -> 138.4, 2 -> 139.3, 3 and more -> 155+: off.
     int count_extra9 = 6;           // k = 9: extra PAIRS (VK_COUNT_EXTRA9).  74 pairs over 11 segments leave six pairs with
                                     // 1.5 % of the work; 2.76 ms (0) -> 2.64 (2) -> 2.59 (6) -> 2.66 (10) per Gbp
+    int reads_per_cta = 0;          // VK_COUNT_READS_PER_CTA: > 0 caps the count CTAs of a small sample (plan_kernel)
     int count_grid() const { return n_sms * count_ctas_per_sm + count_extra; }
 
     // "outbox": [Plan, padded to kPlanPad bytes][pixels of every level] contiguous on the device and mirrored in pinned
@@ -182,6 +183,7 @@ void enqueue_parse(vk_ctx* c, const vk_params* params, bool rescan = true)
     a.cap_reads = cap;
     a.cap_sorted = c->sorted.cap;
     a.n_count_ctas = (uint32_t)c->count_grid();
+    a.reads_per_cta = (uint32_t)c->reads_per_cta;
     if (params && params->k == 9 && c->use_count16)                             // k = 9 counts in CTA pairs (count9h_kernel)
         a.n_count_ctas = (uint32_t)(c->n_sms * c->count_ctas_per_sm / 2 + c->count_extra9);
     a.exact_layout = c->exact_layout ? 1u : 0u;
@@ -506,6 +508,7 @@ int vk_ctx_create(int device, vk_ctx** out)
         if (const char* e = getenv("VK_COUNT_CTAS")) c->count_ctas_per_sm = atoi(e);
         if (const char* e = getenv("VK_COUNT_EXTRA")) c->count_extra = std::max(0, std::min(64, atoi(e)));
         if (const char* e = getenv("VK_COUNT_EXTRA9")) c->count_extra9 = std::max(0, std::min(64, atoi(e)));
+        if (const char* e = getenv("VK_COUNT_READS_PER_CTA")) c->reads_per_cta = std::max(0, atoi(e));
         if (const char* e = getenv("VK_TEST_TIGHT_BUCKETS")) c->test_tight = atoi(e) != 0;
         if (const char* e = getenv("VK_PDL")) c->use_pdl = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT16")) c->use_count16 = atoi(e) != 0;

@@ -271,6 +271,7 @@ struct PlanArgs {
     uint64_t cap_reads;
     uint64_t cap_sorted;    // entries the sorted array holds
     uint32_t n_count_ctas;  // grid of the count kernel
+    uint32_t reads_per_cta; // > 0: use at most ceil(n_reads / reads_per_cta) CTAs (small samples leave SMs to other samples)
     uint32_t exact_layout;  // 1: every segment region holds all reads (retry after a bucket overflow)
     uint32_t test_tight;    // tests only (VK_TEST_TIGHT_BUCKETS=1): regions of half the expected size, to force the retry
 };
@@ -413,8 +414,14 @@ plan_kernel(const uint8_t* __restrict__ text, uint64_t* __restrict__ starts, uin
         if (l == 0) plan->seg_begin[kMaxLevels] = s_off;
         // CTAs: one per segment, the rest in proportion to the expected bases; leftovers one by one to the segment with
         // the most expected bases per CTA (greedy = optimal for the slowest segment, which is what the kernel waits for)
-        const bool enough = (uint32_t)nl <= a.n_count_ctas;
-        const uint32_t spare = enough ? a.n_count_ctas - (uint32_t)nl : 0u;
+        uint32_t n_ctas = a.n_count_ctas;
+        if (a.reads_per_cta) {
+            const uint64_t want = (n_reads + a.reads_per_cta - 1) / a.reads_per_cta;
+            if (want < n_ctas) n_ctas = want > (uint64_t)nl ? (uint32_t)want : (uint32_t)nl;
+            if (n_ctas > a.n_count_ctas) n_ctas = a.n_count_ctas;
+        }
+        const bool enough = (uint32_t)nl <= n_ctas;
+        const uint32_t spare = enough ? n_ctas - (uint32_t)nl : 0u;
         uint32_t mine = (l < nl && enough) ? 1u : 0u;
         if (l < nl && enough && s_wsum > 0.0) mine += (uint32_t)((double)spare * (f / s_wsum));
         s_ncta[l] = mine;
@@ -422,7 +429,7 @@ plan_kernel(const uint8_t* __restrict__ text, uint64_t* __restrict__ starts, uin
         if (l == 0 && enough && s_wsum > 0.0) {
             uint32_t given = 0;
             for (int s = 0; s < nl; ++s) given += s_ncta[s];
-            for (uint32_t left = a.n_count_ctas > given ? a.n_count_ctas - given : 0u; left > 0; --left) {
+            for (uint32_t left = n_ctas > given ? n_ctas - given : 0u; left > 0; --left) {
                 int best = 0;
                 float load = -1.f;
                 for (int s = 0; s < nl; ++s) {
