@@ -94,7 +94,8 @@ int vk_set_mapping(vk_ctx* ctx, int slot, int k, int side, const int32_t* lut_ho
 
 /*
  * Input: the uncompressed bytes of <int>/clean_reads/<sample>.fq.gz (image.py:971).
- * vk_upload copies host bytes into a context-owned device buffer (pinned staging, async chunks);
+ * vk_upload copies host bytes into a context-owned device buffer (one stream-ordered cudaMemcpyAsync; at PCIe speed
+ * when the host buffer is page-locked);
  * vk_attach uses caller-owned device memory (16-byte aligned; readable up to the next 16-byte boundary).
  */
 int vk_upload(vk_ctx* ctx, const void* host_bytes, uint64_t n_bytes);
@@ -173,13 +174,20 @@ int vk_base_content(vk_ctx* ctx, int32_t pos_begin, int32_t pos_end, uint64_t* c
  * [5] render, [6] read-back (D2H), [7] total. */
 int vk_last_timings(vk_ctx* ctx, float* ms8);
 
-/* on (default): CUDA events are recorded between the kernel groups so that vk_last_timings can split a step.  An event
- * between two kernels is a full stream dependency and defeats programmatic dependent launch across it; off keeps only
- * the first and last event ([7] total; the other entries read 0). */
+/* on: CUDA events are recorded between the kernel groups so that vk_last_timings can split a step.  An event between two
+ * kernels is a full stream dependency: it defeats programmatic dependent launch across it and keeps the step from being
+ * submitted as one CUDA graph.  off (default) keeps only the first, the post-upload and the last event ([0] upload and
+ * [7] total; the other entries read 0). */
 int vk_set_fine_timing(vk_ctx* ctx, int on);
 
 /* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
 uint64_t vk_launch_count(vk_ctx* ctx);
+
+/* vk_reads_to_images submits a step as ONE CUDA graph (captured once per k / pixel table / level count, replayed for every
+ * sample; what differs between samples travels in a device-resident argument block).  *launches: steps submitted as a
+ * graph so far; *captures: graphs captured; *state: 1 graphs in use, 0 switched off (VK_GRAPH=0), -1 a capture failed and
+ * the context fell back to plain launches.  Any pointer may be NULL. */
+int vk_graph_stats(vk_ctx* ctx, uint64_t* launches, uint64_t* captures, int32_t* state);
 
 /* How often a step had to be repeated because a ladder segment received more reads than the region sized from its
  * expected share (8 sigma + slack): always 0 in practice; tests force it with VK_TEST_TIGHT_BUCKETS=1. */
@@ -189,6 +197,13 @@ uint64_t vk_bucket_retries(vk_ctx* ctx);
  * Fixed read length L: record r occupies bytes [r*(2L+17), (r+1)*(2L+17)); returns bytes written in *n_out. */
 int vk_synth_fastq(vk_ctx* ctx, void* dev_bytes, uint64_t capacity, uint64_t n_bases, int read_len, uint64_t seed,
                    uint64_t first_read, uint64_t* n_out);
+
+/* Same generator with VARIABLE read lengths (the shape of fastp-cleaned, merged
+ * reads): lengths uniform min_len..max_len, short_per_10000 / 10000 of the reads shorter than k (0..k-1 bases, empty
+ * reads included).  dev_bytes = NULL only reports the size.  *n_out = bytes, *n_bases_out = bases (nullable). */
+int vk_synth_fastq_variable(vk_ctx* ctx, void* dev_bytes, uint64_t capacity, uint64_t n_reads, uint64_t seed,
+                            uint64_t first_read, int min_len, int max_len, int short_per_10000, int k, uint64_t* n_out,
+                            uint64_t* n_bases_out);
 
 #ifdef __cplusplus
 }

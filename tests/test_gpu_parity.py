@@ -284,11 +284,21 @@ def test_full_size_properties_config2(engine):
     assert (res.pixels.max(axis=(1, 2)) == 255).all()
     for lvl in (0, 4, 8):
         assert (res.pixels[lvl] == oimg.image_exact(canon[lvl], table.lut)).all()
-    # a 1 Mbp prefix of the same reads, counted by the CPU oracle, must match the GPU on that prefix
-    nb = synth.fixed_total_bytes(1_000_050, L)
-    head = dev[:nb].cpu().numpy().tobytes()
-    r2 = engine.reads_to_images(head, Params(k=k, min_bp=0, max_bp=None, is_query=True), table, want_canon=True)
-    assert (r2.canon[0] == dsk.canonical_counts(head, k, threads=0)).all()
+    # the WHOLE sample against the CPU oracle: every level, every k-mer, every pixel, bit-exact
+    host = dev[:total].cpu().numpy()
+    expect = oracle_levels_fast(host, k, 1, res.levels, n_bases)
+    assert (canon == expect).all()
+    for lvl in range(len(res.levels)):
+        assert (res.pixels[lvl] == oimg.image_exact(expect[lvl], table.lut)).all()
+
+
+def oracle_levels_fast(buf, k, seed, levels, nsites, read_index_base=0):
+    """canon_full per level by the CPU oracle's one-pass multi-level counter (C/OpenMP, all host threads): the same
+    rule as helpers.oracle_levels, fast enough for the BASELINE-size samples."""
+    thr = [0 if bp >= nsites else dsk.threshold(bp, nsites) for bp in levels]
+    take_all = [1 if bp >= nsites else 0 for bp in levels]
+    _, canon = dsk.count_levels(buf, k, seed, thr, take_all, read_index_base=read_index_base, threads=0)
+    return canon
 
 
 def test_sharded_driver_with_real_engine_nccl(engine):
@@ -339,6 +349,42 @@ def test_bucket_overflow_retry_is_exact(monkeypatch):
         assert (canon2 == expect).all() and eng.bucket_retries() >= 2
     finally:
         eng.close()
+
+
+def test_read_table_overflow_retry_tiny_records():
+    """The read table is sized from the byte count (one record per 24 bytes + slack).  Records shorter than that --
+    empty headers, reads of 5..9 bases, blank lines -- overflow it: the device must not touch the tables on that
+    attempt (plan_kernel hands out no CTAs and no regions, the scatter returns) and the repeated step, with tables of the
+    exact size, must be bit-exact.  A fresh context, so that the first attempt really runs with the small tables."""
+    from varkoder_b200.engine import Engine
+    rng = np.random.default_rng(4242)
+    reads = ["".join(rng.choice(list("ACGT"), int(rng.integers(5, 10)))) for _ in range(6000)]
+    buf = b"".join(b"@\n" + r.encode() + b"\n+\n" + b"I" * len(r) + b"\n" for r in reads)
+    assert len(buf) / len(reads) < 21
+    table = get_kmer_mapping(5, "cgr")
+    for fused in (True, False):
+        eng = Engine(0)
+        try:
+            params = Params(k=5, min_bp=2_000, max_bp=None, seed=3)
+            if fused:
+                res = eng.reads_to_images(buf, params, table, want_canon=True)
+                canon, pixels = res.canon, res.pixels
+            else:
+                eng.upload(buf)
+                st = eng.parse()
+                assert st["n_reads"] == len(reads)
+                res = eng.count(params)
+                canon, pixels = eng.render(table, 5, len(res.levels))
+            p = dsk.parse_fastq(buf)
+            assert res.n_reads == len(reads) and res.nsites == p["nsites_ref"] and len(res.levels) >= 3
+            expect = oracle_levels(buf, 5, 3, res.levels, res.nsites)
+            assert (canon == expect).all()
+            assert (pixels == oracle_images(expect, table.lut)).all()
+            # and the context keeps working afterwards (no sticky CUDA error)
+            r2 = eng.reads_to_images(EDGE_FASTQ["plain"], Params(k=5, min_bp=0, max_bp=None, is_query=True), table, want_canon=True)
+            assert (r2.canon[0] == dsk.canonical_counts(EDGE_FASTQ["plain"], 5)).all()
+        finally:
+            eng.close()
 
 
 @pytest.mark.parametrize("k", [7, 8, 9])
@@ -516,11 +562,12 @@ def test_full_size_properties_config3(engine):
     torch.cuda.synchronize()
     canon2, _ = engine.render(None, k, len(res.levels), both.data_ptr())
     assert (canon2 == canon).all()
-    # a 1 Mbp prefix, counted by the CPU oracle
-    nb = synth.fixed_total_bytes(1_000_050, L)
-    head = dev[:nb].cpu().numpy().tobytes()
-    r2 = engine.reads_to_images(head, Params(k=k, min_bp=0, max_bp=None, is_query=True), table, want_canon=True)
-    assert (r2.canon[0] == dsk.canonical_counts(head, k, threads=0)).all()
+    # the WHOLE sample against the CPU oracle: all eleven levels, every 9-mer and every pixel, bit-exact
+    host = dev[:total].cpu().numpy()
+    expect = oracle_levels_fast(host, k, 3, res.levels, n_bases)
+    assert (canon == expect).all()
+    for lvl in range(len(res.levels)):
+        assert (res.pixels[lvl] == oimg.image_exact(expect[lvl], table.lut)).all()
 
 
 def test_text_beyond_4_gib(engine):
@@ -738,3 +785,99 @@ def test_base_content_argument_and_state_errors():
         assert e.base_content(0, 12)[:, 4].tolist() == [1] * 12
     finally:
         e.close()
+
+
+# ------------------------------------------------------------------- step variants: graph / plain, packed / text
+@pytest.mark.parametrize("packed,graph", [("1", "1"), ("1", "0"), ("0", "1"), ("0", "0")])
+def test_step_variants_bit_exact(monkeypatch, packed, graph):
+    """The fused call in its four forms -- submitted as one CUDA graph or kernel by kernel, count kernels fed by the 2-bit
+    pack of the framing pass or classifying the text themselves -- on samples of very different sizes through ONE
+    context (a graph captured for the first sample must serve the others: everything that differs travels in the
+    device-resident argument block), for every k: bit-exact against the oracle each time."""
+    from varkoder_b200.engine import Engine
+    monkeypatch.setenv("VK_PACKED", packed)
+    monkeypatch.setenv("VK_GRAPH", graph)
+    eng = Engine(0)
+    try:
+        rng = np.random.default_rng(17)
+        bufs = [synth.variable(7000, seed=91).tobytes(), synth.fixed(300_000, 150, seed=92).tobytes(),
+                fastq(rand_reads(rng, 300, 0, 90, p_n=0.02) + ["acgtn" * 20, "ACGT" * 400, "G" * 700, ""]),
+                synth.variable(60_000, seed=93).tobytes(), EDGE_FASTQ["unterminated_seq_line"], b""]
+        for k, mapping in ((7, "cgr"), (5, "varKode"), (8, "cgr"), (9, "varKode"), (6, "cgr")):
+            table = get_kmer_mapping(k, mapping)
+            for i, buf in enumerate(bufs):
+                params = Params(k=k, min_bp=3_000, max_bp=None, seed=40 + i)
+                p = dsk.parse_fastq(buf)
+                if p["nsites_ref"] <= 3_000:
+                    params = Params(k=k, min_bp=0, max_bp=None, seed=40 + i, is_query=True)
+                res = eng.reads_to_images(buf, params, table, want_canon=True, max_levels=12)
+                assert res.nsites == p["nsites_ref"] and res.n_reads == p["n_reads"]
+                expect = oracle_levels(buf, k, 40 + i, res.levels, res.nsites)
+                assert (res.canon == expect).all(), (k, i)
+                if len(res.levels):
+                    assert (res.pixels == oracle_images(expect, table.lut)).all(), (k, i)
+        launches, captures, state = eng.graph_stats()
+        if graph == "1":
+            # five (k, table) pairs; a graph is captured again only when a buffer grows
+            assert state == 1 and launches >= 25 and 5 <= captures <= 16
+        else:
+            assert state == 0 and launches == 0 and captures == 0
+    finally:
+        eng.close()
+
+
+def test_device_variable_generator_equals_host_generator(engine):
+    import torch
+    n_reads = 5000
+    host = synth.variable(n_reads, seed=314, k=7, first_read=77)
+    nb, bases = engine.synth_fastq_variable(None, 0, n_reads, seed=314, first_read=77)
+    assert nb == len(host)
+    dev = torch.empty(nb + 64, dtype=torch.uint8, device="cuda")
+    assert engine.synth_fastq_variable(dev.data_ptr(), dev.numel(), n_reads, seed=314, first_read=77) == (nb, bases)
+    assert (dev[:nb].cpu().numpy() == host).all()
+    assert dsk.parse_fastq(host)["nsites_ref"] == bases
+
+
+def test_full_shape_config4_batch_against_oracle(engine, tmp_path):
+    """BASELINE configs[3] at its full shape: 96 samples of 10-50 Mbp with variable read lengths (60..280, 1 % shorter
+    than k, empty reads), k = 7, varKode, -m 500K, every ladder from the sample's own nsites -- generated on the device,
+    pushed through the batch entry point (device-resident samples, several in flight) and compared with the CPU oracle:
+    every level of every sample, every pixel, and the PNG files of one sample."""
+    import torch
+    from PIL import Image
+    from varkoder_b200 import stages
+    from varkoder_b200.ladder import image_name, ladder
+    table = get_kmer_mapping(7, "varKode")
+    rng = np.random.default_rng(20260118 + 4000)
+    sizes = [int(x) for x in rng.integers(10_000_000, 50_000_001, 96)]
+    samples, keep = [], []
+    first = 0
+    for i, nb_target in enumerate(sizes):
+        n_reads = nb_target * 100 // 16833            # mean length 168.33 (99 % uniform 60..280, 1 % below k)
+        nbytes, bases = engine.synth_fastq_variable(None, 0, n_reads, seed=4000 + i, first_read=first)
+        d = torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda")
+        engine.synth_fastq_variable(d.data_ptr(), d.numel(), n_reads, seed=4000 + i, first_read=first)
+        first += n_reads
+        keep.append((d, nbytes, bases))
+        samples.append(dict(sample=f"B{i:02d}", device=(d.data_ptr(), nbytes), labels=["x"], base_sd=0.0))
+    out = tmp_path / "img"
+    seeds = [7000 + i for i in range(96)]
+    got = {}
+    stats = stages.images_for_samples(samples, out, table, k=7, mapping_code="varKode", min_bp=500_000, max_bp=None,
+                                      seeds=seeds, gpu_workers=4, write_png_of=lambda s: s["sample"] == "B05",
+                                      on_result=lambda s, res: got.__setitem__(s["sample"], res))
+    assert list(stats) == [s["sample"] for s in samples]
+    for i, s in enumerate(samples):
+        d, nbytes, bases = keep[i]
+        host = d[:nbytes].cpu().numpy()
+        res = got[s["sample"]]
+        assert res.nsites == bases and abs(bases - sizes[i]) < 0.02 * sizes[i]
+        levels = ladder(bases, 500_000, None)
+        assert res.levels == levels and 5 <= len(levels) <= 8
+        assert stats[s["sample"]]["splitting_bp_per_file"] == ",".join(str(x) for x in levels)
+        expect = oracle_levels_fast(host, 7, seeds[i], levels, bases)
+        assert (res.canon == expect).all(), s["sample"]
+        assert (res.pixels == oracle_images(expect, table.lut)).all(), s["sample"]
+        if s["sample"] == "B05":
+            for lvl, bp in enumerate(levels):
+                assert (np.asarray(Image.open(out / image_name("B05", bp, "varKode", 7))) == res.pixels[lvl]).all()

@@ -19,6 +19,7 @@ SYMBOLS = [
     "vk_attach", "vk_parse", "vk_count", "vk_render", "vk_render_counts", "vk_reads_to_images", "vk_device_pixels", "vk_remap",
     "vk_base_content",
     "vk_last_timings", "vk_set_fine_timing", "vk_launch_count", "vk_bucket_retries", "vk_synth_fastq",
+    "vk_synth_fastq_variable", "vk_graph_stats",
 ]
 
 
@@ -81,6 +82,9 @@ def load():
     L.vk_bucket_retries.restype = C.c_uint64
     L.vk_synth_fastq.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64,
                                  C.POINTER(C.c_uint64)]
+    L.vk_synth_fastq_variable.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.vk_graph_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("vk_last_error", "vk_launch_count", "vk_bucket_retries"):

@@ -21,17 +21,25 @@ constexpr int kBucketItems = 4;      // reads per thread and iteration of the sc
 // Regions were sized from the expected segment shares by plan_kernel (vk_parse.cuh); a read that does not fit
 // raises plan->bucket_overflow and the host repeats the step with regions that hold every read.
 __global__ void __launch_bounds__(kBucketThreads)
-bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __restrict__ ends, int k, uint64_t seed,
-                      uint64_t read_index_base, uint64_t text_base, uint64_t* __restrict__ sorted,
-                      Plan* __restrict__ plan)
+bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __restrict__ ends, const StepArgs* __restrict__ sa,
+                      uint64_t text_base, uint64_t* __restrict__ sorted, Plan* __restrict__ plan)
 {
     pdl_wait();
+    const int k = sa->pa.p.k;
+    const uint64_t seed = sa->pa.p.seed, read_index_base = sa->pa.p.read_index_base;
     constexpr uint32_t FULL = 0xffffffffu;
     __shared__ uint32_t s_cnt[kMaxLevels], s_all[kMaxLevels];
     __shared__ unsigned long long s_len[kMaxLevels];
     __shared__ unsigned long long s_base[kMaxLevels];
     __shared__ uint64_t s_thr[kMaxLevels], s_begin[kMaxLevels], s_cap[kMaxLevels];
     __shared__ uint32_t s_long;
+    // the tables do not fit (plan_kernel): the step is repeated with larger ones, nothing here may be dereferenced.
+    // (bucket_overflow can also be raised by this kernel itself, below; a CTA that starts late and sees it only skips
+    // work whose result is thrown away.)
+    __shared__ uint32_t s_abort;
+    if (threadIdx.x == 0) s_abort = plan->table_overflow | plan->bucket_overflow;      // one reader: the branch is block-uniform
+    __syncthreads();
+    if (s_abort) return;
     const int nl = plan->n_levels;
     const uint64_t n_reads = plan->n_reads;
     const uint64_t per_iter = (uint64_t)gridDim.x * blockDim.x;

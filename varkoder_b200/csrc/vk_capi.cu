@@ -38,15 +38,16 @@ template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;      // elements
-    void ensure(size_t n)
+    bool ensure(size_t n)      // true: the buffer moved (captured graphs that hold its address are stale)
     {
-        if (n <= cap) return;
+        if (n <= cap) return false;
         if (p) CU(cudaFree(p));
         p = nullptr;
         cap = 0;
         size_t want = n + n / 8 + 256;
         CU(cudaMalloc(&p, want * sizeof(T)));
         cap = want;
+        return true;
     }
     void release()
     {
@@ -108,6 +109,29 @@ struct vk_ctx {
     uint64_t bucket_retries = 0;
     int counted_k = 0;
 
+    // per-step arguments of the kernels (vk::StepArgs): written by the host into pinned memory, copied to the device by
+    // the first node of every step
+    vk::StepArgs* args_d = nullptr;
+    vk::StepArgs* args_h = nullptr;
+    bool use_packed = true;         // VK_PACKED=0: the count kernels classify the text themselves (round-1 path) instead of
+                                    // reading the 2-bit codes + validity bits the framing pass writes
+    DevBuf<uint4> codes;            // 2-bit codes of every text byte, 16 B per 64 text bytes (parse_mask_kernel<true>)
+    DevBuf<uint2> valid;            // validity bits, 8 B per 64 text bytes
+    // one step = one CUDA graph: captured once per (k, pixel table, levels, layout) and replayed for every sample
+    bool use_graph = true;          // VK_GRAPH=0: launch the kernels of a step one by one
+    struct StepGraph {
+        int k, slot, side, max_levels, exact, packed;
+        uint64_t generation;
+        cudaGraphExec_t exec;
+        uint32_t kernels;
+    };
+    std::vector<StepGraph> graphs;
+    uint64_t generation = 0;        // bumped whenever a device buffer moves
+    uint64_t graph_launches = 0, graph_captures = 0;
+    int graph_failed = 0;           // capture or instantiation failed once: stay on plain launches
+    bool capturing = false;
+    uint32_t captured_kernels = 0;
+
     DevBuf<uint64_t> tile_status, masks, starts, ends, sorted;      // tile_status = exclusive newline prefix per tile
     DevBuf<uint32_t> tile_count, warp_count;
     DevBuf<uint32_t> slabs;
@@ -115,12 +139,15 @@ struct vk_ctx {
     DevBuf<uint8_t> remap_in, remap_out, remap_mult;
     DevBuf<int32_t> remap_src;
     DevBuf<unsigned long long> content;
+    DevBuf<uint64_t> synth_off;     // vk_synth_fastq_variable: record offsets
     Mapping maps[4];
 
-    bool fine_timing = true;        // vk_set_fine_timing: events between the kernel groups (they serialise the stream)
+    bool fine_timing = false;       // vk_set_fine_timing: events between the kernel groups (they serialise the stream and keep
+                                    // the step from being submitted as one graph); off: first / upload / last event only
     void mark(int e)
     {
-        if (!fine_timing && e != EV_START && e != EV_DONE) { ev_valid[e] = false; return; }
+        if (!fine_timing && e != EV_START && e != EV_UPLOAD && e != EV_DONE) { ev_valid[e] = false; return; }
+        if (capturing) return;
         CU(cudaEventRecord(ev[e], stream));
         ev_valid[e] = true;
     }
@@ -147,50 +174,77 @@ void launch(vk_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     cfg.attrs = attr;
     cfg.numAttrs = c->use_pdl ? 1 : 0;
     CU(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+    if (c->capturing) ++c->captured_kernels; else ++c->launches;
 }
 
 
-// ---- K1: framing -------------------------------------------------------------------------------------
-void enqueue_parse(vk_ctx* c, const vk_params* params, bool rescan = true)
+// ---- per-step argument block ----------------------------------------------------------------------------
+// Fills the pinned StepArgs and enqueues its copy to the device (the first node of a step).  `n_bytes`, the text pointer
+// and the sample's options are the ONLY things that vary between steps of one context.
+void enqueue_args(vk_ctx* c, const vk_params* params)
 {
     using namespace vk;
-    const uint64_t n = c->n_bytes;
-    const uint32_t n_tiles = (uint32_t)((n + kParseTileBytes - 1) / kParseTileBytes);
-    c->tile_status.ensure(n_tiles + 1);
-    const size_t cap = c->starts.cap;
-    if (rescan) CU(cudaMemsetAsync(c->plan_d, 0, offsetof(Plan, n_lines), c->stream));      // parse fields: counters, sums, ticket
-    if (n_tiles && rescan) {
-        c->masks.ensure((size_t)n_tiles * kParseThreads);
-        c->tile_count.ensure(n_tiles);
-        c->warp_count.ensure((size_t)n_tiles * kParseWarps);
-        CU(cudaMemsetAsync(c->tile_count.p, 0, sizeof(uint32_t) * n_tiles, c->stream));
-        const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)c->n_sms * 16);
-        launch(c, parse_mask_kernel, dim3(grid), dim3(kParseThreads), 0, reinterpret_cast<const uint4*>(c->text), n, n_tiles,
-                                                                 c->masks.p, c->tile_count.p, c->warp_count.p);
-        CU(cudaGetLastError());
-        launch(c, parse_scan_kernel, dim3(1), dim3(1024), 0, c->tile_count.p, n_tiles, c->tile_status.p, c->plan_d);
-        CU(cudaGetLastError());
-        const int egrid = (int)std::min<uint64_t>(((uint64_t)n_tiles * kEmitUnitsPerTile + 7) / 8, (uint64_t)c->n_sms * 32);
-        launch(c, parse_emit_kernel, dim3(egrid), dim3(256), 0, c->masks.p, c->tile_status.p, c->warp_count.p, n_tiles, 0,
-                                                        c->starts.p, c->ends.p, cap, c->plan_d);
-        CU(cudaGetLastError());
-        c->launches += 3;
-    }
-    PlanArgs a;
+    StepArgs& a = *c->args_h;
     memset(&a, 0, sizeof(a));
-    if (params) a.p = *params;
-    a.n_bytes = n;
-    a.cap_reads = cap;
-    a.cap_sorted = c->sorted.cap;
-    a.n_count_ctas = (uint32_t)c->count_grid();
-    a.reads_per_cta = (uint32_t)c->reads_per_cta;
+    a.text = c->text;
+    a.n_bytes = c->n_bytes;
+    a.n_tiles = (uint32_t)((c->n_bytes + kParseTileBytes - 1) / kParseTileBytes);
+    if (params) a.pa.p = *params;
+    a.pa.n_bytes = c->n_bytes;
+    a.pa.cap_reads = c->starts.cap;
+    a.pa.cap_sorted = c->sorted.cap;
+    a.pa.n_count_ctas = (uint32_t)c->count_grid();
+    a.pa.reads_per_cta = (uint32_t)c->reads_per_cta;
     if (params && params->k == 9 && c->use_count16)                             // k = 9 counts in CTA pairs (count9h_kernel)
-        a.n_count_ctas = (uint32_t)(c->n_sms * c->count_ctas_per_sm / 2 + c->count_extra9);
-    a.exact_layout = c->exact_layout ? 1u : 0u;
-    a.test_tight = c->test_tight ? 1u : 0u;
-    launch(c, plan_kernel, dim3(1), dim3(64), 0, c->text, c->starts.p, c->ends.p, a, c->plan_d);
+        a.pa.n_count_ctas = (uint32_t)(c->n_sms * c->count_ctas_per_sm / 2 + c->count_extra9);
+    a.pa.exact_layout = c->exact_layout ? 1u : 0u;
+    a.pa.test_tight = c->test_tight ? 1u : 0u;
+}
+void enqueue_args_copy(vk_ctx* c)
+{
+    CU(cudaMemcpyAsync(c->args_d, c->args_h, sizeof(vk::StepArgs), cudaMemcpyHostToDevice, c->stream));
+}
+
+// buffers of the framing pass for a text of n bytes (never allocates inside a graph capture: called before it)
+void ensure_parse_buffers(vk_ctx* c, uint64_t n)
+{
+    using namespace vk;
+    const uint32_t n_tiles = (uint32_t)((n + kParseTileBytes - 1) / kParseTileBytes);
+    c->generation += c->tile_status.ensure((size_t)n_tiles + 1);
+    c->generation += c->masks.ensure((size_t)n_tiles * kParseThreads + 1);
+    c->generation += c->tile_count.ensure((size_t)n_tiles + 1);
+    c->generation += c->warp_count.ensure((size_t)n_tiles * kParseWarps + 1);
+    if (c->use_packed) {
+        c->generation += c->codes.ensure((size_t)n_tiles * kParseThreads + 1);
+        c->generation += c->valid.ensure((size_t)n_tiles * kParseThreads + 1);
+    }
+}
+
+// ---- K1: framing -------------------------------------------------------------------------------------
+// Grids do not depend on the sample (grid-stride loops over sa->n_tiles), so the same launches serve every step.
+void enqueue_parse(vk_ctx* c, bool rescan = true)
+{
+    using namespace vk;
+    if (rescan) {
+        CU(cudaMemsetAsync(c->plan_d, 0, offsetof(Plan, n_lines), c->stream));      // parse fields: counters, sums, ticket
+        CU(cudaMemsetAsync(c->tile_count.p, 0, sizeof(uint32_t) * c->tile_count.cap, c->stream));
+        const int grid = c->n_sms * 16;
+        if (c->use_packed)
+            launch(c, parse_mask_kernel<true>, dim3(grid), dim3(kParseThreads), 0, (const StepArgs*)c->args_d, c->masks.p,
+                   c->tile_count.p, c->warp_count.p, c->codes.p, c->valid.p);
+        else
+            launch(c, parse_mask_kernel<false>, dim3(grid), dim3(kParseThreads), 0, (const StepArgs*)c->args_d, c->masks.p,
+                   c->tile_count.p, c->warp_count.p, (uint4*)nullptr, (uint2*)nullptr);
+        CU(cudaGetLastError());
+        launch(c, parse_scan_kernel, dim3(1), dim3(1024), 0, c->tile_count.p, (const StepArgs*)c->args_d, c->tile_status.p, c->plan_d);
+        CU(cudaGetLastError());
+        const int egrid = c->n_sms * 32;
+        launch(c, parse_emit_kernel, dim3(egrid), dim3(256), 0, c->masks.p, c->tile_status.p, c->warp_count.p,
+               (const StepArgs*)c->args_d, 0, c->starts.p, c->ends.p, c->plan_d);
+        CU(cudaGetLastError());
+    }
+    launch(c, plan_kernel, dim3(1), dim3(64), 0, (const StepArgs*)c->args_d, c->starts.p, c->ends.p, c->plan_d);
     CU(cudaGetLastError());
-    ++c->launches;
 }
 
 // entries the segment-sorted read table needs for n reads in n_levels segments (plan_kernel's layout rule)
@@ -205,30 +259,70 @@ uint64_t sorted_need(uint64_t n_reads, uint64_t n_levels, bool exact)
 
 void ensure_tables_for(vk_ctx* c, uint64_t n_reads_hint)
 {
-    c->starts.ensure(n_reads_hint);
-    c->ends.ensure(n_reads_hint);
-    if (!c->exact_layout) c->sorted.ensure(sorted_need(n_reads_hint, vk::kMaxLevels, false));
+    c->generation += c->starts.ensure(n_reads_hint);
+    c->generation += c->ends.ensure(n_reads_hint);
+    if (!c->exact_layout) c->generation += c->sorted.ensure(sorted_need(n_reads_hint, vk::kMaxLevels, false));
+}
+
+void ensure_count_buffers(vk_ctx* c, int k)
+{
+    const uint32_t nk = 1u << (2 * k);
+    if (k <= 7 || (k == 8 && c->use_count16)) c->generation += c->slabs.ensure((size_t)c->count_grid() * nk);
+    if (k == 9 && c->use_count16)
+        c->generation += c->slabs.ensure((size_t)2 * (c->n_sms * c->count_ctas_per_sm / 2 + c->count_extra9) * 65536u);
+}
+
+// dynamic shared memory of every count kernel variant, set once per context (not inside a capture)
+template <int K>
+void prepare_count_kernels()
+{
+    using namespace vk;
+    constexpr uint32_t NK = 1u << (2 * K);
+    if constexpr (K <= 7) {
+        const int smem = (int)(0x10000 + (size_t)(NK + 32) * sizeof(uint32_t));
+        CU(cudaFuncSetAttribute(count_kernel<K, kSmem32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(count_kernel<K, kSmem32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    if constexpr (K == 7 || K == 8) {
+        const int smem = (int)((size_t)(32768 + (K == 7 ? 16384 : 0)) * sizeof(uint32_t));
+        CU(cudaFuncSetAttribute(count16_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(count16_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    if constexpr (K == 9) {
+        const int smem = (int)((size_t)32768 * sizeof(uint32_t) + 2048);
+        CU(cudaFuncSetAttribute(count9h_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(count9h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+}
+void prepare_kernels()
+{
+    prepare_count_kernels<5>();
+    prepare_count_kernels<6>();
+    prepare_count_kernels<7>();
+    prepare_count_kernels<8>();
+    prepare_count_kernels<9>();
+    // the cluster image kernel: up to 8 slices of 2048 keys
+    CU(cudaFuncSetAttribute(vk::image_kernel_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)((size_t)vk::kImgCluster * 2048 * sizeof(unsigned long long))));
 }
 
 // ---- K1b + K2 + K3 -----------------------------------------------------------------------------------
-template <int K>
-void launch_count(vk_ctx* c, unsigned long long* seg_hist, int breaklen)
+template <int K, bool PACKED>
+void launch_count(vk_ctx* c, unsigned long long* seg_hist)
 {
     using namespace vk;
     constexpr uint32_t NK = 1u << (2 * K);
     const dim3 grid(c->count_grid()), block(c->count_threads);
     const uint64_t total = (uint64_t)kMaxLevels * NK;
+    const StepArgs* sa = c->args_d;
+    const PackedSrc pk = {reinterpret_cast<const uint2*>(c->codes.p), reinterpret_cast<const uint32_t*>(c->valid.p)};
     if constexpr (K == 7 || K == 8) {
         if (K == 8 ? c->use_count16 : c->use_pairs) {
             // 16-bit bins in shared memory: k = 8 directly, k = 7 through pairs (vk_count.cuh)
             const size_t smem = (size_t)(32768 + (K == 7 ? 16384 : 0)) * sizeof(uint32_t);
-            CU(cudaFuncSetAttribute(count16_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            launch(c, count16_kernel<K>, grid, block, smem, reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d,
-                   c->slabs.p, breaklen);
-            ++c->launches;
+            launch(c, (count16_kernel<K, PACKED>), grid, block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p);
             c->mark(EV_COUNT);
             launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist);
-            ++c->launches;
             return;
         }
     }
@@ -237,59 +331,44 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist, int breaklen)
             // canonical classes in two halves, one per CTA of a pair (vk_count.cuh)
             const unsigned pairs = (unsigned)(c->n_sms * c->count_ctas_per_sm / 2 + c->count_extra9);
             const size_t smem = (size_t)32768 * sizeof(uint32_t) + 2048;      // + padding to a 2 KiB shared address
-            CU(cudaFuncSetAttribute(count9h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            launch(c, count9h_kernel, dim3(2 * pairs), block, smem, reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d,
-                   c->slabs.p, breaklen);
-            ++c->launches;
+            launch(c, (count9h_kernel<PACKED>), dim3(2 * pairs), block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p);
             c->mark(EV_COUNT);
             launch(c, reduce_slabs9h_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, seg_hist);
-            ++c->launches;
             return;
         }
     }
     if constexpr (K <= 7) {
         // the histogram sits at a 64 KiB-aligned shared address (vk_count.cuh): up to 64 KiB of padding in front
         const size_t smem = 0x10000 + (size_t)(NK + 32) * sizeof(uint32_t);
-        CU(cudaFuncSetAttribute(count_kernel<K, kSmem32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        launch(c, (count_kernel<K, kSmem32>), grid, block, smem, reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d,
-               c->slabs.p, seg_hist, breaklen);
-        ++c->launches;
+        launch(c, (count_kernel<K, kSmem32, PACKED>), grid, block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p, seg_hist);
         c->mark(EV_COUNT);
         launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist);
-        ++c->launches;
     } else {
         launch(c, zero_u64_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, seg_hist, total);
-        ++c->launches;
         c->mark(EV_BUCKET);
-        launch(c, (count_kernel<K, kGlobal>), grid, block, 0, reinterpret_cast<const uint4*>(c->text), c->sorted.p, c->plan_d,
-               c->slabs.p, seg_hist, breaklen);
-        ++c->launches;
+        launch(c, (count_kernel<K, kGlobal, PACKED>), grid, block, 0, sa, pk, c->sorted.p, c->plan_d, c->slabs.p, seg_hist);
         c->mark(EV_COUNT);
     }
 }
 
-void enqueue_count(vk_ctx* c, const vk_params* p, unsigned long long* seg_hist, uint64_t n_reads_bound)
+void enqueue_count(vk_ctx* c, int k, unsigned long long* seg_hist)
 {
     using namespace vk;
-    const int k = p->k;
-    const uint32_t nk = 1u << (2 * k);
-    if (k <= 7 || (k == 8 && c->use_count16)) c->slabs.ensure((size_t)c->count_grid() * nk);
-    if (k == 9 && c->use_count16) c->slabs.ensure((size_t)2 * (c->n_sms * c->count_ctas_per_sm / 2 + c->count_extra9) * 65536u);
-    const int bgrid = (int)std::min<uint64_t>((n_reads_bound + kBucketThreads * kBucketItems - 1) / (kBucketThreads * kBucketItems) + 1,
-                                             (uint64_t)c->n_sms * 8);
-    launch(c, bucket_scatter_kernel, dim3(bgrid), dim3(kBucketThreads), 0, c->starts.p, c->ends.p, k, p->seed, p->read_index_base, 0,
-                                                                  c->sorted.p, c->plan_d);
+    const int bgrid = c->n_sms * 8;
+    launch(c, bucket_scatter_kernel, dim3(bgrid), dim3(kBucketThreads), 0, c->starts.p, c->ends.p, (const StepArgs*)c->args_d, 0,
+           c->sorted.p, c->plan_d);
     CU(cudaGetLastError());
-    ++c->launches;
     c->mark(EV_BUCKET);
+    const bool pk = c->use_packed;
     switch (k) {
-    case 5: launch_count<5>(c, seg_hist, p->breaklength); break;
-    case 6: launch_count<6>(c, seg_hist, p->breaklength); break;
-    case 7: launch_count<7>(c, seg_hist, p->breaklength); break;
-    case 8: launch_count<8>(c, seg_hist, p->breaklength); break;
-    case 9: launch_count<9>(c, seg_hist, p->breaklength); break;
+    case 5: pk ? launch_count<5, true>(c, seg_hist) : launch_count<5, false>(c, seg_hist); break;
+    case 6: pk ? launch_count<6, true>(c, seg_hist) : launch_count<6, false>(c, seg_hist); break;
+    case 7: pk ? launch_count<7, true>(c, seg_hist) : launch_count<7, false>(c, seg_hist); break;
+    case 8: pk ? launch_count<8, true>(c, seg_hist) : launch_count<8, false>(c, seg_hist); break;
+    case 9: pk ? launch_count<9, true>(c, seg_hist) : launch_count<9, false>(c, seg_hist); break;
     default: throw ApiError{VK_EINVAL, "k must be 5..9"};
     }
+    CU(cudaGetLastError());
 }
 
 // ---- K4 ----------------------------------------------------------------------------------------------
@@ -302,6 +381,18 @@ uint32_t next_pow2(uint32_t v)
 
 void ensure_outbox(vk_ctx* c, size_t n);
 
+void ensure_render_buffers(vk_ctx* c, const Mapping& m, int k, int levels)
+{
+    const uint32_t nk = 1u << (2 * k);
+    const uint32_t n_pix = (uint32_t)m.side * (uint32_t)m.side;
+    c->generation += c->canon.ensure((size_t)levels * nk);
+    ensure_outbox(c, (size_t)levels * n_pix);
+    if (n_pix > 16384) {
+        c->generation += c->vals.ensure((size_t)levels * next_pow2(n_pix));
+        c->generation += c->bins.ensure((size_t)levels * 256);
+    }
+}
+
 // levels: number of levels to render (grid size); canon must hold levels * 4^k
 void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsigned long long* seg_hist)
 {
@@ -309,14 +400,12 @@ void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsign
     const uint32_t nk = 1u << (2 * k);
     const uint32_t n_pix = (uint32_t)m.side * (uint32_t)m.side;
     const uint32_t n_pad = next_pow2(n_pix);
-    c->canon.ensure((size_t)levels * nk);
-    ensure_outbox(c, (size_t)levels * n_pix);
+    if (!c->capturing) ensure_render_buffers(c, m, k, levels);
     c->last_levels = levels;
     c->last_side = m.side;
     if (seg_hist) {
         launch(c, fold_kernel, dim3((nk + 255) / 256), dim3(256), 0, seg_hist, k, levels, c->canon.p);
         CU(cudaGetLastError());
-        ++c->launches;
     }
     c->mark(EV_FOLD);
     if (n_pix <= 16384) {
@@ -325,45 +414,35 @@ void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsign
         if (S < 64) S = 64;
         const size_t smem = (size_t)vk::kImgCluster * S * sizeof(unsigned long long);
         const unsigned threads = S / 2 > 1024 ? 1024 : S / 2;
-        CU(cudaFuncSetAttribute(image_kernel_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         launch(c, image_kernel_cluster, dim3(vk::kImgCluster, levels), dim3(threads), smem, c->canon.p, m.lut.p, nk, n_pix, S, c->pix_d());
         CU(cudaGetLastError());
-        ++c->launches;
     } else {
-        c->vals.ensure((size_t)levels * n_pad);
-        c->bins.ensure((size_t)levels * 256);
         dim3 g1((n_pad + 255) / 256, levels);
         launch(c, image_gather_kernel, dim3(g1), dim3(256), 0, c->canon.p, m.lut.p, nk, n_pix, n_pad, c->vals.p);
         CU(cudaGetLastError());
-        ++c->launches;
         dim3 gt(n_pad / kSortTile, levels);
         launch(c, bitonic_tile_kernel, dim3(gt), dim3(1024), 0, c->vals.p, n_pad, 2, kSortTile, kSortTile / 2);
         CU(cudaGetLastError());
-        ++c->launches;
         for (uint32_t size = 2 * kSortTile; size <= n_pad; size <<= 1) {
             uint32_t stride = size >> 1;
             for (; (stride >> 1) >= kSortTile; stride >>= 2) {           // two strides per pass while both are global
                 dim3 gs((n_pad / 4 + 255) / 256, levels);
                 launch(c, bitonic_global_step2, dim3(gs), dim3(256), 0, c->vals.p, n_pad, size, stride);
                 CU(cudaGetLastError());
-                ++c->launches;
             }
             if (stride >= kSortTile) {
                 dim3 gs((n_pad / 2 + 255) / 256, levels);
                 launch(c, bitonic_global_step, dim3(gs), dim3(256), 0, c->vals.p, n_pad, size, stride);
                 CU(cudaGetLastError());
-                ++c->launches;
             }
             launch(c, bitonic_tile_kernel, dim3(gt), dim3(1024), 0, c->vals.p, n_pad, size, size, kSortTile / 2);
             CU(cudaGetLastError());
-            ++c->launches;
         }
         launch(c, image_bins_kernel, dim3(levels), dim3(256), 0, c->vals.p, n_pix, n_pad, c->bins.p);
         CU(cudaGetLastError());
         dim3 gd((n_pix + 255) / 256, levels);
         launch(c, image_digitize_kernel, dim3(gd), dim3(256), 0, c->canon.p, m.lut.p, nk, n_pix, c->bins.p, c->pix_d());
         CU(cudaGetLastError());
-        c->launches += 2;
     }
     c->mark(EV_RENDER);
 }
@@ -420,6 +499,7 @@ void ensure_outbox(vk_ctx* c, size_t n)
     c->out_d = nd;
     c->out_h = nh;
     c->out_cap = want;
+    ++c->generation;
     c->plan_d = reinterpret_cast<vk::Plan*>(nd);
     c->plan_h = reinterpret_cast<vk::Plan*>(nh);
 }
@@ -478,9 +558,77 @@ void with_table_retry(vk_ctx* c, F&& body)
             // segment room for every read
             c->exact_layout = true;
             ++c->bucket_retries;
-            c->sorted.ensure(sorted_need(c->plan_h->n_reads, (uint64_t)std::max(c->plan_h->n_levels, 1), true));
+            c->generation += c->sorted.ensure(sorted_need(c->plan_h->n_reads, (uint64_t)std::max(c->plan_h->n_levels, 1), true));
         }
     }
+}
+
+void drop_graphs(vk_ctx* c)
+{
+    for (auto& g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
+}
+
+// The kernels of one whole step (arguments copy, framing, ladder, scatter, count, reduce, fold, images, read-back) in
+// stream order; the body of both the plain path and the graph capture.
+void enqueue_step(vk_ctx* c, const Mapping& m, int k, int max_levels_out)
+{
+    const size_t n_pix = (size_t)m.side * m.side;
+    enqueue_args_copy(c);
+    enqueue_parse(c);
+    c->mark(EV_PARSE);
+    enqueue_count(c, k, c->seg_hist.p);
+    // the number of levels is only known on the device: render max_levels_out, rows beyond the ladder
+    // come from all-zero segments and are ignored by the caller
+    enqueue_render(c, m, k, max_levels_out, c->seg_hist.p);
+    // Plan + pixels in one copy
+    CU(cudaMemcpyAsync(c->out_h, c->out_d, kPlanPad + (size_t)max_levels_out * n_pix, cudaMemcpyDeviceToHost, c->stream));
+}
+
+// Executable graph of a step for this (k, table, levels, layout); captured on first use, replayed afterwards.  Everything
+// that differs between samples reaches the kernels through the StepArgs block, so one graph serves every sample until a
+// device buffer moves (generation).  Returns nullptr when graphs are off or could not be built (plain launches then).
+vk_ctx::StepGraph* step_graph(vk_ctx* c, const Mapping& m, int slot, int k, int max_levels_out)
+{
+    if (!c->use_graph || c->graph_failed || c->fine_timing) return nullptr;
+    for (auto& g : c->graphs)
+        if (g.k == k && g.slot == slot && g.side == m.side && g.max_levels == max_levels_out && g.exact == (int)c->exact_layout &&
+            g.packed == (int)c->use_packed && g.generation == c->generation)
+            return &g;
+    // stale graphs (a buffer moved) are of no use any more
+    for (size_t i = 0; i < c->graphs.size();) {
+        if (c->graphs[i].generation != c->generation) {
+            cudaGraphExecDestroy(c->graphs[i].exec);
+            c->graphs.erase(c->graphs.begin() + i);
+        } else ++i;
+    }
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    c->capturing = true;
+    c->captured_kernels = 0;
+    bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (ok) {
+        try {
+            enqueue_step(c, m, k, max_levels_out);
+        } catch (...) {
+            ok = false;
+        }
+        if (cudaStreamEndCapture(c->stream, &graph) != cudaSuccess || !graph) ok = false;
+    }
+    c->capturing = false;
+    if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) ok = false;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+        cudaGetLastError();
+        if (exec) cudaGraphExecDestroy(exec);
+        c->graph_failed = 1;
+        return nullptr;
+    }
+    ++c->graph_captures;
+    c->graphs.push_back({k, slot, m.side, max_levels_out, (int)c->exact_layout, (int)c->use_packed, c->generation, exec,
+                         c->captured_kernels});
+    return &c->graphs.back();
 }
 
 }  // namespace
@@ -513,11 +661,16 @@ int vk_ctx_create(int device, vk_ctx** out)
         if (const char* e = getenv("VK_PDL")) c->use_pdl = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT16")) c->use_count16 = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT_PAIRS")) c->use_pairs = atoi(e) != 0;
+        if (const char* e = getenv("VK_PACKED")) c->use_packed = atoi(e) != 0;
+        if (const char* e = getenv("VK_GRAPH")) c->use_graph = atoi(e) != 0;
         if (c->count_threads < 32 || c->count_threads > 1024 || c->count_threads % 32 || c->count_ctas_per_sm < 1 || c->count_ctas_per_sm > 3)
             throw ApiError{VK_EINVAL, "bad VK_COUNT_THREADS / VK_COUNT_CTAS"};
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (int i = 0; i < EV_N; ++i) CU(cudaEventCreate(&c->ev[i]));
         ensure_outbox(c, 0);
+        CU(cudaMalloc(&c->args_d, sizeof(vk::StepArgs)));
+        CU(cudaMallocHost(&c->args_h, sizeof(vk::StepArgs)));
+        prepare_kernels();
         *out = c;
     });
 }
@@ -527,6 +680,11 @@ int vk_ctx_destroy(vk_ctx* c)
     if (!c) return VK_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    drop_graphs(c);
+    if (c->args_d) cudaFree(c->args_d);
+    if (c->args_h) cudaFreeHost(c->args_h);
+    c->codes.release();
+    c->valid.release();
     c->text_own.release();
     c->tile_status.release();
     c->masks.release();
@@ -544,6 +702,8 @@ int vk_ctx_destroy(vk_ctx* c)
     c->remap_out.release();
     c->remap_mult.release();
     c->remap_src.release();
+    c->content.release();
+    c->synth_off.release();
     for (auto& m : c->maps) m.lut.release();
     if (c->out_h) cudaFreeHost(c->out_h);
     if (c->out_d) cudaFree(c->out_d);
@@ -613,9 +773,12 @@ int vk_parse(vk_ctx* c, vk_stats* out)
         if (!c->have_text) throw ApiError{VK_ESTATE, "vk_parse before vk_upload / vk_attach"};
         set_device(c);
         ensure_tables_for(c, reads_bound(c->n_bytes));
+        ensure_parse_buffers(c, c->n_bytes);
         with_table_retry(c, [&] {
             if (!c->ev_valid[EV_UPLOAD]) { c->mark(EV_START); c->mark(EV_UPLOAD); }
-            enqueue_parse(c, nullptr);
+            enqueue_args(c, nullptr);
+            enqueue_args_copy(c);
+            enqueue_parse(c);
             c->mark(EV_PARSE);
             fetch_plan(c);
         });
@@ -634,15 +797,19 @@ int vk_count(vk_ctx* c, const vk_params* p, uint64_t* seg_hist_dev, vk_result* o
         const uint32_t nk = 1u << (2 * p->k);
         unsigned long long* sh = reinterpret_cast<unsigned long long*>(seg_hist_dev);
         if (!sh) {
-            c->seg_hist.ensure((size_t)vk::kMaxLevels * nk);
+            c->generation += c->seg_hist.ensure((size_t)vk::kMaxLevels * nk);
             sh = c->seg_hist.p;
         }
         ensure_tables_for(c, reads_bound(c->n_bytes));
+        ensure_parse_buffers(c, c->n_bytes);
+        ensure_count_buffers(c, p->k);
         with_table_retry(c, [&] {
             if (!c->ev_valid[EV_UPLOAD]) { c->mark(EV_START); c->mark(EV_UPLOAD); }
-            enqueue_parse(c, p, !c->parsed);      // framing found by vk_parse is kept; the ladder needs the parameters
+            enqueue_args(c, p);
+            enqueue_args_copy(c);
+            enqueue_parse(c, !c->parsed);         // framing found by vk_parse is kept; the ladder needs the parameters
             c->mark(EV_PARSE);
-            enqueue_count(c, p, sh, std::max<uint64_t>(c->starts.cap, 1));
+            enqueue_count(c, p->k, sh);
             fetch_plan(c);
             c->parsed = false;                     // a retry (table overflow) must rescan
         });
@@ -672,10 +839,9 @@ int vk_render(vk_ctx* c, int slot, int k, int n_levels, const uint64_t* seg_hist
         if (m) {
             enqueue_render(c, *m, k, n_levels, sh);
         } else {
-            c->canon.ensure((size_t)n_levels * nk);
+            c->generation += c->canon.ensure((size_t)n_levels * nk);
             launch(c, vk::fold_kernel, dim3((nk + 255) / 256), dim3(256), 0, sh, k, n_levels, c->canon.p);
             CU(cudaGetLastError());
-            ++c->launches;
         }
         if (canon_host)
             CU(cudaMemcpyAsync(canon_host, c->canon.p, (size_t)n_levels * nk * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
@@ -694,7 +860,7 @@ int vk_render_counts(vk_ctx* c, int slot, int k, int n, const uint64_t* canon_ho
         set_device(c);
         const Mapping& m = get_mapping(c, slot, k);
         const uint32_t nk = 1u << (2 * k);
-        c->canon.ensure((size_t)n * nk);
+        c->generation += c->canon.ensure((size_t)n * nk);
         CU(cudaMemcpyAsync(c->canon.p, canon_host, (size_t)n * nk * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
         enqueue_render(c, m, k, n, nullptr);      // canon is already in place: no fold
         CU(cudaMemcpyAsync(pixels_host, c->pix_d(), (size_t)n * m.side * m.side, cudaMemcpyDeviceToHost, c->stream));
@@ -716,30 +882,37 @@ int vk_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, int on_dev
         const uint32_t nk = 1u << (2 * k);
         const Mapping& m = get_mapping(c, slot, k);
         const size_t n_pix = (size_t)m.side * m.side;
-        c->seg_hist.ensure((size_t)vk::kMaxLevels * nk);
-        ensure_tables_for(c, reads_bound(n_bytes));
-        ensure_outbox(c, (size_t)max_levels_out * n_pix);
         if (!on_device) {
             if (n_bytes >> 40) throw ApiError{VK_ERANGE, "buffers of 2^40 bytes or more are not supported"};
             c->text_own.ensure(n_bytes + 64);
         }
         with_table_retry(c, [&] {
-            c->mark(EV_START);
+            // every buffer at its size before anything is enqueued (a capture must not allocate); after an overflow the
+            // tables have grown and the graph is captured again
+            c->generation += c->seg_hist.ensure((size_t)vk::kMaxLevels * nk);
+            ensure_tables_for(c, reads_bound(n_bytes));
+            ensure_parse_buffers(c, n_bytes);
+            ensure_count_buffers(c, k);
+            ensure_render_buffers(c, m, k, max_levels_out);
             if (!on_device) {
-                if (n_bytes) CU(cudaMemcpyAsync(c->text_own.p, text, n_bytes, cudaMemcpyHostToDevice, c->stream));
                 c->text = c->text_own.p;
                 c->n_bytes = n_bytes;
                 c->have_text = true;
             }
+            enqueue_args(c, p);
+            vk_ctx::StepGraph* g = step_graph(c, m, slot, k, max_levels_out);
+            c->mark(EV_START);
+            if (!on_device && n_bytes) CU(cudaMemcpyAsync(c->text_own.p, text, n_bytes, cudaMemcpyHostToDevice, c->stream));
             c->mark(EV_UPLOAD);
-            enqueue_parse(c, p);
-            c->mark(EV_PARSE);
-            enqueue_count(c, p, c->seg_hist.p, std::max<uint64_t>(c->starts.cap, 1));
-            // the number of levels is only known on the device: render max_levels_out, rows beyond the ladder
-            // come from all-zero segments and are ignored by the caller
-            enqueue_render(c, m, k, max_levels_out, c->seg_hist.p);
-            // Plan + pixels in one copy
-            CU(cudaMemcpyAsync(c->out_h, c->out_d, kPlanPad + (size_t)max_levels_out * n_pix, cudaMemcpyDeviceToHost, c->stream));
+            if (g) {
+                CU(cudaGraphLaunch(g->exec, c->stream));
+                c->launches += g->kernels;
+                ++c->graph_launches;
+                c->last_levels = max_levels_out;
+                c->last_side = m.side;
+            } else {
+                enqueue_step(c, m, k, max_levels_out);
+            }
             c->mark(EV_DONE);
         });
         if (c->plan_h->long_reads) throw ApiError{VK_ERANGE, "a read is longer than 2^24-1 bases"};
@@ -781,7 +954,6 @@ int vk_base_content(vk_ctx* c, int32_t pos_begin, int32_t pos_end, uint64_t* cou
             launch(c, vk::base_content_kernel, dim3(grid), dim3(vk::kContentThreads), 0, c->text, (const uint64_t*)c->starts.p,
                    (const uint64_t*)c->ends.p, (const vk::Plan*)c->plan_d, (uint32_t)pos_begin, n_pos, c->content.p);
             CU(cudaGetLastError());
-            ++c->launches;
         }
         CU(cudaMemcpyAsync(counts_host, c->content.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
@@ -843,7 +1015,6 @@ int vk_remap(vk_ctx* c, int n_images, uint32_t n_in, uint32_t n_out, const uint8
         CU(cudaMemcpyAsync(c->remap_mult.p, mult, (size_t)2 * n_out, cudaMemcpyHostToDevice, c->stream));
         launch(c, vk::remap_kernel, dim3(n_images), dim3(256), 0, c->remap_in.p, n_in, c->remap_src.p, c->remap_src.p + n_out,
                c->remap_mult.p, n_out, sum_rc, c->remap_out.p);
-        ++c->launches;
         CU(cudaMemcpyAsync(out_host, c->remap_out.p, (size_t)n_images * n_out, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
     });
@@ -857,6 +1028,15 @@ int vk_set_fine_timing(vk_ctx* c, int on)
 }
 
 uint64_t vk_launch_count(vk_ctx* c) { return c ? c->launches : 0; }
+
+int vk_graph_stats(vk_ctx* c, uint64_t* launches, uint64_t* captures, int32_t* state)
+{
+    if (!c) return VK_EINVAL;
+    if (launches) *launches = c->graph_launches;
+    if (captures) *captures = c->graph_captures;
+    if (state) *state = !c->use_graph ? 0 : (c->graph_failed ? -1 : 1);
+    return VK_OK;
+}
 uint64_t vk_bucket_retries(vk_ctx* c) { return c ? c->bucket_retries : 0; }
 
 int vk_synth_fastq(vk_ctx* c, void* dev_bytes, uint64_t capacity, uint64_t n_bases, int read_len, uint64_t seed,
@@ -875,9 +1055,39 @@ int vk_synth_fastq(vk_ctx* c, void* dev_bytes, uint64_t capacity, uint64_t n_bas
         launch(c, vk::synth_fixed_kernel, dim3(grid), dim3(256), 0, static_cast<uint8_t*>(dev_bytes), total, n_reads, (uint32_t)L,
                                                             (uint32_t)last_len, seed, first_read);
         CU(cudaGetLastError());
-        ++c->launches;
         CU(cudaStreamSynchronize(c->stream));
         *n_out = total;
+    });
+}
+
+int vk_synth_fastq_variable(vk_ctx* c, void* dev_bytes, uint64_t capacity, uint64_t n_reads, uint64_t seed,
+                            uint64_t first_read, int min_len, int max_len, int short_per_10000, int k, uint64_t* n_out,
+                            uint64_t* n_bases_out)
+{
+    return guarded([&] {
+        if (!c || !n_out) throw ApiError{VK_EINVAL, "NULL argument"};
+        if (min_len < 1 || max_len < min_len || max_len > 100000 || short_per_10000 < 0 || short_per_10000 > 10000 || k < 1 ||
+            n_reads == 0 || n_reads > (1ull << 32))
+            throw ApiError{VK_EINVAL, "bad generator arguments"};
+        set_device(c);
+        c->synth_off.ensure(n_reads + 1);
+        const int grid = (int)std::min<uint64_t>((n_reads + 255) / 256, (uint64_t)c->n_sms * 16);
+        launch(c, vk::synth_var_sizes_kernel, dim3(grid), dim3(256), 0, c->synth_off.p, n_reads, seed, first_read,
+               (uint32_t)min_len, (uint32_t)max_len, (uint32_t)short_per_10000, (uint32_t)k);
+        launch(c, vk::synth_scan_kernel, dim3(1), dim3(1024), 0, c->synth_off.p, n_reads);
+        CU(cudaGetLastError());
+        uint64_t total = 0;
+        CU(cudaMemcpyAsync(&total, c->synth_off.p + n_reads, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        *n_out = total;
+        if (n_bases_out) *n_bases_out = (total - 17ull * n_reads) / 2;
+        if (!dev_bytes) return;                         // size query
+        if (total > capacity) throw ApiError{VK_EINVAL, "synthetic FASTQ does not fit the buffer"};
+        const int g2 = (int)std::min<uint64_t>((n_reads + 7) / 8, (uint64_t)c->n_sms * 32);
+        launch(c, vk::synth_var_kernel, dim3(g2), dim3(256), 0, static_cast<uint8_t*>(dev_bytes), (const uint64_t*)c->synth_off.p,
+               n_reads, seed, first_read);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));
     });
 }
 

@@ -51,6 +51,30 @@ struct Plan {
     unsigned long long seg_next2[kMaxLevels];    // second set of unit counters (k = 9: the other half of every CTA pair)
 };
 
+// What plan_kernel needs beside the framing: the sample's options and the capacities of the tables.
+struct PlanArgs {
+    vk_params p;
+    uint64_t n_bytes;       // total bytes of the buffer
+    uint64_t cap_reads;
+    uint64_t cap_sorted;    // entries the sorted array holds
+    uint32_t n_count_ctas;  // grid of the count kernel
+    uint32_t reads_per_cta; // > 0: use at most ceil(n_reads / reads_per_cta) CTAs (small samples leave SMs to other samples)
+    uint32_t exact_layout;  // 1: every segment region holds all reads (retry after a bucket overflow)
+    uint32_t test_tight;    // tests only (VK_TEST_TIGHT_BUCKETS=1): regions of half the expected size, to force the retry
+};
+
+// Everything about ONE step (one sample through the path) that varies from step to step lives in this device-resident
+// block, not in kernel arguments: the kernels of a step are then launched with arguments that never change, so the
+// whole step can be captured once as a CUDA graph and replayed for every sample (vk_capi.cu).  The host writes the
+// block into pinned memory; the first node of a step copies it to the device.
+struct StepArgs {
+    const uint8_t* text;    // device pointer of the FASTQ bytes (16-byte aligned, readable up to the next 64-byte boundary)
+    uint64_t n_bytes;
+    uint32_t n_tiles;       // 32 KiB framing tiles
+    uint32_t reserved;
+    PlanArgs pa;
+};
+
 // splitmix64 finaliser over (seed, global read index): the seeded per-read priority (DESIGN.md "Sub-sampling").
 __host__ __device__ __forceinline__ uint64_t prio64(uint64_t seed, uint64_t read_index)
 {

@@ -115,14 +115,17 @@ struct Unit {
     uint32_t total;    // chunks in the unit (warp-uniform)
     uint32_t nz;       // lanes that hold a read (warp-uniform; reads are a prefix of the lanes)
 };
+// ALIGN: text alignment of a read's first chunk -- 16 when the chunk is two 16-byte text loads, 32 when it is one
+// 32-byte block of the packed arrays
+template <uint32_t ALIGN>
 __device__ __forceinline__ Unit make_unit(uint64_t ent, uint32_t lane)
 {
     constexpr uint32_t FULL = 0xffffffffu;
     Unit u;
     u.ent = ent;
     const uint32_t len = (uint32_t)(ent & kEntryLenMask);
-    const uint32_t lo16 = (uint32_t)(ent >> kEntryLenBits) & 15u;
-    const uint32_t n = len ? (lo16 + len + 31u) >> 5 : 0u;           // 32-byte chunks from the 16-byte word of the first base
+    const uint32_t lo16 = (uint32_t)(ent >> kEntryLenBits) & (ALIGN - 1u);
+    const uint32_t n = len ? (lo16 + len + 31u) >> 5 : 0u;           // 32-byte chunks from the aligned word of the first base
     uint32_t incl = n;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -137,7 +140,7 @@ __device__ __forceinline__ Unit make_unit(uint64_t ent, uint32_t lane)
 
 // What one lane needs to count its chunk: fetched one iteration ahead of its use.
 struct Chunk {
-    uint4 wa, wb;      // the 32 text bytes
+    uint4 wa, wb;      // the 32 text bytes (PACKED: wa.x, wa.y = their 2-bit codes, wa.z = their validity bits)
     uint32_t range;    // valid bytes of the chunk (bit mask); 0 for an idle lane
     uint32_t j;        // chunk number inside its read (0: no bases to the left)
     uint32_t rlen;     // length of the read (break points)
@@ -145,7 +148,16 @@ struct Chunk {
     uint32_t last;     // last lane of the window that holds a chunk (warp-uniform; 31 except where units run out)
 };
 
+// PACKED: the chunks come from the 2-bit codes + validity bits that parse_mask_kernel<true> wrote (vk_parse.cuh, one
+// 8-byte and one 4-byte load per chunk, nothing to classify) instead of from the text (two 16-byte loads per chunk).
+struct PackedSrc {
+    const uint2* codes64;      // 32 bases per element
+    const uint32_t* valid32;
+};
+template <bool PACKED>
 struct ChunkStream {
+    static constexpr uint32_t ALIGN = PACKED ? 32u : 16u;
+    PackedSrc pk;
     const uint4* text16;
     const uint64_t* seg_sorted;
     unsigned long long* seg_counter;
@@ -173,10 +185,10 @@ struct ChunkStream {
         return (lane < size && base < seg_len && base + lane < seg_len) ? seg_sorted[base + lane] : 0ull;
     }
     // n_warps_seg: warps that serve this segment (all CTAs of it)
-    __device__ __forceinline__ void init(const uint4* t, const uint64_t* ss, uint32_t sl, unsigned long long* sc, uint32_t ln,
-                                         uint64_t n_bytes, uint32_t n_warps_seg)
+    __device__ __forceinline__ void init(const uint4* t, PackedSrc src, const uint64_t* ss, uint32_t sl, unsigned long long* sc,
+                                         uint32_t ln, uint64_t n_bytes, uint32_t n_warps_seg)
     {
-        text16 = t; seg_sorted = ss; seg_len = sl; seg_counter = sc; lane = ln;
+        text16 = t; pk = src; seg_sorted = ss; seg_len = sl; seg_counter = sc; lane = ln;
         text_words = (n_bytes + 15) >> 4;
         pos = 0; own = 0; own_j = 0;
         n_warps = n_warps_seg ? n_warps_seg : 1u;
@@ -191,11 +203,11 @@ struct ChunkStream {
             const uint64_t ea = (base < seg_len && base + lane < seg_len) ? seg_sorted[base + lane] : 0ull;
             const uint64_t eb = (base + 32 < seg_len && base + 32 + lane < seg_len) ? seg_sorted[base + 32 + lane] : 0ull;
             entC = (base + 64 < seg_len && base + 64 + lane < seg_len) ? seg_sorted[base + 64 + lane] : 0ull;
-            A = make_unit(ea, lane);
-            B = make_unit(eb, lane);
+            A = make_unit<ALIGN>(ea, lane);
+            B = make_unit<ALIGN>(eb, lane);
         } else {                                                        // small segment: unit by unit keeps the warps balanced
-            A = make_unit(claim(), lane);
-            B = make_unit(claim(), lane);
+            A = make_unit<ALIGN>(claim(), lane);
+            B = make_unit<ALIGN>(claim(), lane);
             entC = claim();
         }
     }
@@ -206,7 +218,7 @@ struct ChunkStream {
             pos -= A.total;
             own -= 32;                                  // an owner in B keeps its lane
             A = B;
-            B = make_unit(entC, lane);
+            B = make_unit<ALIGN>(entC, lane);
             entC = claim();
         }
         Chunk c;
@@ -241,17 +253,27 @@ struct ChunkStream {
         }
         const uint64_t rstart = e >> kEntryLenBits;
         const uint32_t rlen = (uint32_t)(e & kEntryLenMask);
-        const uint32_t rlo = (uint32_t)rstart & 15u;
-        const uint4* const ptr = text16 + (rstart >> 4) + 2ull * j;
+        const uint32_t rlo = (uint32_t)rstart & (ALIGN - 1u);
         const uint32_t lo = j == 0 ? rlo : 0u;
         const uint32_t endrel = rlo + rlen - 32u * j;               // > 0 for an active lane
         const uint32_t hi = endrel < 32u ? endrel : 32u;
         c.wa = make_uint4(0, 0, 0, 0);
         c.wb = c.wa;
-        if (act) {
-            VK_ASSERT((uint64_t)(ptr - text16) + (hi > 16u ? 1 : 0) < text_words && rlen != 0 && j < ((rlo + rlen + 31u) >> 5));
-            c.wa = __ldg(ptr);
-            if (hi > 16u) c.wb = __ldg(ptr + 1);
+        if (PACKED) {
+            if (act) {
+                const uint64_t blk = (rstart >> 5) + j;             // 32-byte block of the text = one element of each array
+                VK_ASSERT(blk < ((text_words + 1) >> 1) && rlen != 0 && j < ((rlo + rlen + 31u) >> 5));
+                const uint2 cd = __ldg(pk.codes64 + blk);
+                c.wa.x = cd.x; c.wa.y = cd.y;
+                c.wa.z = __ldg(pk.valid32 + blk);
+            }
+        } else {
+            const uint4* const ptr = text16 + (rstart >> 4) + 2ull * j;
+            if (act) {
+                VK_ASSERT((uint64_t)(ptr - text16) + (hi > 16u ? 1 : 0) < text_words && rlen != 0 && j < ((rlo + rlen + 31u) >> 5));
+                c.wa = __ldg(ptr);
+                if (hi > 16u) c.wb = __ldg(ptr + 1);
+            }
         }
         c.range = act ? (0xffffffffu >> (32u - hi)) & (0xffffffffu << lo) : 0u;
         c.j = j;
@@ -269,19 +291,26 @@ struct Decoded {
     uint32_t Cc;         // codes of the K-1 bases to the left (first at bit 0)
     uint32_t E;          // bit b: the K-mer that ENDS at base b is to be counted
 };
-template <int K>
+template <int K, bool PACKED = false>
 __device__ __forceinline__ Decoded decode_chunk(const Chunk& cur, uint32_t& carry, uint32_t lane, int breaklen)
 {
     constexpr int KM1 = K - 1;
     constexpr uint32_t FULL = 0xffffffffu;
-    const Cls4z c0 = classify4z(cur.wa.x), c1 = classify4z(cur.wa.y), c2 = classify4z(cur.wa.z), c3 = classify4z(cur.wa.w);
-    const Cls4z c4 = classify4z(cur.wb.x), c5 = classify4z(cur.wb.y), c6 = classify4z(cur.wb.z), c7 = classify4z(cur.wb.w);
-    const uint32_t v01 = gather8(c0.z, c1.z), v23 = gather8(c2.z, c3.z);
-    const uint32_t v45 = gather8(c4.z, c5.z), v67 = gather8(c6.z, c7.z);
-    const uint32_t V = __byte_perm(__byte_perm(v01, v23, 0x0073), __byte_perm(v45, v67, 0x0073), 0x5410) & cur.range;
     Decoded d;
-    d.Plo = __byte_perm(__byte_perm(c0.packed_hi, c1.packed_hi, 0x0073), __byte_perm(c2.packed_hi, c3.packed_hi, 0x0073), 0x5410);
-    d.Phi = __byte_perm(__byte_perm(c4.packed_hi, c5.packed_hi, 0x0073), __byte_perm(c6.packed_hi, c7.packed_hi, 0x0073), 0x5410);
+    uint32_t V;
+    if (PACKED) {
+        d.Plo = cur.wa.x;
+        d.Phi = cur.wa.y;
+        V = cur.wa.z & cur.range;
+    } else {
+        const Cls4z c0 = classify4z(cur.wa.x), c1 = classify4z(cur.wa.y), c2 = classify4z(cur.wa.z), c3 = classify4z(cur.wa.w);
+        const Cls4z c4 = classify4z(cur.wb.x), c5 = classify4z(cur.wb.y), c6 = classify4z(cur.wb.z), c7 = classify4z(cur.wb.w);
+        const uint32_t v01 = gather8(c0.z, c1.z), v23 = gather8(c2.z, c3.z);
+        const uint32_t v45 = gather8(c4.z, c5.z), v67 = gather8(c6.z, c7.z);
+        V = __byte_perm(__byte_perm(v01, v23, 0x0073), __byte_perm(v45, v67, 0x0073), 0x5410) & cur.range;
+        d.Plo = __byte_perm(__byte_perm(c0.packed_hi, c1.packed_hi, 0x0073), __byte_perm(c2.packed_hi, c3.packed_hi, 0x0073), 0x5410);
+        d.Phi = __byte_perm(__byte_perm(c4.packed_hi, c5.packed_hi, 0x0073), __byte_perm(c6.packed_hi, c7.packed_hi, 0x0073), 0x5410);
+    }
     // ---- the K-1 bases before this chunk: from the lane to the left when it holds the same read
     const uint32_t tail = (d.Phi >> (32 - 2 * KM1)) | ((V >> (32 - KM1)) << 16);
     uint32_t hist = __shfl_up_sync(FULL, tail, 1);
@@ -356,12 +385,14 @@ __device__ __forceinline__ void emit16(const uint64_t W4, const uint32_t E, cons
     }
 }
 
-template <int K, int MODE>
+template <int K, int MODE, bool PACKED>
 __global__ void __launch_bounds__(kCountThreads)
-count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sorted, Plan* __restrict__ plan,
-             uint32_t* __restrict__ slabs, unsigned long long* __restrict__ seg_hist, int breaklen)
+count_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __restrict__ sorted, Plan* __restrict__ plan,
+             uint32_t* __restrict__ slabs, unsigned long long* __restrict__ seg_hist)
 {
     pdl_wait();
+    const uint4* __restrict__ text16 = reinterpret_cast<const uint4*>(sa->text);
+    const int breaklen = sa->pa.p.breaklength;
     static_assert(MODE == kSmem32 || MODE == kGlobal, "count16_kernel is the kSmem16 kernel");
     constexpr uint32_t NK = 1u << (2 * K);
     constexpr int KM1 = K - 1;
@@ -385,14 +416,14 @@ count_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sort
         __syncthreads();
     }
 
-    ChunkStream cs;
-    cs.init(text16, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane, plan->n_bytes,
+    ChunkStream<PACKED> cs;
+    cs.init(text16, pk, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane, plan->n_bytes,
             (plan->seg_cta_begin[seg + 1] - plan->seg_cta_begin[seg]) * (blockDim.x >> 5));
     uint32_t carry = 0;                                             // tail of lane 31 of the previous iteration
     Chunk cur = cs.fetch();
     while (__ballot_sync(FULL, cur.range != 0) != 0) {
         const Chunk nxt = cs.fetch();
-        const Decoded d = decode_chunk<K>(cur, carry, lane, breaklen);
+        const Decoded d = decode_chunk<K, PACKED>(cur, carry, lane, breaklen);
         const uint64_t Wa = ((uint64_t)d.Cc | ((uint64_t)d.Plo << (2 * KM1))) << 2;
         const uint64_t Wb = ((uint64_t)(d.Plo >> (32 - 2 * KM1)) | ((uint64_t)d.Phi << (2 * KM1))) << 2;
         emit16<K, MODE>(Wa, d.E & 0xFFFFu, hist_addr, trash_addr, gh);
@@ -474,12 +505,14 @@ __device__ __forceinline__ void count16_flush(uint32_t* __restrict__ h8, uint32_
     }
 }
 
-template <int K>
+template <int K, bool PACKED>
 __global__ void __launch_bounds__(kCountThreads)
-count16_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sorted, Plan* __restrict__ plan,
-               uint32_t* __restrict__ slabs, int breaklen)
+count16_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __restrict__ sorted, Plan* __restrict__ plan,
+               uint32_t* __restrict__ slabs)
 {
     pdl_wait();
+    const uint4* __restrict__ text16 = reinterpret_cast<const uint4*>(sa->text);
+    const int breaklen = sa->pa.p.breaklength;
     static_assert(K == 7 || K == 8, "16-bit bins: k = 8 directly, k = 7 through pairs");
     constexpr uint32_t NK = 1u << (2 * K);
     constexpr int KM1 = K - 1;
@@ -501,14 +534,14 @@ count16_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ so
     for (uint32_t i = tid; i < NK; i += nthr) slab[i] = 0;             // drains and the final fold ADD to the slab
     __syncthreads();
 
-    ChunkStream cs;
-    cs.init(text16, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane, plan->n_bytes,
+    ChunkStream<PACKED> cs;
+    cs.init(text16, pk, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane, plan->n_bytes,
             (plan->seg_cta_begin[seg + 1] - plan->seg_cta_begin[seg]) * (blockDim.x >> 5));
     uint32_t carry = 0;
     Chunk cur = cs.fetch();
     while (__ballot_sync(FULL, cur.range != 0) != 0) {
         const Chunk nxt = cs.fetch();
-        const Decoded d = decode_chunk<K>(cur, carry, lane, breaklen);
+        const Decoded d = decode_chunk<K, PACKED>(cur, carry, lane, breaklen);
         const uint64_t Wa = ((uint64_t)d.Cc | ((uint64_t)d.Plo << (2 * KM1))) << 2;
         const uint64_t Wb = ((uint64_t)(d.Plo >> (32 - 2 * KM1)) | ((uint64_t)d.Phi << (2 * KM1))) << 2;
         if (K == 8) {
@@ -653,11 +686,14 @@ __device__ __forceinline__ void drain9_steps(uint32_t Wl, uint32_t Wh, uint32_t 
     }
 }
 
+template <bool PACKED>
 __global__ void __launch_bounds__(kCountThreads)
-count9h_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ sorted, Plan* __restrict__ plan,
-               uint32_t* __restrict__ slabs, int breaklen)
+count9h_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __restrict__ sorted, Plan* __restrict__ plan,
+               uint32_t* __restrict__ slabs)
 {
     pdl_wait();
+    const uint4* __restrict__ text16 = reinterpret_cast<const uint4*>(sa->text);
+    const int breaklen = sa->pa.p.breaklength;
     constexpr int K = 9;
     constexpr uint32_t NB = 65536u;               // bins of one half
     constexpr uint32_t FULL = 0xffffffffu;
@@ -677,8 +713,8 @@ count9h_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ so
     for (uint32_t i = tid; i < 32768u; i += nthr) s_raw[i] = 0;
     __syncthreads();
 
-    ChunkStream cs;
-    cs.init(text16, sorted + plan->seg_begin[seg], seg_len, half ? &plan->seg_next2[seg] : &plan->seg_next[seg], lane,
+    ChunkStream<PACKED> cs;
+    cs.init(text16, pk, sorted + plan->seg_begin[seg], seg_len, half ? &plan->seg_next2[seg] : &plan->seg_next[seg], lane,
             plan->n_bytes, (plan->seg_cta_begin[seg + 1] - plan->seg_cta_begin[seg]) * (blockDim.x >> 5));
     const uint32_t zero = (uint32_t)(plan->n_bytes >> 63);                   // 0 (texts are shorter than 2^40), but not to ptxas
     const Opaque9 q = {0x80000000u >> zero, 2048u >> zero, h_addr, (1u - half) << 19};
@@ -686,7 +722,7 @@ count9h_kernel(const uint4* __restrict__ text16, const uint64_t* __restrict__ so
     Chunk cur = cs.fetch();
     while (__ballot_sync(FULL, cur.range != 0) != 0) {
         const Chunk nxt = cs.fetch();
-        const Decoded d = decode_chunk<K>(cur, carry, lane, breaklen);
+        const Decoded d = decode_chunk<K, PACKED>(cur, carry, lane, breaklen);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             // 24 bases: the 9-mers that end at chunk positions 16h .. 16h+15 (8 bases in front of the first one)

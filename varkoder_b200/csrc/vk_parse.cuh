@@ -38,13 +38,79 @@ __device__ __forceinline__ uint32_t nl16(uint4 w)
     return nl4(w.x) | (nl4(w.y) << 4) | (nl4(w.z) << 8) | (nl4(w.w) << 12);
 }
 
+// ---- 2-bit pack (K1a with PACK): the same pass that finds the newlines also classifies every byte, blind to the
+// framing: code = (byte >> 1) & 3 (A0 C1 T2 G3, the dsk code; vk_count.cuh) and valid = byte is one of ACGTacgt.
+// Layout ("position layout"): text byte i has its code at bits [2 (i & 31), +2) of codes64[i >> 5] and its validity
+// at bit (i & 31) of valid32[i >> 5] -- headers and quality lines are packed too (their words are never read: the
+// count kernels only visit the 32-byte blocks of sequence lines, and only trust codes under a set validity bit).
+// A newline is an invalid byte, so runs of k valid bytes can never span two reads.  Nothing here depends on k.
+//
+// Arithmetic per 32-bit word x, SIMD over its four bytes (pipe balance matters: the kernel sits at the ALU-pipe limit,
+// so additions and the multiplications by small constants go to the FMA pipe as IMAD):
+//   y  = x & 0x06060606                         codes at bits 1-2 of each byte
+//   codes: top byte of y * 0x00820820           (no two partial products meet in bits 24..31)
+//   T?  : (y * 3) & 0x08  -- y*3 is 0, 6, 12, 18 for codes A, C, T, G; only 12 has bit 3 set
+//   d   = ((x & 0xD9) ^ 0x41) ^ (T? ? 0x11 : 0) -- 0 iff the byte, case bit cleared, is the letter its code names:
+//         'A' 0x41, 'C' 0x43, 'G' 0x47 agree outside bits 1-2 (mask 0xD9 drops bits 1, 2 and 5 = case); 'T' 0x54 differs
+//         from that pattern by 0x11.  Zero bytes of d are then found with the exact carry-free test.
+__device__ __forceinline__ uint32_t mul_lo(uint32_t a, uint32_t b)      // IMAD (FMA pipe), even by a power of two
+{
+    uint32_t d;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b, uint32_t one)      // a * 1 + b as IMAD; `one` opaque to ptxas
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+}
+struct Packed4 {
+    uint32_t codes_hi;    // byte 3 = the four 2-bit codes
+    uint32_t zv;          // 0x80 in every byte that is one of ACGTacgt
+    uint32_t zn;          // 0x80 in every byte that is '\n'
+};
+__device__ __forceinline__ Packed4 pack4(uint32_t x, uint32_t one)
+{
+    Packed4 r;
+    const uint32_t y = x & 0x06060606u;
+    r.codes_hi = y * 0x00820820u;
+    const uint32_t t8 = (y * 3u) & 0x08080808u;
+    const uint32_t t11 = (t8 >> 3) * 0x11u;
+    uint32_t d1;                                               // (x & 0xD9..) ^ 0x41..
+    asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(d1) : "r"(x), "r"(0xD9D9D9D9u), "r"(0x41414141u));
+    uint32_t dm;                                               // (d1 ^ t11) & 0x7F..
+    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(dm) : "r"(d1), "r"(t11), "r"(0x7F7F7F7Fu));
+    const uint32_t sv = add_fma(dm, 0x7F7F7F7Fu, one);
+    // bit 7 of d is bit 7 of x (neither 0x41 nor 0x11 touches it): valid <=> ~(sv | x) & 0x80
+    asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(r.zv) : "r"(sv), "r"(x), "r"(0x80808080u));
+    uint32_t nm;                                               // (x ^ 0x0A..) & 0x7F..
+    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(nm) : "r"(x), "r"(0x0A0A0A0Au), "r"(0x7F7F7F7Fu));
+    const uint32_t sn = add_fma(nm, 0x7F7F7F7Fu, one);
+    asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(r.zn) : "r"(sn), "r"(x), "r"(0x80808080u));
+    return r;
+}
+// 8 flags (0x80 per byte in za, zb) -> byte 3: bits 24..27 = word a (bytes 0..3), bits 28..31 = word b
+__device__ __forceinline__ uint32_t gather_flags8(uint32_t za, uint32_t zb) { return (zb | (za >> 4)) * 0x00204081u; }
+// byte 3 of four registers -> one word (a lowest)
+__device__ __forceinline__ uint32_t top_bytes4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    return __byte_perm(__byte_perm(a, b, 0x0073), __byte_perm(c, d, 0x0073), 0x5410);
+}
+
 // K1a: thread t of tile T owns bytes [T*32Ki + 64t, +64): mask bit j = byte j is '\n'.
+template <bool PACK>
 __global__ void __launch_bounds__(kParseThreads)
-parse_mask_kernel(const uint4* __restrict__ text16, uint64_t n_bytes, uint32_t n_tiles,
-                  uint64_t* __restrict__ masks, uint32_t* __restrict__ tile_count, uint32_t* __restrict__ warp_count)
+parse_mask_kernel(const StepArgs* __restrict__ sa,
+                  uint64_t* __restrict__ masks, uint32_t* __restrict__ tile_count, uint32_t* __restrict__ warp_count,
+                  uint4* __restrict__ codes16, uint2* __restrict__ valid8)
 {
     pdl_wait();
+    const uint4* __restrict__ text16 = reinterpret_cast<const uint4*>(sa->text);
+    const uint64_t n_bytes = sa->n_bytes;
+    const uint32_t n_tiles = sa->n_tiles;
     const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t one = PACK ? (uint32_t)(n_bytes >> 62) + 1u : 1u;       // 1 (texts are shorter than 2^40), but not to ptxas
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t tbyte = (uint64_t)tile * kParseTileBytes + (uint64_t)tid * 64;
         uint64_t m = 0;
@@ -55,9 +121,35 @@ parse_mask_kernel(const uint4* __restrict__ text16, uint64_t n_bytes, uint32_t n
                 const uint64_t b = tbyte + 16ull * i;
                 w[i] = (b < n_bytes) ? __ldcs(text16 + (b >> 4)) : make_uint4(0, 0, 0, 0);      // streaming: the text must not evict the masks
             }
+            if (PACK) {
+                uint32_t cw[4], vb[4], nb[4];      // per 16 bytes: 32 bits of codes, validity byte pair, newline byte pair
+                uint32_t vq[2][2], nq[2][2];
 #pragma unroll
-            for (int i = 0; i < kParseWordsPerThread; ++i) m |= (uint64_t)nl16(w[i]) << (16 * i);
-            if (n_bytes - tbyte < 64) m &= (1ull << (n_bytes - tbyte)) - 1;
+                for (int i = 0; i < kParseWordsPerThread; ++i) {
+                    const Packed4 a = pack4(w[i].x, one), b = pack4(w[i].y, one), c = pack4(w[i].z, one), d = pack4(w[i].w, one);
+                    cw[i] = top_bytes4(a.codes_hi, b.codes_hi, c.codes_hi, d.codes_hi);
+                    vq[i & 1][0] = gather_flags8(a.zv, b.zv); vq[i & 1][1] = gather_flags8(c.zv, d.zv);
+                    nq[i & 1][0] = gather_flags8(a.zn, b.zn); nq[i & 1][1] = gather_flags8(c.zn, d.zn);
+                    if (i & 1) {
+                        vb[i >> 1] = top_bytes4(vq[0][0], vq[0][1], vq[1][0], vq[1][1]);
+                        nb[i >> 1] = top_bytes4(nq[0][0], nq[0][1], nq[1][0], nq[1][1]);
+                    }
+                }
+                uint32_t v0 = vb[0], v1 = vb[1];
+                m = (uint64_t)nb[0] | ((uint64_t)nb[1] << 32);
+                if (n_bytes - tbyte < 64) {
+                    const uint64_t keep = (1ull << (n_bytes - tbyte)) - 1;
+                    m &= keep;
+                    v0 &= (uint32_t)keep;
+                    v1 &= (uint32_t)(keep >> 32);
+                }
+                codes16[tbyte >> 6] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+                valid8[tbyte >> 6] = make_uint2(v0, v1);
+            } else {
+#pragma unroll
+                for (int i = 0; i < kParseWordsPerThread; ++i) m |= (uint64_t)nl16(w[i]) << (16 * i);
+                if (n_bytes - tbyte < 64) m &= (1ull << (n_bytes - tbyte)) - 1;
+            }
         }
         masks[(uint64_t)tile * kParseThreads + tid] = m;
         const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popcll(m));
@@ -72,10 +164,11 @@ parse_mask_kernel(const uint4* __restrict__ text16, uint64_t n_bytes, uint32_t n
 // Counts are staged through shared memory in chunks (coalesced loads/stores), each thread scans a contiguous slice.
 constexpr uint32_t kScanChunk = 8192;            // 32 KiB of static shared memory
 __global__ void __launch_bounds__(1024)
-parse_scan_kernel(const uint32_t* __restrict__ tile_count, uint32_t n_tiles, uint64_t* __restrict__ tile_prefix,
+parse_scan_kernel(const uint32_t* __restrict__ tile_count, const StepArgs* __restrict__ sa, uint64_t* __restrict__ tile_prefix,
                   Plan* __restrict__ plan)
 {
     pdl_wait();
+    const uint32_t n_tiles = sa->n_tiles;
     __shared__ uint32_t s_cnt[kScanChunk];
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total;
@@ -177,10 +270,12 @@ __device__ __forceinline__ int32_t emit_unit(uint32_t (&w)[2 * kEmitMasks], uint
 
 __global__ void __launch_bounds__(256)
 parse_emit_kernel(const uint64_t* __restrict__ masks, const uint64_t* __restrict__ tile_prefix,
-                  const uint32_t* __restrict__ warp_count, uint32_t n_tiles, uint64_t byte_base,
-                  uint64_t* __restrict__ starts, uint64_t* __restrict__ ends, uint64_t cap_reads, Plan* __restrict__ plan)
+                  const uint32_t* __restrict__ warp_count, const StepArgs* __restrict__ sa, uint64_t byte_base,
+                  uint64_t* __restrict__ starts, uint64_t* __restrict__ ends, Plan* __restrict__ plan)
 {
     pdl_wait();
+    const uint32_t n_tiles = sa->n_tiles;
+    const uint64_t cap_reads = sa->pa.cap_reads;
     const uint32_t lane = threadIdx.x & 31;
     // 32-bit unit arithmetic: the text is shorter than 2^40 bytes, so there are fewer than 2^28 units
     const uint32_t n_units = n_tiles * kEmitUnitsPerTile;
@@ -265,16 +360,6 @@ parse_emit_kernel(const uint64_t* __restrict__ masks, const uint64_t* __restrict
 }
 
 // ---- K1L: finish the framing and build the ladder, single thread ---------------------------------------
-struct PlanArgs {
-    vk_params p;
-    uint64_t n_bytes;       // total bytes of the buffer
-    uint64_t cap_reads;
-    uint64_t cap_sorted;    // entries the sorted array holds
-    uint32_t n_count_ctas;  // grid of the count kernel
-    uint32_t reads_per_cta; // > 0: use at most ceil(n_reads / reads_per_cta) CTAs (small samples leave SMs to other samples)
-    uint32_t exact_layout;  // 1: every segment region holds all reads (retry after a bucket overflow)
-    uint32_t test_tight;    // tests only (VK_TEST_TIGHT_BUCKETS=1): regions of half the expected size, to force the retry
-};
 
 __device__ inline uint64_t div_2p64(uint64_t num, uint64_t den)
 {
@@ -290,10 +375,12 @@ __device__ inline uint64_t div_2p64(uint64_t num, uint64_t den)
 }
 
 __global__ void __launch_bounds__(64)
-plan_kernel(const uint8_t* __restrict__ text, uint64_t* __restrict__ starts, uint64_t* __restrict__ ends, PlanArgs a,
+plan_kernel(const StepArgs* __restrict__ sa, uint64_t* __restrict__ starts, uint64_t* __restrict__ ends,
             Plan* __restrict__ plan)
 {
     pdl_wait();
+    const uint8_t* __restrict__ text = sa->text;
+    const PlanArgs a = sa->pa;
     // one CTA of 64 threads: thread 0 finishes the framing and walks the ladder (sequential by nature, ~10 levels),
     // then thread l computes level l's priority threshold (a 64-step long division each) and clears its segment slots
     __shared__ uint64_t s_lv[kMaxLevels];
@@ -449,6 +536,17 @@ plan_kernel(const uint8_t* __restrict__ text, uint64_t* __restrict__ starts, uin
         }
         __syncthreads();
         if (l >= nl) plan->seg_cta_begin[l] = s_crun;      // no CTAs beyond the ladder
+        // A read table or a segment layout that does not fit its allocation: the host repeats the step with larger
+        // buffers (with_table_retry).  Until then nothing downstream may touch the tables: starts / ends beyond the
+        // capacity were never written, regions would lie outside `sorted`.  No CTA gets a segment, no region has room;
+        // bucket_scatter_kernel and base_content_kernel return at once when they see either flag.
+        __syncthreads();
+        if (plan->table_overflow || plan->bucket_overflow) {
+            plan->seg_cta_begin[l] = 0;
+            plan->seg_cap[l] = 0;
+            plan->seg_begin[l] = 0;
+            if (l == 0) { plan->seg_cta_begin[kMaxLevels] = 0; plan->seg_begin[kMaxLevels] = 0; }
+        }
     }
 }
 

@@ -27,7 +27,7 @@ base_content_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t i = tid; i < (kContentThreads / 32) * kContentMaxPos * 5; i += blockDim.x) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
-    const uint64_t n_reads = plan->n_reads;
+    const uint64_t n_reads = plan->table_overflow ? 0 : plan->n_reads;      // an overflowed table is never dereferenced
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     // at most 2^26 reads per warp row: 32-bit rows cannot overflow
     for (uint64_t r0 = (uint64_t)blockIdx.x * blockDim.x + (tid & ~31u); r0 < n_reads; r0 += stride) {

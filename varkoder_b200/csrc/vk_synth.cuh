@@ -67,4 +67,99 @@ synth_fixed_kernel(uint8_t* __restrict__ out, uint64_t n_out, uint64_t n_reads, 
     }
 }
 
+// ---- variable read lengths ("Bembidion-shaped"): lengths uniform min_len..max_len, a
+// fraction short_per_10000 / 10000 of the reads shorter than k (0..k-1 bases, empty ones included).  Same bytes as
+// varkoder_b200/synth.py variable().
+__host__ __device__ __forceinline__ uint32_t synth_var_len(uint64_t seed, uint64_t r, uint32_t min_len, uint32_t max_len,
+                                                           uint32_t short_per_10000, uint32_t k)
+{
+    const uint64_t hl = synth_hash(seed ^ 0x5EEDull, r, 0);
+    if ((uint32_t)((hl >> 32) % 10000u) < short_per_10000) return (uint32_t)((hl >> 48) % k);
+    return min_len + (uint32_t)(hl % (uint64_t)(max_len - min_len + 1));
+}
+
+// record sizes (2 len + 17) of reads first_read .. first_read + n_reads - 1
+__global__ void __launch_bounds__(256)
+synth_var_sizes_kernel(uint64_t* __restrict__ rec, uint64_t n_reads, uint64_t seed, uint64_t first_read, uint32_t min_len,
+                       uint32_t max_len, uint32_t short_per_10000, uint32_t k)
+{
+    pdl_wait();
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_reads; g += (uint64_t)gridDim.x * blockDim.x)
+        rec[g] = 2ull * synth_var_len(seed, first_read + g, min_len, max_len, short_per_10000, k) + 17ull;
+}
+
+// in-place exclusive prefix sum of n 64-bit values, one CTA (generator only: a sample has < 10^6 reads); v[n] = total
+__global__ void __launch_bounds__(1024)
+synth_scan_kernel(uint64_t* __restrict__ v, uint64_t n)
+{
+    pdl_wait();
+    __shared__ uint64_t s_warp[32];
+    __shared__ uint64_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint64_t c0 = 0; c0 < n; c0 += 1024) {
+        const uint64_t i = c0 + tid;
+        const uint64_t x = i < n ? v[i] : 0;
+        uint64_t incl = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint64_t wv = s_warp[lane];
+            uint64_t wi = wv;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t t = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= (uint32_t)d) wi += t;
+            }
+            s_warp[lane] = wi - wv;
+        }
+        __syncthreads();
+        const uint64_t carry = s_carry;
+        if (i < n) v[i] = carry + s_warp[warp] + incl - x;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[warp] + incl;
+        __syncthreads();
+    }
+    if (tid == 0) v[n] = s_carry;
+}
+
+// one warp per record
+__global__ void __launch_bounds__(256)
+synth_var_kernel(uint8_t* __restrict__ out, const uint64_t* __restrict__ off, uint64_t n_reads, uint64_t seed,
+                 uint64_t first_read)
+{
+    pdl_wait();
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t rl = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rl < n_reads; rl += n_warps) {
+        const uint64_t o0 = off[rl];
+        const uint32_t rs = (uint32_t)(off[rl + 1] - o0);
+        const uint32_t len = (rs - 17u) >> 1;
+        const uint64_t r = first_read + rl;
+        for (uint32_t o = lane; o < rs; o += 32) {
+            uint8_t c;
+            if (o == 0) c = '@';
+            else if (o == 1) c = 'S';
+            else if (o < 12) {
+                uint64_t v = r % 10000000000ull;
+                for (uint32_t d = 11; d > o; --d) v /= 10;
+                c = (uint8_t)('0' + v % 10);
+            } else if (o == 12) c = '\n';
+            else if (o < 13 + len) c = synth_base(seed, r, o - 13, len);
+            else if (o == 13 + len) c = '\n';
+            else if (o == 14 + len) c = '+';
+            else if (o == 15 + len) c = '\n';
+            else if (o < 16 + 2 * len) c = synth_qual(seed, r, o - 16 - len);
+            else c = '\n';
+            out[o0 + o] = c;
+        }
+    }
+}
+
 }  // namespace vk

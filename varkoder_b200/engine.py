@@ -243,6 +243,12 @@ class Engine:
     def launch_count(self):
         return int(self._L.vk_launch_count(self._ctx))
 
+    def graph_stats(self):
+        """(steps submitted as one CUDA graph, graphs captured, state: 1 on / 0 off / -1 capture failed)"""
+        a, b, st = C.c_uint64(), C.c_uint64(), C.c_int32()
+        self._check(self._L.vk_graph_stats(self._ctx, C.byref(a), C.byref(b), C.byref(st)))
+        return int(a.value), int(b.value), int(st.value)
+
     def bucket_retries(self):
         return int(self._L.vk_bucket_retries(self._ctx))
 
@@ -251,3 +257,11 @@ class Engine:
         self._check(self._L.vk_synth_fastq(self._ctx, dev_ptr, capacity, n_bases, read_len, seed, first_read,
                                            C.byref(n)))
         return int(n.value)
+
+    def synth_fastq_variable(self, dev_ptr, capacity, n_reads, seed=0, first_read=0, min_len=60, max_len=280,
+                             short_frac=0.01, k=7):
+        """device twin of synth.variable(); dev_ptr=None only reports the size.  -> (bytes, bases)"""
+        n, nb = C.c_uint64(), C.c_uint64()
+        self._check(self._L.vk_synth_fastq_variable(self._ctx, dev_ptr, capacity, n_reads, seed, first_read, min_len,
+                                                    max_len, int(short_frac * 10000), k, C.byref(n), C.byref(nb)))
+        return int(n.value), int(nb.value)

@@ -308,9 +308,14 @@ class SampleFeeder:
     """Iterate ``(index, item, PinnedBuffer, n_bytes)`` over samples in submission order, inflating up to ``depth``
     samples ahead on ``threads`` worker threads.  Buffers are recycled: hand one back with :meth:`release`."""
 
-    def __init__(self, items, path_of=lambda it: it, threads=None, depth=None, pinned=True):
+    def __init__(self, items, path_of=lambda it: it, threads=None, depth=None, pinned=True, errors="raise"):
+        """``path_of(item)`` may return None: the item has no file (its bytes are already somewhere) and is passed
+        through with ``buf = None``.  ``errors="yield"``: a sample that cannot be read is yielded as ``(index, item,
+        exception, -1)`` instead of ending the iteration, so that a batch survives a damaged file the way the reference's
+        per-sample loop does (image.py:1020-1027)."""
         self.items = list(items)
         self.path_of = path_of
+        self.errors = errors
         self.threads = threads or max(1, min(len(os.sched_getaffinity(0)), 16))
         self.depth = depth or self.threads + 1
         # fewer samples than threads: the spare threads split single gzip members (pigz-written files) into pieces
@@ -321,14 +326,23 @@ class SampleFeeder:
         self.pool = ThreadPoolExecutor(max_workers=self.threads, thread_name_prefix="vk-inflate")
 
     def _job(self, it):
+        path = self.path_of(it)
+        if path is None:
+            return None, 0
         with self._lock:
             buf = self._free.popleft() if self._free else None
         if buf is None:
             buf = _cached_buffer(self.pinned)
-        n = inflate_into(self.path_of(it), buf, self.piece_threads)
+        try:
+            n = inflate_into(path, buf, self.piece_threads)
+        except BaseException:
+            self.release(buf)
+            raise
         return buf, n
 
     def release(self, buf):
+        if buf is None or isinstance(buf, BaseException):
+            return
         with self._lock:
             self._free.append(buf)
 
@@ -341,7 +355,12 @@ class SampleFeeder:
                     pending.append((nxt, self.items[nxt], self.pool.submit(self._job, self.items[nxt])))
                     nxt += 1
                 i, it, fut = pending.popleft()
-                buf, n = fut.result()
+                try:
+                    buf, n = fut.result()
+                except Exception as exc:
+                    if self.errors != "yield":
+                        raise
+                    buf, n = exc, -1
                 yield i, it, buf, n
         finally:
             for _, _, fut in pending:

@@ -83,6 +83,16 @@ def write_png(pixels, path, labels=(), base_sd=0, base_sd_thresh=QUAL_THRESH, ma
     img.save(Path(path), optimize=True, pnginfo=meta)
 
 
+def _stage_times(tm):
+    """(splitting_time, kmer_counting_time) in seconds from Engine.timings().  With the per-kernel events on
+    (Engine.set_fine_timing(True)) the stages are the kernel groups; by default a sample is ONE graph launch and only its
+    upload and its total are known: splitting_time is the upload, the counting time carries all the GPU work of the step
+    (framing, sub-sampling, counting, rendering)."""
+    if tm["count"] > 0:
+        return (tm["upload"] + tm["parse"] + tm["plan_bucket"]) / 1e3, (tm["count"] + tm["reduce_fold"]) / 1e3
+    return tm["upload"] / 1e3, max(tm["total"] - tm["upload"], 0.0) / 1e3
+
+
 def _image_folder(outfolder, outfile, subfolder_levels):
     outfolder = Path(outfolder)
     if subfolder_levels:
@@ -132,9 +142,10 @@ def reads_to_images(infile, sample, outfolder, kmer_mapping, k=7, mapping_code="
     t2 = time.perf_counter()
     tm = eng.timings()
     stats = OrderedDict()
-    stats["splitting_time"] = (tm["upload"] + tm["parse"] + tm["plan_bucket"]) / 1e3
+    split_s, count_s = _stage_times(tm)
+    stats["splitting_time"] = split_s
     stats["splitting_bp_per_file"] = ",".join(str(x) for x in res.levels)
-    stats[str(k) + "mer_counting_time"] = (tm["count"] + tm["reduce_fold"]) / 1e3
+    stats[str(k) + "mer_counting_time"] = count_s
     stats["k" + str(k) + "_img_time"] = tm["render"] / 1e3 + (t2 - t1)
     if measured_sd is not None:
         stats["base_frequencies_sd"] = measured_sd          # the key run_clean2img sets (image.py:1096)
@@ -246,22 +257,28 @@ def make_image(infile, outfolder, kmer_mapping, threads=1, overwrite=False, verb
 # ------------------------------------------------------------------------------------------ batch
 def images_for_samples(samples, outfolder, kmer_mapping, k=7, mapping_code="varKode", min_bp=50000, max_bp=None,
                        is_query=False, seeds=None, subfolder_levels=0, overwrite=False, threads=None, engine=None,
-                       on_error=None, gpu_workers=1, device=None):
+                       on_error=None, gpu_workers=1, device=None, on_result=None, write_png_of=None):
     """Steps C-E of run_clean2img for MANY samples (the loop of ImageCommand.process_samples, image.py:1265-1294) on
     one GPU: samples are inflated ahead by worker threads into pinned memory (varkoder_b200.feed), pushed through the
     GPU by ``gpu_workers`` threads that each own a context, and their PNGs are written by the inflate pool off the
-    critical path.  From gzip files the batch is bound by inflate on the host cores (2.0 Gbases/s with 16 threads,
-    tools/bench_feed.py), so one GPU worker is the default; with inputs that are already in memory the path of one
-    sample is a chain of short dependent kernels and three or four samples in flight fill the gaps (580 -> 778
-    Gbases/s on 200 Mbp samples, 68 -> 180 on 10 Mbp ones, profiles/r01_notes.md).
+    critical path.  From gzip files the batch is bound by inflate on the host cores, so one GPU worker is the default;
+    with inputs that are already in memory the path of one sample is a chain of short dependent kernels and three or
+    four samples in flight fill the gaps.
 
     ``samples``: iterable of dicts ``{"sample": name, "path": clean .fq(.gz), "labels": [...], "base_sd": float}``;
+    instead of ``"path"`` a sample may carry ``"data"`` (its uncompressed bytes in host memory: bytes / numpy uint8) or
+    ``"device": (pointer, n_bytes)`` (the text already resident on this GPU, 16-byte aligned).
     ``"base_sd": None`` measures the quality flag from the reads on the GPU (quality.py) instead of taking it from a
     fastp report.
     ``seeds``: per-sample seeds (default: the sample's position).  ``engine``: use this one context only.
-    Returns ``{sample: stats}`` (submission order) with the reference's stats keys; a sample with too little data gets
-    ``{"failed_step": "split"}`` exactly as run_clean2img records it (image.py:1020-1027), and ``on_error(sample,
-    exc)`` is called when given."""
+    ``on_result(sample, Result)``: called with every finished sample's counts (``Result.canon``) and pixels.
+    ``write_png_of(sample) -> bool``: which samples get their PNG files (default: all).
+
+    Returns ``{sample: stats}`` (submission order) with the reference's stats keys.  Failures stay with their sample,
+    as in run_clean2img: too little data gives ``{"failed_step": "split"}`` (image.py:1020-1027), a file that cannot be
+    read ``{"failed_step": "split", "error": ...}``, an error on the GPU side (a read beyond the supported length, a
+    CUDA error) ``{"failed_step": "image", "error": ...}``; ``on_error(sample, exc)`` is called when given and the batch
+    goes on with the next sample."""
     import threading
     from collections import deque
     from concurrent.futures import ThreadPoolExecutor
@@ -274,6 +291,7 @@ def images_for_samples(samples, outfolder, kmer_mapping, k=7, mapping_code="varK
         device = int(os.environ.get("VARKODER_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
     tls = threading.local()
     made = []
+    want_canon = on_result is not None
 
     def gpu_job(i, s, buf, n, feeder):
         eng = engine
@@ -287,10 +305,16 @@ def images_for_samples(samples, outfolder, kmer_mapping, k=7, mapping_code="varK
                         is_query=bool(is_query), seed=seed)
         t0 = time.perf_counter()
         try:
-            res = eng.reads_to_images(buf.array[:n], params, table)
+            if "device" in s:
+                ptr, nb = s["device"]
+                res = eng.reads_to_images(int(ptr), params, table, on_device=True, n_bytes=int(nb), want_canon=want_canon)
+            elif buf is None:
+                res = eng.reads_to_images(s["data"], params, table, want_canon=want_canon)
+            else:
+                res = eng.reads_to_images(buf.array[:n], params, table, want_canon=want_canon)
             tm = eng.timings()
             sd = s.get("base_sd", 0)
-            if sd is None:              # no fastp report for this sample: measure it (quality.py)
+            if sd is None and res.status == 0:              # no fastp report for this sample: measure it (quality.py)
                 sd = quality.base_frequency_sd(eng.base_content())
         finally:
             feeder.release(buf)
@@ -299,21 +323,37 @@ def images_for_samples(samples, outfolder, kmer_mapping, k=7, mapping_code="varK
     all_stats = OrderedDict()
     png_jobs = []
 
-    def finish(s, res, tm, dt, sd, feeder):
+    def fail(s, step, exc):
+        if on_error is not None:
+            on_error(s, exc)
+        st = OrderedDict(failed_step=step)
+        if not isinstance(exc, LessThanMinimumData):
+            st["error"] = f"{type(exc).__name__}: {exc}"
+        all_stats[str(s["sample"])] = st
+
+    def finish(s, fut, feeder):
         name = str(s["sample"])
+        try:
+            res, tm, dt, sd = fut.result()
+        except Exception as exc:                     # this sample only; the batch goes on (image.py:1020-1027, 1111-1118)
+            fail(s, "image", exc)
+            return
         if res.status != 0:
-            if on_error is not None:
-                on_error(s, LessThanMinimumData())
-            all_stats[name] = OrderedDict(failed_step="split")
+            fail(s, "split", LessThanMinimumData())
             return
         stats = OrderedDict()
-        stats["splitting_time"] = (tm["upload"] + tm["parse"] + tm["plan_bucket"]) / 1e3
+        split_s, count_s = _stage_times(tm)
+        stats["splitting_time"] = split_s
         stats["splitting_bp_per_file"] = ",".join(str(x) for x in res.levels)
-        stats[str(k) + "mer_counting_time"] = (tm["count"] + tm["reduce_fold"]) / 1e3
+        stats[str(k) + "mer_counting_time"] = count_s
         stats["k" + str(k) + "_img_time"] = dt
         if s.get("base_sd", 0) is None:
             stats["base_frequencies_sd"] = sd
         all_stats[name] = stats
+        if on_result is not None:
+            on_result(s, res)
+        if write_png_of is not None and not write_png_of(s):
+            return
         for lvl, bp in enumerate(res.levels):
             outfile = image_name(name, bp, mapping_code, k)
             folder = _image_folder(outfolder, outfile, subfolder_levels)
@@ -324,20 +364,24 @@ def images_for_samples(samples, outfolder, kmer_mapping, k=7, mapping_code="varK
 
     gpu_pool = ThreadPoolExecutor(max_workers=max(1, int(gpu_workers)), thread_name_prefix="vk-gpu")
     try:
-        with SampleFeeder(samples, path_of=lambda s: s["path"], threads=threads) as feeder:
+        with SampleFeeder(samples, path_of=lambda s: s.get("path"), threads=threads, errors="yield") as feeder:
             inflight = deque()
             for i, s, buf, n in feeder:
+                if n < 0:                            # the file could not be read / inflated: split_fastq would have raised
+                    fail(s, "split", buf)
+                    continue
                 inflight.append((s, gpu_pool.submit(gpu_job, i, s, buf, n, feeder)))
                 while len(inflight) > gpu_workers:
                     s0, fut = inflight.popleft()
-                    finish(s0, *fut.result(), feeder)
+                    finish(s0, fut, feeder)
             while inflight:
                 s0, fut = inflight.popleft()
-                finish(s0, *fut.result(), feeder)
+                finish(s0, fut, feeder)
             for j in png_jobs:
                 j.result()
     finally:
         gpu_pool.shutdown(wait=True)
         for e in made:
             e.close()
-    return all_stats
+    # submission order, whatever order the samples finished or failed in
+    return OrderedDict((str(s["sample"]), all_stats[str(s["sample"])]) for s in samples if str(s["sample"]) in all_stats)
