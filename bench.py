@@ -393,6 +393,7 @@ def run_c5(args, world, rank, local, torch, dist):
     assert eng.synth_fastq(dev.data_ptr(), dev.numel(), shard_bases, READ_LEN, seed=20260118 + 5000, first_read=first) == nbytes
     seg = torch.zeros(64 * 4 ** 7, dtype=torch.int64, device="cuda")
     sp = Params(k=7, min_bp=MIN_BP, max_bp=None, seed=11)
+    parity = check_sharded_parity(eng, table, world, rank, torch, dist) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -435,9 +436,43 @@ def run_c5(args, world, rank, local, torch, dist):
                                    f"all_reduce(int64 x {len(rs.levels) * 4 ** 7 + 128})",
                        "bases_per_step": args.total_bases, "levels": len(rs.levels),
                        "l2_policy": "shards are far larger than L2"},
-            "levels": rs.levels, "level_bases": rs.level_bases,
+            "levels": rs.levels, "level_bases": rs.level_bases, "sharded_parity": parity,
             "kernel_ms_last_step_rank0": tm, "clocks": clocks}), flush=True)
     eng.close()
+
+
+def check_sharded_parity(eng, table, world, rank, torch, dist, n_bases=5_000_000):
+    """Before anything read-sharded is timed: one ~5 Mbp sample cut at record boundaries into `world` shards, counted
+    by all ranks with the real engine and ONE NCCL all-reduce, must give -- on every rank -- the counts and pixels of
+    (a) the same bytes pushed through the unsharded path on that rank's GPU and (b), on rank 0, the CPU oracle (used
+    here as the checker only).  Any difference aborts the bench."""
+    import numpy as np
+    from varkoder_b200 import sharding, synth
+    from varkoder_b200.engine import Params
+    from varkoder_b200.ladder import parse_seed
+    buf = synth.fixed(n_bases, READ_LEN, seed=20260118 + 7000)          # the same bytes on every rank
+    parts = sharding.split_records(buf, world)
+    b, e, _ = parts[rank]
+    sp = Params(k=K, min_bp=100_000, max_bp=None, seed=1234)
+    rs = sharding.sharded_reads_to_images(eng, buf[b:e], sp, table, want_canon=True)
+    whole = eng.reads_to_images(buf, sp, table, want_canon=True)
+    ok = (rs.levels == whole.levels and rs.level_bases == whole.level_bases and rs.level_reads == whole.level_reads
+          and rs.nsites == whole.nsites == n_bases and bool((rs.canon == whole.canon).all())
+          and bool((rs.pixels == whole.pixels).all()) and len(rs.levels) >= 5)
+    what = "sharded == unsharded on every rank"
+    if rank == 0:
+        from oracle import dsk, image as oimg                            # checker only
+        thr = [0 if bp >= n_bases else dsk.threshold(bp, n_bases) for bp in rs.levels]
+        _, expect = dsk.count_levels(buf, K, parse_seed(1234), thr, [1 if bp >= n_bases else 0 for bp in rs.levels], threads=0)
+        ok = ok and bool((rs.canon == expect).all()) and all(
+            bool((rs.pixels[l] == oimg.image_exact(expect[l], table.lut)).all()) for l in range(len(rs.levels)))
+        what += " == CPU oracle (rank 0)"
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.cpu()[0]) != 1:
+        raise SystemExit(f"rank {rank}: read-sharded result differs from the unsharded path / the oracle -- bench aborted")
+    return {"status": "ok", "checked": what, "bases": n_bases, "levels": len(rs.levels), "ranks": world,
+            "compared": "canonical counts of every level (uint64, bit-exact) and every pixel"}
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -664,8 +699,10 @@ def main():
     # ---- N > 1 only: ONE sample of N x 200 Mbp read-sharded over the ranks (BASELINE configs[4] shape): every rank
     # frames and counts its shard, one NCCL all-reduce sums the per-segment histograms, every rank renders.
     sharded = None
+    sharded_parity = None
     if world > 1:
         from varkoder_b200 import sharding
+        sharded_parity = check_sharded_parity(eng, table, world, rank, torch, dist)     # aborts the bench on a mismatch
         seg = torch.zeros(64 * 4 ** K, dtype=torch.int64, device="cuda")
         sp = Params(k=K, min_bp=MIN_BP, max_bp=None, seed=7)
         eng.attach(dev.data_ptr(), total)
@@ -728,6 +765,7 @@ def main():
         }
         if sharded is not None:
             out["read_sharded"] = sharded
+            out["sharded_parity"] = sharded_parity
         out["one_context"] = one_stream
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = run_cpu_baseline(host.numpy())

@@ -214,6 +214,9 @@ def test_stage_functions_write_reference_named_pngs(engine, tmp_path):
                               engine=engine) == {}
     with pytest.raises(Exception, match="Input file has less than minimum data."):
         stages.split_fastq(fq, "sampleA", tmp_path / "x", min_bp=300_000, max_bp=200_000_000, engine=engine)
+    # something else runs on the same context between the stages: the sample's text is no longer resident, and
+    # count_kmers must notice (text generation) and upload it again instead of counting the intruder's reads
+    engine.reads_to_images(synth.fixed(90_000, 150, seed=99).tobytes(), Params(k=7, min_bp=0, max_bp=None, is_query=True), table)
     for f in sorted((tmp_path / "split_fastqs").glob("sampleA@*")):
         cs = stages.count_kmers(f, tmp_path / "7mer_counts", k=7, engine=engine)
         assert "7mer_counting_time" in cs

@@ -16,51 +16,7 @@ from varkoder_b200.ladder import LessThanMinimumData, ladder, parse_seed
 from varkoder_b200.mapping import get_kmer_mapping
 
 
-class OracleEngine:
-    """CPU stand-in with the Engine methods the sharded driver uses; per-segment forward histograms, lex index."""
-    device = 0
-
-    def upload(self, buf):
-        self.buf = bytes(buf)
-        return len(self.buf)
-
-    def parse(self):
-        self.p = dsk.parse_fastq(self.buf)
-        return dict(n_bytes=len(self.buf), n_lines=self.p["n_lines"], n_reads=self.p["n_reads"],
-                    nsites=self.p["nsites_ref"], nsites_true=self.p["nsites_true"])
-
-    def count(self, params, seg_hist_ptr=None):
-        p, k = self.p, params.k
-        nk = 4 ** k
-        nsites = params.nsites_override or p["nsites_ref"]
-        try:
-            levels = ladder(nsites, params.min_bp, params.max_bp, params.is_query)
-            status = 0
-        except LessThanMinimumData:
-            levels, status = [], _lib.VK_LADDER_LESS_THAN_MIN
-        seed = parse_seed(params.seed)
-        member = [dsk.select_reads(p["n_reads"], seed, bp, nsites, params.read_index_base).astype(bool) for bp in levels]
-        long_enough = p["lens"] >= k
-        out = np.ctypeslib.as_array(ctypes.cast(seg_hist_ptr, ctypes.POINTER(ctypes.c_uint64)),
-                                    shape=(_lib.VK_MAX_LEVELS, nk))
-        out[:] = 0
-        reads, bases = [], []
-        for s in range(len(levels)):
-            sel = member[s] & ~(member[s + 1] if s + 1 < len(levels) else np.zeros_like(member[s]))
-            out[s] = dsk.count_forward(self.buf, p["starts"], p["lens"], k, sel.astype(np.uint8))
-            reads.append(int((member[s] & long_enough).sum()))
-            bases.append(int(p["lens"][member[s] & long_enough].sum()))
-        return Result(len(self.buf), p["n_lines"], p["n_reads"], p["nsites_ref"], p["nsites_true"], status,
-                      levels, reads, bases)
-
-    def render(self, table, k, n_levels, seg_hist_ptr=None, want_canon=True):
-        nk = 4 ** k
-        seg = np.ctypeslib.as_array(ctypes.cast(seg_hist_ptr, ctypes.POINTER(ctypes.c_uint64)),
-                                    shape=(_lib.VK_MAX_LEVELS, nk))
-        cum = np.cumsum(seg[:n_levels][::-1], axis=0, dtype=np.uint64)[::-1]
-        canon = np.stack([dsk.fold_canonical(c, k) for c in cum]) if n_levels else np.zeros((0, nk), np.uint64)
-        pixels = np.stack([oimg.image_exact(c, table.lut) for c in canon]) if n_levels and table is not None else None
-        return (canon if want_canon else None), pixels
+from tests.helpers import OracleEngine  # noqa: E402  (CPU stand-in for the CUDA engine)
 
 
 def test_assign_samples_lpt():

@@ -113,7 +113,7 @@ struct vk_ctx {
     // the first node of every step
     vk::StepArgs* args_d = nullptr;
     vk::StepArgs* args_h = nullptr;
-    bool use_packed = true;         // VK_PACKED=0: the count kernels classify the text themselves (round-1 path) instead of
+    bool use_packed = false;        // VK_PACKED=1 (measured, a net loss); 0: the count kernels classify the text themselves (round-1 path) instead of
                                     // reading the 2-bit codes + validity bits the framing pass writes
     DevBuf<uint4> codes;            // 2-bit codes of every text byte, 16 B per 64 text bytes (parse_mask_kernel<true>)
     DevBuf<uint2> valid;            // validity bits, 8 B per 64 text bytes
@@ -200,9 +200,12 @@ void enqueue_args(vk_ctx* c, const vk_params* params)
     a.pa.exact_layout = c->exact_layout ? 1u : 0u;
     a.pa.test_tight = c->test_tight ? 1u : 0u;
 }
-void enqueue_args_copy(vk_ctx* c)
+// first kernel of a step: StepArgs host -> device, and (rescan) the framing accumulators cleared (vk_parse.cuh K0)
+void enqueue_begin(vk_ctx* c, bool rescan)
 {
-    CU(cudaMemcpyAsync(c->args_d, c->args_h, sizeof(vk::StepArgs), cudaMemcpyHostToDevice, c->stream));
+    launch(c, vk::step_begin_kernel, dim3(8), dim3(1024), 0, reinterpret_cast<const uint32_t*>(c->args_h),
+           reinterpret_cast<uint32_t*>(c->args_d), c->plan_d, c->tile_count.p, (uint32_t)c->tile_count.cap, rescan ? 1 : 0);
+    CU(cudaGetLastError());
 }
 
 // buffers of the framing pass for a text of n bytes (never allocates inside a graph capture: called before it)
@@ -225,9 +228,8 @@ void ensure_parse_buffers(vk_ctx* c, uint64_t n)
 void enqueue_parse(vk_ctx* c, bool rescan = true)
 {
     using namespace vk;
+    enqueue_begin(c, rescan);
     if (rescan) {
-        CU(cudaMemsetAsync(c->plan_d, 0, offsetof(Plan, n_lines), c->stream));      // parse fields: counters, sums, ticket
-        CU(cudaMemsetAsync(c->tile_count.p, 0, sizeof(uint32_t) * c->tile_count.cap, c->stream));
         const int grid = c->n_sms * 16;
         if (c->use_packed)
             launch(c, parse_mask_kernel<true>, dim3(grid), dim3(kParseThreads), 0, (const StepArgs*)c->args_d, c->masks.p,
@@ -575,7 +577,6 @@ void drop_graphs(vk_ctx* c)
 void enqueue_step(vk_ctx* c, const Mapping& m, int k, int max_levels_out)
 {
     const size_t n_pix = (size_t)m.side * m.side;
-    enqueue_args_copy(c);
     enqueue_parse(c);
     c->mark(EV_PARSE);
     enqueue_count(c, k, c->seg_hist.p);
@@ -777,7 +778,6 @@ int vk_parse(vk_ctx* c, vk_stats* out)
         with_table_retry(c, [&] {
             if (!c->ev_valid[EV_UPLOAD]) { c->mark(EV_START); c->mark(EV_UPLOAD); }
             enqueue_args(c, nullptr);
-            enqueue_args_copy(c);
             enqueue_parse(c);
             c->mark(EV_PARSE);
             fetch_plan(c);
@@ -806,7 +806,6 @@ int vk_count(vk_ctx* c, const vk_params* p, uint64_t* seg_hist_dev, vk_result* o
         with_table_retry(c, [&] {
             if (!c->ev_valid[EV_UPLOAD]) { c->mark(EV_START); c->mark(EV_UPLOAD); }
             enqueue_args(c, p);
-            enqueue_args_copy(c);
             enqueue_parse(c, !c->parsed);         // framing found by vk_parse is kept; the ladder needs the parameters
             c->mark(EV_PARSE);
             enqueue_count(c, p->k, sh);

@@ -80,27 +80,38 @@ __device__ __forceinline__ uint32_t smem_add_ret(uint32_t shared_addr, uint32_t 
     return old;
 }
 
-// SIMD-in-register classification of 4 text bytes (one 32-bit word x).
-//   y     = per byte the 2-bit code (ascii >> 1) & 3                      (A0 C1 T2 G3)
-//   pack  : (y * 0x01041040) puts the four codes, densely packed, into byte 3 (partial products never overlap)
-//   valid : a byte is one of ACGTacgt iff it equals the letter rebuilt from its own code:
-//           letter = 'A' + 2*code + 15*[code == T]   ->  A 0x41, C 0x43, G 0x47, T 0x54;  bit 5 (case) is ignored.
-//           The rebuild runs on the FMA pipe (IMAD), which the rest of the loop leaves idle.
+// SIMD-in-register classification of 4 text bytes (one 32-bit word x).  The loop is bound by the ALU pipe (LOP3 / SHF /
+// PRMT) and by the shared-memory data pipe while the FMA pipe idles, so everything that can be a multiply-add is one:
+//   y     = x & 0x06060606: the 2-bit code (ascii >> 1) & 3 (A0 C1 T2 G3) still at bits 1-2 of each byte
+//   pack  : y * 0x00820820 puts the four codes, densely packed, into byte 3 (no two partial products share a bit there)
+//   T?    : y * 3 is 0, 6, 12, 18 for A, C, T, G -- only 12 has bit 3 set
+//   valid : a byte is one of ACGTacgt iff, case bit cleared, it is the letter its own code names.  'A' 0x41, 'C' 0x43,
+//           'G' 0x47 agree outside bits 1-2, so (x & 0xD9) ^ 0x41 is 0 for them (mask 0xD9 drops bits 1, 2 and the case
+//           bit 5) and 0x11 for 'T' 0x54: d = ((x & 0xD9) ^ 0x41) ^ (T? ? 0x11 : 0) is 0 exactly for the eight letters.
+//           Zero bytes of d by the carry-free test; bit 7 of d is bit 7 of x, so it is taken from x directly.
+//   6 ALU-pipe + 4 FMA-pipe instructions per word (the first version of this kernel: 9 + 2).
 struct Cls4z {
     uint32_t packed_hi;   // byte 3 = 4 packed codes
     uint32_t z;           // 0x80 in every byte that is one of ACGTacgt
 };
-__device__ __forceinline__ Cls4z classify4z(uint32_t x)
+__device__ __forceinline__ uint32_t mad_lo_op(uint32_t a, uint32_t b, uint32_t c)      // a * b + c as IMAD even when b is 1
 {
-    const uint32_t y = (x >> 1) & 0x03030303u;
-    const uint32_t t = (x >> 2) & ~(x >> 1) & 0x01010101u;          // 1 where the code is T (10b)
-    uint32_t e0;                                                      // 'A' + 2*code: bits 1,2 of 'A' are clear, so OR
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(e0) : "r"(x), "r"(0x06060606u), "r"(0x41414141u));
-    const uint32_t e = t * 15u + e0;                                  // expected upper-case letter per byte
-    const uint32_t d = (x & 0xDFDFDFDFu) ^ e;                         // 0 in a byte <=> valid
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ Cls4z classify4z(uint32_t x, uint32_t one)
+{
+    const uint32_t y = x & 0x06060606u;
+    const uint32_t t8 = (y * 3u) & 0x08080808u;
+    const uint32_t t11 = (t8 >> 3) * 0x11u;
+    uint32_t d1, dm;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(d1) : "r"(x), "r"(0xD9D9D9D9u), "r"(0x41414141u));      // (x & M) ^ C
+    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(dm) : "r"(d1), "r"(t11), "r"(0x7F7F7F7Fu));            // (d1 ^ t11) & 0x7F..
+    const uint32_t sv = mad_lo_op(dm, one, 0x7F7F7F7Fu);                                                 // + 0x7F.. on the FMA pipe
     Cls4z c;
-    c.z = ~(((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
-    c.packed_hi = y * 0x01041040u;
+    asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(c.z) : "r"(sv), "r"(x), "r"(0x80808080u));             // ~(sv | x) & 0x80..
+    c.packed_hi = y * 0x00820820u;
     return c;
 }
 // 8 validity flags of two classified words in byte 3: bits 24..27 = word a (bytes 0..3), bits 28..31 = word b.
@@ -291,8 +302,9 @@ struct Decoded {
     uint32_t Cc;         // codes of the K-1 bases to the left (first at bit 0)
     uint32_t E;          // bit b: the K-mer that ENDS at base b is to be counted
 };
+// one: the constant 1 in a register ptxas cannot see through (from a kernel argument), see classify4z
 template <int K, bool PACKED = false>
-__device__ __forceinline__ Decoded decode_chunk(const Chunk& cur, uint32_t& carry, uint32_t lane, int breaklen)
+__device__ __forceinline__ Decoded decode_chunk(const Chunk& cur, uint32_t& carry, uint32_t lane, int breaklen, uint32_t one)
 {
     constexpr int KM1 = K - 1;
     constexpr uint32_t FULL = 0xffffffffu;
@@ -303,8 +315,8 @@ __device__ __forceinline__ Decoded decode_chunk(const Chunk& cur, uint32_t& carr
         d.Phi = cur.wa.y;
         V = cur.wa.z & cur.range;
     } else {
-        const Cls4z c0 = classify4z(cur.wa.x), c1 = classify4z(cur.wa.y), c2 = classify4z(cur.wa.z), c3 = classify4z(cur.wa.w);
-        const Cls4z c4 = classify4z(cur.wb.x), c5 = classify4z(cur.wb.y), c6 = classify4z(cur.wb.z), c7 = classify4z(cur.wb.w);
+        const Cls4z c0 = classify4z(cur.wa.x, one), c1 = classify4z(cur.wa.y, one), c2 = classify4z(cur.wa.z, one), c3 = classify4z(cur.wa.w, one);
+        const Cls4z c4 = classify4z(cur.wb.x, one), c5 = classify4z(cur.wb.y, one), c6 = classify4z(cur.wb.z, one), c7 = classify4z(cur.wb.w, one);
         const uint32_t v01 = gather8(c0.z, c1.z), v23 = gather8(c2.z, c3.z);
         const uint32_t v45 = gather8(c4.z, c5.z), v67 = gather8(c6.z, c7.z);
         V = __byte_perm(__byte_perm(v01, v23, 0x0073), __byte_perm(v45, v67, 0x0073), 0x5410) & cur.range;
@@ -393,6 +405,7 @@ count_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __re
     pdl_wait();
     const uint4* __restrict__ text16 = reinterpret_cast<const uint4*>(sa->text);
     const int breaklen = sa->pa.p.breaklength;
+    const uint32_t one = (uint32_t)(sa->n_bytes >> 62) + 1u;          // 1 (texts are shorter than 2^40), but not to ptxas
     static_assert(MODE == kSmem32 || MODE == kGlobal, "count16_kernel is the kSmem16 kernel");
     constexpr uint32_t NK = 1u << (2 * K);
     constexpr int KM1 = K - 1;
@@ -423,7 +436,7 @@ count_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __re
     Chunk cur = cs.fetch();
     while (__ballot_sync(FULL, cur.range != 0) != 0) {
         const Chunk nxt = cs.fetch();
-        const Decoded d = decode_chunk<K, PACKED>(cur, carry, lane, breaklen);
+        const Decoded d = decode_chunk<K, PACKED>(cur, carry, lane, breaklen, one);
         const uint64_t Wa = ((uint64_t)d.Cc | ((uint64_t)d.Plo << (2 * KM1))) << 2;
         const uint64_t Wb = ((uint64_t)(d.Plo >> (32 - 2 * KM1)) | ((uint64_t)d.Phi << (2 * KM1))) << 2;
         emit16<K, MODE>(Wa, d.E & 0xFFFFu, hist_addr, trash_addr, gh);
@@ -513,6 +526,7 @@ count16_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __
     pdl_wait();
     const uint4* __restrict__ text16 = reinterpret_cast<const uint4*>(sa->text);
     const int breaklen = sa->pa.p.breaklength;
+    const uint32_t one = (uint32_t)(sa->n_bytes >> 62) + 1u;          // 1 (texts are shorter than 2^40), but not to ptxas
     static_assert(K == 7 || K == 8, "16-bit bins: k = 8 directly, k = 7 through pairs");
     constexpr uint32_t NK = 1u << (2 * K);
     constexpr int KM1 = K - 1;
@@ -541,7 +555,7 @@ count16_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __
     Chunk cur = cs.fetch();
     while (__ballot_sync(FULL, cur.range != 0) != 0) {
         const Chunk nxt = cs.fetch();
-        const Decoded d = decode_chunk<K, PACKED>(cur, carry, lane, breaklen);
+        const Decoded d = decode_chunk<K, PACKED>(cur, carry, lane, breaklen, one);
         const uint64_t Wa = ((uint64_t)d.Cc | ((uint64_t)d.Plo << (2 * KM1))) << 2;
         const uint64_t Wb = ((uint64_t)(d.Plo >> (32 - 2 * KM1)) | ((uint64_t)d.Phi << (2 * KM1))) << 2;
         if (K == 8) {
@@ -694,6 +708,7 @@ count9h_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __
     pdl_wait();
     const uint4* __restrict__ text16 = reinterpret_cast<const uint4*>(sa->text);
     const int breaklen = sa->pa.p.breaklength;
+    const uint32_t one = (uint32_t)(sa->n_bytes >> 62) + 1u;          // 1 (texts are shorter than 2^40), but not to ptxas
     constexpr int K = 9;
     constexpr uint32_t NB = 65536u;               // bins of one half
     constexpr uint32_t FULL = 0xffffffffu;
@@ -722,7 +737,7 @@ count9h_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __
     Chunk cur = cs.fetch();
     while (__ballot_sync(FULL, cur.range != 0) != 0) {
         const Chunk nxt = cs.fetch();
-        const Decoded d = decode_chunk<K, PACKED>(cur, carry, lane, breaklen);
+        const Decoded d = decode_chunk<K, PACKED>(cur, carry, lane, breaklen, one);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             // 24 bases: the 9-mers that end at chunk positions 16h .. 16h+15 (8 bases in front of the first one)

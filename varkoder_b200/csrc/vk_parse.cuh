@@ -38,6 +38,24 @@ __device__ __forceinline__ uint32_t nl16(uint4 w)
     return nl4(w.x) | (nl4(w.y) << 4) | (nl4(w.z) << 8) | (nl4(w.w) << 12);
 }
 
+// ---- K0: the first kernel of every step.  Copies the step's argument block from the pinned HOST buffer the caller has
+// just written (the pointer is device-accessible: unified addressing) into device memory, where every later kernel
+// reads it, and clears what the framing pass accumulates into.  A kernel rather than a copy-engine memcpy + two
+// memsets: the hand-over from the copy engine to the first compute kernel cost ~45 us of a 300 us step.
+constexpr uint32_t kStepArgWords = (uint32_t)(sizeof(StepArgs) / 4);
+static_assert(sizeof(StepArgs) % 4 == 0, "StepArgs is copied as 32-bit words");
+__global__ void __launch_bounds__(1024)
+step_begin_kernel(const uint32_t* __restrict__ args_host, uint32_t* __restrict__ args_dev, Plan* __restrict__ plan,
+                  uint32_t* __restrict__ tile_count, uint32_t tile_cap, int rescan)
+{
+    pdl_wait();
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < kStepArgWords) args_dev[g] = args_host[g];
+    if (!rescan) return;
+    if (g < offsetof(Plan, n_lines) / 4) reinterpret_cast<uint32_t*>(plan)[g] = 0;        // parse fields: counters, sums, ticket
+    for (uint32_t i = g; i < tile_cap; i += gridDim.x * blockDim.x) tile_count[i] = 0;
+}
+
 // ---- 2-bit pack (K1a with PACK): the same pass that finds the newlines also classifies every byte, blind to the
 // framing: code = (byte >> 1) & 3 (A0 C1 T2 G3, the dsk code; vk_count.cuh) and valid = byte is one of ACGTacgt.
 // Layout ("position layout"): text byte i has its code at bits [2 (i & 31), +2) of codes64[i >> 5] and its validity

@@ -92,6 +92,7 @@ class Engine:
         self._slot_keys = [None] * 4
         self._next_slot = 0
         self._keep = None
+        self.text_generation = 0      # bumped whenever the context's resident text is replaced (stages._resident)
 
     def close(self):
         if self._ctx:
@@ -126,11 +127,13 @@ class Engine:
     # ------------------------------------------------------------------ stages
     def upload(self, host_bytes):
         ptr, n, keep = _host_ptr(host_bytes)
+        self.text_generation += 1
         self._check(self._L.vk_upload(self._ctx, ptr, n))
         return n
 
     def attach(self, dev_ptr, n_bytes, keepalive=None):
         self._keep = keepalive
+        self.text_generation += 1
         self._check(self._L.vk_attach(self._ctx, dev_ptr, n_bytes))
 
     def parse(self):
@@ -183,6 +186,7 @@ class Engine:
         canon = np.empty((L, nk), dtype=np.uint64) if want_canon else None
         r = _lib.VkResult()
         p = params.to_c()
+        self.text_generation += 1
         self._check(self._L.vk_reads_to_images(self._ctx, ptr, n, 1 if on_device else 0, C.byref(p), slot,
                                                int(max_levels), C.byref(r),
                                                canon.ctypes.data if canon is not None else None, pixels.ctypes.data))

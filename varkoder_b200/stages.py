@@ -160,12 +160,17 @@ _SAMPLE = {}      # the sample currently resident on the GPU of this process: so
 
 
 def _resident(source, eng):
+    """the framed text of ``source`` on the GPU.  The engine keeps ONE text; anything else that ran on it since
+    (another sample, a fused call, a sharded count) has replaced ours -- its text generation tells -- and the sample is
+    uploaded again rather than counted from someone else's reads."""
     st = _SAMPLE.get("state")
     key = (str(source), os.path.getmtime(source), id(eng))
-    if st is None or st["key"] != key:
+    if st is None or st["key"] != key or st["gen"] != getattr(eng, "text_generation", None):
         data = read_clean_fastq(source)
         eng.upload(data)
-        st = dict(key=key, stats=eng.parse(), counts={})
+        stats = eng.parse()
+        st = dict(key=key, stats=stats, counts=st["counts"] if st is not None and st["key"] == key else {},
+                  gen=getattr(eng, "text_generation", None))
         _SAMPLE["state"] = st
     return st
 
