@@ -52,6 +52,30 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def hbm_probe(torch, nbytes=1 << 30, reps=6):
+    """what THIS box's HBM does on a plain device-to-device copy (read + write bytes, best of `reps`, CUDA events): the
+    boxes of the pool differ by several per cent, and the framing kernels of this path are HBM-bound, so the number is
+    recorded next to the official denominator (MEASURED_PEAKS.json, measured by the driver the same way)."""
+    try:
+        a = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        b = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        a.zero_()
+        best = None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            b.copy_(a)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None or ms < best else best
+        del a, b
+        torch.cuda.empty_cache()
+        return 2 * nbytes / (best * 1e-3) / 1e9
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """SM clock and clock-event reasons sampled DURING the timed region: NVML polled from a thread every ~2 ms
     (a step lasts ~0.5 ms, so nvidia-smi's 100 ms loop would miss short runs); nvidia-smi -lms is the fallback."""
@@ -401,14 +425,14 @@ def run_c5(args, world, rank, local, torch, dist):
         torch.cuda.synchronize()
 
     def step():
-        eng.attach(dev.data_ptr(), nbytes)
         if world > 1:
-            return sharding.sharded_reads_to_images(eng, None, sp, table, seg_hist=seg)
-        return eng.reads_to_images(dev.data_ptr(), sp, table, on_device=True, n_bytes=nbytes, max_levels=16)
+            return sharding.fused_sharded_reads_to_images(eng, dev.data_ptr(), sp, table, on_device=True, n_bytes=nbytes,
+                                                          max_levels=18)
+        return eng.reads_to_images(dev.data_ptr(), sp, table, on_device=True, n_bytes=nbytes, max_levels=18)
 
     for _ in range(max(2, min(args.warmup, 3))):
         rs = step()
-    assert rs.nsites == args.total_bases and rs.levels[0] == args.total_bases and rs.level_bases[0] == args.total_bases
+    assert rs.levels[0] == args.total_bases and rs.level_bases[0] == args.total_bases and rs.n_reads == total_reads
     steps = max(1, min(args.steps, 20))
     sampler = ClockSampler(local)
     if rank == 0:
@@ -432,8 +456,8 @@ def run_c5(args, world, rank, local, torch, dist):
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"configs[4]: ONE sample of {args.total_bases} bases (read length 150), k=7, cgr, -M 0 "
                                    f"({len(rs.levels)} levels), read-sharded over {world} GPU(s): shards of {shard_bases} bases "
-                                   f"({nbytes / 1e9:.1f} GB of text) resident per GPU, all_gather(2 scalars) + ONE NCCL "
-                                   f"all_reduce(int64 x {len(rs.levels) * 4 ** 7 + 128})",
+                                   f"({nbytes / 1e9:.1f} GB of text) resident per GPU; per step and rank ONE enqueue on the library's stream: "
+                                   f"framing, ncclAllGather(2 x u64), ladder, count, ONE ncclAllReduce(u64 x {18 * 4 ** 7 + 130}), images",
                        "bases_per_step": args.total_bases, "levels": len(rs.levels),
                        "l2_policy": "shards are far larger than L2"},
             "levels": rs.levels, "level_bases": rs.level_bases, "sharded_parity": parity,
@@ -454,12 +478,15 @@ def check_sharded_parity(eng, table, world, rank, torch, dist, n_bases=5_000_000
     parts = sharding.split_records(buf, world)
     b, e, _ = parts[rank]
     sp = Params(k=K, min_bp=100_000, max_bp=None, seed=1234)
-    rs = sharding.sharded_reads_to_images(eng, buf[b:e], sp, table, want_canon=True)
+    rs = sharding.fused_sharded_reads_to_images(eng, buf[b:e], sp, table, want_canon=True)       # the form that is timed
+    r_staged = sharding.sharded_reads_to_images(eng, buf[b:e], sp, table, want_canon=True)        # torch.distributed form
     whole = eng.reads_to_images(buf, sp, table, want_canon=True)
-    ok = (rs.levels == whole.levels and rs.level_bases == whole.level_bases and rs.level_reads == whole.level_reads
-          and rs.nsites == whole.nsites == n_bases and bool((rs.canon == whole.canon).all())
-          and bool((rs.pixels == whole.pixels).all()) and len(rs.levels) >= 5)
-    what = "sharded == unsharded on every rank"
+    ok = len(rs.levels) >= 5
+    for r in (rs, r_staged):
+        ok = ok and (r.levels == whole.levels and r.level_bases == whole.level_bases and r.level_reads == whole.level_reads
+                     and r.n_reads == whole.n_reads and bool((r.canon == whole.canon).all())
+                     and bool((r.pixels == whole.pixels).all()))
+    what = "sharded (library-issued NCCL on the engine's stream; and the staged torch.distributed form) == unsharded on every rank"
     if rank == 0:
         from oracle import dsk, image as oimg                            # checker only
         thr = [0 if bp >= n_bases else dsk.threshold(bp, n_bases) for bp in rs.levels]
@@ -703,30 +730,34 @@ def main():
     if world > 1:
         from varkoder_b200 import sharding
         sharded_parity = check_sharded_parity(eng, table, world, rank, torch, dist)     # aborts the bench on a mismatch
-        seg = torch.zeros(64 * 4 ** K, dtype=torch.int64, device="cuda")
         sp = Params(k=K, min_bp=MIN_BP, max_bp=None, seed=7)
-        eng.attach(dev.data_ptr(), total)
-        for _ in range(2):
-            rs = sharding.sharded_reads_to_images(eng, None, sp, table, seg_hist=seg)
-        assert rs.nsites == world * n_bases and rs.levels[0] == world * n_bases
-        s_steps = max(1, min(args.steps, 50))
+        ML = 16
+
+        def sharded_step():
+            return sharding.fused_sharded_reads_to_images(eng, dev.data_ptr(), sp, table, on_device=True, n_bytes=total,
+                                                          max_levels=ML)
+        for _ in range(3):
+            rs = sharded_step()
+        assert rs.n_reads == world * n_reads_sample and rs.levels[0] == world * n_bases and rs.level_bases[0] == world * n_bases
+        s_steps = max(1, min(args.steps, 100))
         barrier()
         t0 = time.perf_counter()
         for _ in range(s_steps):
-            eng.attach(dev.data_ptr(), total)
-            rs = sharding.sharded_reads_to_images(eng, None, sp, table, seg_hist=seg)
+            rs = sharded_step()
         barrier()
         sh_ms = 1e3 * (time.perf_counter() - t0) / s_steps
         sharded = {"workload": f"one sample of {world}x{n_bases} bases read-sharded over {world} GPUs, k={K} {MAPPING}, "
-                               f"{len(rs.levels)} levels, all_gather(2 scalars) + ONE NCCL all_reduce(int64 x {len(rs.levels) * 4 ** K + 128})",
+                               f"{len(rs.levels)} levels; per step and rank ONE enqueue: framing, ncclAllGather(2 x u64), ladder, "
+                               f"count, ONE ncclAllReduce(u64 x {ML * 4 ** K + 130}) on the library's stream, images; one host sync",
                    "steps": s_steps, "ms_per_step_wall": sh_ms, "value": world * n_bases / (sh_ms * 1e-3) / 1e9,
-                   "unit": "Gbases/s"}
+                   "unit": "Gbases/s", "level_bases": rs.level_bases}
 
     t = torch.tensor([dev_ms, wall_ms, e2e_ms, per_kernel["count"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, wall_ms, e2e_ms, count_ms = [float(x) for x in t.cpu()]
 
+    probe_gbs = hbm_probe(torch) if rank == 0 else None
     if rank == 0:
         peak, peak_src = measured_peaks()
         steps = args.steps
@@ -754,6 +785,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "count_kernel<7,smem>" if K <= 7 else ("count9h_kernel" if K == 9 else f"count16_kernel<{K}>"), "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n_bases * BYTES_PER_BASE,
+                         "hbm_copy_probe_this_box_gbs": probe_gbs,
                          "kernel_ms": count_s * 1e3,
                          "whole_step_frac": (n_bases * BYTES_PER_BASE / (dev_ms * 1e-3 / steps) / 1e9) / peak},
             "ms_per_step_wall": wall_ms / steps,

@@ -198,6 +198,27 @@ uint64_t vk_bucket_retries(vk_ctx* ctx);
 int vk_synth_fastq(vk_ctx* ctx, void* dev_bytes, uint64_t capacity, uint64_t n_bases, int read_len, uint64_t seed,
                    uint64_t first_read, uint64_t* n_out);
 
+/*
+ * Read-sharded samples (one sample spread over the GPUs of a box): every rank frames and counts its
+ * contiguous shard of the records, and two exchange steps run ON THE CONTEXT'S STREAM between the kernels, with no host
+ * synchronisation in between: an all-gather of two integers per rank (records and bases of the shard -> sample-wide base
+ * count for the ladder, global index of the shard's first record for the seeded priorities) and ONE all-reduce of the
+ * per-segment histograms with the per-segment totals behind them.  NCCL is opened at run time (dlopen of libnccl.so.2, the
+ * same library a torch.distributed process already holds); this library does not link against it.
+ *
+ * vk_comm_unique_id: 128 bytes made on one rank and handed to all (any transport: torch.distributed, MPI, a file).
+ * vk_comm_init:      collective over all ranks; one communicator per context.
+ * vk_sharded_reads_to_images: collective; arguments as vk_reads_to_images, `text` = this rank's shard (whole records).
+ *   Every rank receives the sample-wide result (ladder, realised reads / bases, counts, pixels); stats.n_reads is the
+ *   sample's record count, stats.n_bytes / n_lines / nsites describe the local shard.  max_levels_out rows are exchanged;
+ *   a ladder with more levels is an error (VK_ERANGE), so pass the bound of the largest sample (16 covers 30 Gbp).
+ */
+int vk_comm_unique_id(void* out128);
+int vk_comm_init(vk_ctx* ctx, const void* unique_id128, int rank, int world);
+int vk_comm_destroy(vk_ctx* ctx);
+int vk_sharded_reads_to_images(vk_ctx* ctx, const void* text, uint64_t n_bytes, int on_device, const vk_params* params,
+                               int slot, int max_levels_out, vk_result* result, uint64_t* canon_host, uint8_t* pixels_host);
+
 /* Same generator with VARIABLE read lengths (the shape of fastp-cleaned, merged
  * reads): lengths uniform min_len..max_len, short_per_10000 / 10000 of the reads shorter than k (0..k-1 bases, empty
  * reads included).  dev_bytes = NULL only reports the size.  *n_out = bytes, *n_bases_out = bases (nullable). */

@@ -325,6 +325,25 @@ def test_sharded_driver_with_real_engine_nccl(engine):
         assert (res.canon == ref.canon).all() and (res.pixels == ref.pixels).all()
         expect = oracle_levels(buf, 7, 99, res.levels, res.nsites)
         assert (res.canon == expect).all()
+        # the fused form: the library opens NCCL itself and issues the all-gather and the all-reduce on its own stream
+        for on_device in (False, True):
+            if on_device:
+                d = torch.from_numpy(np.frombuffer(buf, dtype=np.uint8).copy()).cuda()
+                r2 = sharding.fused_sharded_reads_to_images(engine, d.data_ptr(), params, table, on_device=True,
+                                                            n_bytes=len(buf), want_canon=True)
+            else:
+                r2 = sharding.fused_sharded_reads_to_images(engine, buf, params, table, want_canon=True)
+            assert r2.levels == ref.levels and r2.level_bases == ref.level_bases and r2.level_reads == ref.level_reads
+            assert r2.n_reads == ref.n_reads and (r2.canon == ref.canon).all() and (r2.pixels == ref.pixels).all()
+        # too few exchanged rows for the ladder is an error, not a silent truncation
+        with pytest.raises(Exception, match="max_levels_out"):
+            sharding.fused_sharded_reads_to_images(engine, buf, params, table, max_levels=2)
+        # tiny records overflow the read table: all ranks repeat the step together (the flags ride in the all-reduce)
+        tiny = b"".join(b"@\nACGTACG\n+\nIIIIIII\n" for _ in range(7000))
+        t5 = get_kmer_mapping(5, "cgr")
+        r3 = sharding.fused_sharded_reads_to_images(engine, tiny, Params(k=5, min_bp=0, max_bp=None, is_query=True), t5, want_canon=True)
+        assert r3.n_reads == 7000 and (r3.canon[0] == dsk.canonical_counts(tiny, 5)).all()
+        engine.comm_destroy()
     finally:
         dist.destroy_process_group()
 

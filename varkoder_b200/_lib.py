@@ -20,6 +20,7 @@ SYMBOLS = [
     "vk_base_content",
     "vk_last_timings", "vk_set_fine_timing", "vk_launch_count", "vk_bucket_retries", "vk_synth_fastq",
     "vk_synth_fastq_variable", "vk_graph_stats",
+    "vk_comm_unique_id", "vk_comm_init", "vk_comm_destroy", "vk_sharded_reads_to_images",
 ]
 
 
@@ -84,6 +85,11 @@ def load():
                                  C.POINTER(C.c_uint64)]
     L.vk_synth_fastq_variable.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.vk_comm_unique_id.argtypes = [vp]
+    L.vk_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.vk_comm_destroy.argtypes = [vp]
+    L.vk_sharded_reads_to_images.argtypes = [vp, vp, C.c_uint64, C.c_int, C.POINTER(VkParams), C.c_int, C.c_int,
+                                             C.POINTER(VkResult), vp, vp]
     L.vk_graph_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
     for name in SYMBOLS:
         fn = getattr(L, name)

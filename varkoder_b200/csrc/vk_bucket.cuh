@@ -26,7 +26,7 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
 {
     pdl_wait();
     const int k = sa->pa.p.k;
-    const uint64_t seed = sa->pa.p.seed, read_index_base = sa->pa.p.read_index_base;
+    const uint64_t seed = sa->pa.p.seed, read_index_base = plan->read_index_base;
     constexpr uint32_t FULL = 0xffffffffu;
     __shared__ uint32_t s_cnt[kMaxLevels], s_all[kMaxLevels];
     __shared__ unsigned long long s_len[kMaxLevels];

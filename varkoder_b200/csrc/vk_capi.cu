@@ -3,8 +3,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <string>
 #include <vector>
+
+#include <nccl.h>      // types only: the library is opened at run time (dlopen), nothing links against it
 
 #include "vk_bucket.cuh"
 #include "vk_common.cuh"
@@ -132,6 +135,11 @@ struct vk_ctx {
     bool capturing = false;
     uint32_t captured_kernels = 0;
 
+    // read-sharded samples: an NCCL communicator of this context's own (vk_comm_init), collectives on the context's stream
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    DevBuf<unsigned long long> shard_table;      // [world][2] (records, bases) after the all-gather; [world] = send slot
+
     DevBuf<uint64_t> tile_status, masks, starts, ends, sorted;      // tile_status = exclusive newline prefix per tile
     DevBuf<uint32_t> tile_count, warp_count;
     DevBuf<uint32_t> slabs;
@@ -199,6 +207,7 @@ void enqueue_args(vk_ctx* c, const vk_params* params)
         a.pa.n_count_ctas = (uint32_t)(c->n_sms * c->count_ctas_per_sm / 2 + c->count_extra9);
     a.pa.exact_layout = c->exact_layout ? 1u : 0u;
     a.pa.test_tight = c->test_tight ? 1u : 0u;
+    a.pa.shard_table = nullptr;
 }
 // first kernel of a step: StepArgs host -> device, and (rescan) the framing accumulators cleared (vk_parse.cuh K0)
 void enqueue_begin(vk_ctx* c, bool rescan)
@@ -225,7 +234,7 @@ void ensure_parse_buffers(vk_ctx* c, uint64_t n)
 
 // ---- K1: framing -------------------------------------------------------------------------------------
 // Grids do not depend on the sample (grid-stride loops over sa->n_tiles), so the same launches serve every step.
-void enqueue_parse(vk_ctx* c, bool rescan = true)
+void enqueue_parse(vk_ctx* c, bool rescan = true, bool with_plan = true)
 {
     using namespace vk;
     enqueue_begin(c, rescan);
@@ -245,6 +254,7 @@ void enqueue_parse(vk_ctx* c, bool rescan = true)
                (const StepArgs*)c->args_d, 0, c->starts.p, c->ends.p, c->plan_d);
         CU(cudaGetLastError());
     }
+    if (!with_plan) return;        // read-sharded: the shards' statistics are exchanged first
     launch(c, plan_kernel, dim3(1), dim3(64), 0, (const StepArgs*)c->args_d, c->starts.p, c->ends.p, c->plan_d);
     CU(cudaGetLastError());
 }
@@ -523,6 +533,51 @@ void check_params(const vk_params* p)
 
 uint64_t reads_bound(uint64_t n_bytes) { return n_bytes / 24 + 1024; }
 
+// ---- NCCL, opened at run time -----------------------------------------------------------------------------
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi& nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        // the soname first: a process that already uses NCCL (torch.distributed) gets the very same library
+        const char* names[] = {getenv("VK_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* nme : names) {
+            if (!nme || !*nme) continue;
+            api.handle = dlopen(nme, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (api.handle) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+            api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+        }
+    }
+    if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.AllGather)
+        throw ApiError{VK_ESTATE, "libnccl.so.2 could not be opened (set VK_NCCL_LIB to its path)"};
+    return api;
+}
+#define NC(x)                                                                                             \
+    do {                                                                                                  \
+        ncclResult_t r_ = (x);                                                                            \
+        if (r_ != ncclSuccess) {                                                                          \
+            NcclApi& a_ = nccl_api();                                                                     \
+            throw ApiError{VK_ECUDA, std::string("NCCL error in " #x ": ") + (a_.GetErrorString ? a_.GetErrorString(r_) : "?")}; \
+        }                                                                                                 \
+    } while (0)
+
 template <typename F>
 int guarded(F&& f)
 {
@@ -682,6 +737,11 @@ int vk_ctx_destroy(vk_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     drop_graphs(c);
+    if (c->comm) {
+        try { nccl_api().CommDestroy(c->comm); } catch (...) {}
+        c->comm = nullptr;
+    }
+    c->shard_table.release();
     if (c->args_d) cudaFree(c->args_d);
     if (c->args_h) cudaFreeHost(c->args_h);
     c->codes.release();
@@ -1056,6 +1116,122 @@ int vk_synth_fastq(vk_ctx* c, void* dev_bytes, uint64_t capacity, uint64_t n_bas
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(c->stream));
         *n_out = total;
+    });
+}
+
+int vk_comm_unique_id(void* out128)
+{
+    return guarded([&] {
+        if (!out128) throw ApiError{VK_EINVAL, "NULL argument"};
+        ncclUniqueId id;
+        NC(nccl_api().GetUniqueId(&id));
+        memcpy(out128, &id, sizeof(id));
+    });
+}
+
+int vk_comm_init(vk_ctx* c, const void* unique_id128, int rank, int world)
+{
+    return guarded([&] {
+        if (!c || !unique_id128) throw ApiError{VK_EINVAL, "NULL argument"};
+        if (world < 1 || rank < 0 || rank >= world) throw ApiError{VK_EINVAL, "bad rank / world"};
+        set_device(c);
+        NcclApi& api = nccl_api();
+        if (c->comm) { NC(api.CommDestroy(c->comm)); c->comm = nullptr; }
+        ncclUniqueId id;
+        memcpy(&id, unique_id128, sizeof(id));
+        NC(api.CommInitRank(&c->comm, world, id, rank));
+        c->comm_rank = rank;
+        c->comm_world = world;
+        c->shard_table.ensure((size_t)2 * world + 2);
+    });
+}
+
+int vk_comm_destroy(vk_ctx* c)
+{
+    return guarded([&] {
+        if (!c) throw ApiError{VK_EINVAL, "NULL argument"};
+        if (c->comm) {
+            set_device(c);
+            CU(cudaStreamSynchronize(c->stream));
+            NC(nccl_api().CommDestroy(c->comm));
+            c->comm = nullptr;
+        }
+        c->comm_world = 1;
+        c->comm_rank = 0;
+    });
+}
+
+int vk_sharded_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, int on_device, const vk_params* p, int slot,
+                               int max_levels_out, vk_result* result, uint64_t* canon_host, uint8_t* pixels_host)
+{
+    int rc = on_device ? vk_attach(c, text, n_bytes) : VK_OK;
+    if (rc != VK_OK) return rc;
+    return guarded([&] {
+        if (!c || !result) throw ApiError{VK_EINVAL, "NULL argument"};
+        check_params(p);
+        if (!c->comm) throw ApiError{VK_ESTATE, "vk_sharded_reads_to_images before vk_comm_init"};
+        if (max_levels_out < 1 || max_levels_out > VK_MAX_LEVELS) throw ApiError{VK_EINVAL, "max_levels_out out of range"};
+        set_device(c);
+        NcclApi& api = nccl_api();
+        const int k = p->k;
+        const uint32_t nk = 1u << (2 * k);
+        const Mapping& m = get_mapping(c, slot, k);
+        const size_t n_pix = (size_t)m.side * m.side;
+        if (!on_device) {
+            if (n_bytes >> 40) throw ApiError{VK_ERANGE, "buffers of 2^40 bytes or more are not supported"};
+            c->text_own.ensure(n_bytes + 64);
+        }
+        const size_t n_hist = (size_t)max_levels_out * nk;                    // rows that are exchanged
+        with_table_retry(c, [&] {
+            c->generation += c->seg_hist.ensure((size_t)vk::kMaxLevels * nk + vk::kShardTail);
+            ensure_tables_for(c, reads_bound(n_bytes));
+            ensure_parse_buffers(c, n_bytes);
+            ensure_count_buffers(c, k);
+            ensure_render_buffers(c, m, k, max_levels_out);
+            if (!on_device) {
+                c->text = c->text_own.p;
+                c->n_bytes = n_bytes;
+                c->have_text = true;
+            }
+            enqueue_args(c, p);
+            c->args_h->pa.shard_table = c->shard_table.p;
+            c->args_h->pa.shard_rank = (uint32_t)c->comm_rank;
+            c->args_h->pa.shard_world = (uint32_t)c->comm_world;
+            c->mark(EV_START);
+            if (!on_device && n_bytes) CU(cudaMemcpyAsync(c->text_own.p, text, n_bytes, cudaMemcpyHostToDevice, c->stream));
+            c->mark(EV_UPLOAD);
+            // framing of this shard, then the shards' (records, bases) to every rank: exchange step 1, 16 bytes per rank
+            enqueue_parse(c, true, /*with_plan=*/false);
+            unsigned long long* const send = c->shard_table.p + 2 * (size_t)c->comm_world;
+            launch(c, vk::shard_stats_kernel, dim3(1), dim3(32), 0, (const vk::StepArgs*)c->args_d, (const vk::Plan*)c->plan_d, send);
+            NC(api.AllGather(send, c->shard_table.p, 2, ncclUint64, c->comm, c->stream));
+            launch(c, vk::plan_kernel, dim3(1), dim3(64), 0, (const vk::StepArgs*)c->args_d, c->starts.p, c->ends.p, c->plan_d);
+            CU(cudaGetLastError());
+            c->mark(EV_PARSE);
+            enqueue_count(c, k, c->seg_hist.p);
+            // exchange step 2: the histograms of every ladder segment + the per-segment totals, ONE all-reduce
+            unsigned long long* const tail = c->seg_hist.p + n_hist;
+            launch(c, vk::shard_tail_kernel, dim3(1), dim3(256), 0, c->plan_d, tail, 0);
+            NC(api.AllReduce(c->seg_hist.p, c->seg_hist.p, n_hist + vk::kShardTail, ncclUint64, ncclSum, c->comm, c->stream));
+            launch(c, vk::shard_tail_kernel, dim3(1), dim3(256), 0, c->plan_d, tail, 1);
+            launch(c, vk::zero_u64_kernel, dim3(1), dim3(256), 0, tail, (uint64_t)vk::kShardTail);      // the row belongs to a segment again
+            enqueue_render(c, m, k, max_levels_out, c->seg_hist.p);
+            CU(cudaMemcpyAsync(c->out_h, c->out_d, kPlanPad + (size_t)max_levels_out * n_pix, cudaMemcpyDeviceToHost, c->stream));
+            c->mark(EV_DONE);
+        });
+        if (c->plan_h->long_reads) throw ApiError{VK_ERANGE, "a read is longer than 2^24-1 bases"};
+        c->parsed = c->counted = true;
+        c->counted_k = k;
+        fill_result(*c->plan_h, result);
+        result->stats.n_reads = c->plan_h->total_reads;
+        int nl = result->n_levels;
+        if (nl > max_levels_out) throw ApiError{VK_ERANGE, "more ladder levels than max_levels_out (read-sharded samples exchange max_levels_out rows)"};
+        c->last_levels = nl;
+        if (pixels_host && nl > 0) memcpy(pixels_host, c->pix_h(), (size_t)nl * n_pix);
+        if (canon_host && nl > 0) {
+            CU(cudaMemcpyAsync(canon_host, c->canon.p, (size_t)nl * nk * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
     });
 }
 

@@ -49,6 +49,8 @@ struct Plan {
     uint32_t bucket_overflow;                    // a segment received more reads than its region holds (retry, exact layout)
     uint64_t seg_cap[kMaxLevels];                // entries each segment's region of the sorted array can hold
     unsigned long long seg_next2[kMaxLevels];    // second set of unit counters (k = 9: the other half of every CTA pair)
+    uint64_t read_index_base;                    // global index of this buffer's first record (plan_kernel -> scatter)
+    uint64_t total_reads;                        // records of the whole sample (= n_reads unless read-sharded)
 };
 
 // What plan_kernel needs beside the framing: the sample's options and the capacities of the tables.
@@ -61,6 +63,11 @@ struct PlanArgs {
     uint32_t reads_per_cta; // > 0: use at most ceil(n_reads / reads_per_cta) CTAs (small samples leave SMs to other samples)
     uint32_t exact_layout;  // 1: every segment region holds all reads (retry after a bucket overflow)
     uint32_t test_tight;    // tests only (VK_TEST_TIGHT_BUCKETS=1): regions of half the expected size, to force the retry
+    // read-sharded sample (vk_sharded_reads_to_images): the shards' (records, bases) pairs as the all-gather left them on
+    // the device, [shard_world][2]; nullptr for an unsharded sample.  The sample-wide base count and this shard's global
+    // read index then come from the table instead of p.nsites_override / p.read_index_base.
+    const unsigned long long* shard_table;
+    uint32_t shard_rank, shard_world;
 };
 
 // Everything about ONE step (one sample through the path) that varies from step to step lives in this device-resident

@@ -793,6 +793,31 @@ reduce_slabs_kernel(const uint32_t* __restrict__ slabs, const Plan* __restrict__
     seg_hist[g] = sum;
 }
 
+// read-sharded samples: the per-segment reads / bases and the two overflow flags of this shard ride in the all-reduce of
+// the histograms, right behind the rows that are exchanged (pack before, unpack after: the Plan then holds sample-wide
+// totals and "some shard overflowed" flags, and the host code that reads it does not care whether the sample was sharded)
+constexpr uint32_t kShardTail = 2 * kMaxLevels + 2;
+__global__ void __launch_bounds__(kShardTail <= 256 ? 256 : 512)
+shard_tail_kernel(Plan* __restrict__ plan, unsigned long long* __restrict__ tail, int unpack)
+{
+    pdl_wait();
+    const uint32_t i = threadIdx.x;
+    if (i >= kShardTail) return;
+    if (!unpack) {
+        unsigned long long v;
+        if (i < (uint32_t)kMaxLevels) v = plan->seg_reads[i];
+        else if (i < 2u * kMaxLevels) v = plan->seg_bases[i - kMaxLevels];
+        else v = i == 2u * kMaxLevels ? plan->table_overflow : plan->bucket_overflow;
+        tail[i] = v;
+    } else {
+        const unsigned long long v = tail[i];
+        if (i < (uint32_t)kMaxLevels) plan->seg_reads[i] = v;
+        else if (i < 2u * kMaxLevels) plan->seg_bases[i - kMaxLevels] = v;
+        else if (i == 2u * kMaxLevels) plan->table_overflow = v ? 1u : 0u;
+        else plan->bucket_overflow = v ? 1u : 0u;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 zero_u64_kernel(unsigned long long* __restrict__ p, uint64_t n)
 {

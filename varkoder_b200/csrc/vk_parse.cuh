@@ -392,6 +392,48 @@ __device__ inline uint64_t div_2p64(uint64_t num, uint64_t den)
     return q;
 }
 
+// What the newline bookkeeping of K1 amounts to at the end of the buffer: Python's line iterator yields an unterminated
+// last line too, and a header newline that is the very last byte opens no sequence line (image.py:662-667).
+struct Framing {
+    uint64_t n_lines, n_reads, nsites_true, nsites_ref;
+    bool close_last;        // the last sequence line is closed by the end of the buffer, not by a newline
+};
+__device__ __forceinline__ Framing finish_framing(const uint8_t* __restrict__ text, uint64_t n, const Plan* __restrict__ plan)
+{
+    Framing f;
+    const uint64_t T = plan->n_newlines;
+    const bool last_nl = n > 0 && text[n - 1] == '\n';
+    f.n_lines = T + ((n > 0 && !last_nl) ? 1 : 0);
+    f.n_reads = (f.n_lines + 2) >> 2;                                  // line indices 1 mod 4
+    uint64_t S = plan->sum_starts, E = plan->sum_ends;
+    uint64_t ref_adjust = 0;
+    f.close_last = false;
+    if ((T & 3) == 1) {
+        // a header newline opened a sequence line that no newline closed
+        if (!last_nl) {                    // unterminated, non-empty sequence line: closes at EOF
+            f.close_last = true;
+            E += n;
+            ref_adjust = 1;                // len(line) - 1 drops a real base here (image.py:666)
+        } else {
+            S -= n;                        // header newline was the last byte: no such line for Python
+        }
+    }
+    f.nsites_true = E - S;
+    f.nsites_ref = E - S - ref_adjust;
+    return f;
+}
+
+// read-sharded samples: this shard's (records, bases) for the all-gather that precedes plan_kernel
+__global__ void __launch_bounds__(32)
+shard_stats_kernel(const StepArgs* __restrict__ sa, const Plan* __restrict__ plan, unsigned long long* __restrict__ out2)
+{
+    pdl_wait();
+    if (threadIdx.x != 0) return;
+    const Framing f = finish_framing(sa->text, sa->pa.n_bytes, plan);
+    out2[0] = f.n_reads;
+    out2[1] = f.nsites_ref;
+}
+
 __global__ void __launch_bounds__(64)
 plan_kernel(const StepArgs* __restrict__ sa, uint64_t* __restrict__ starts, uint64_t* __restrict__ ends,
             Plan* __restrict__ plan)
@@ -407,31 +449,31 @@ plan_kernel(const StepArgs* __restrict__ sa, uint64_t* __restrict__ starts, uint
     const int l = threadIdx.x;
     if (l == 0) {
         const uint64_t n = a.n_bytes;
-        const uint64_t T = plan->n_newlines;
-        const bool last_nl = n > 0 && text[n - 1] == '\n';
-        const uint64_t n_lines = T + ((n > 0 && !last_nl) ? 1 : 0);      // Python yields an unterminated last line too
-        const uint64_t n_reads = (n_lines + 2) >> 2;                      // line indices 1 mod 4
-        uint64_t S = plan->sum_starts, E = plan->sum_ends;
-        uint64_t ref_adjust = 0;
-        if ((T & 3) == 1) {
-            // a header newline opened a sequence line that no newline closed
-            if (!last_nl) {                    // unterminated, non-empty sequence line: closes at EOF
-                if (n_reads >= 1 && n_reads - 1 < a.cap_reads) ends[n_reads - 1] = n;
-                E += n;
-                ref_adjust = 1;                // len(line) - 1 drops a real base here (image.py:666)
-            } else {
-                S -= n;                        // header newline was the last byte: no such line for Python
+        const Framing f = finish_framing(text, n, plan);
+        const uint64_t n_reads = f.n_reads;
+        if (f.close_last && n_reads >= 1 && n_reads - 1 < a.cap_reads) ends[n_reads - 1] = n;
+        plan->n_bytes = n;
+        plan->n_lines = f.n_lines;
+        plan->n_reads = n_reads;
+        plan->nsites_true = f.nsites_true;
+        plan->nsites_ref = f.nsites_ref;
+        if (n_reads > a.cap_reads) plan->table_overflow = 1;
+        // sample-wide base count and global index of this buffer's first record
+        uint64_t nsites_all = a.p.nsites_override ? a.p.nsites_override : f.nsites_ref;
+        uint64_t index_base = a.p.read_index_base, reads_all = n_reads;
+        if (a.shard_table) {
+            nsites_all = 0; index_base = 0; reads_all = 0;
+            for (uint32_t r = 0; r < a.shard_world; ++r) {
+                if (r < a.shard_rank) index_base += a.shard_table[2 * r];
+                reads_all += a.shard_table[2 * r];
+                nsites_all += a.shard_table[2 * r + 1];
             }
         }
-        plan->n_bytes = n;
-        plan->n_lines = n_lines;
-        plan->n_reads = n_reads;
-        plan->nsites_true = E - S;
-        plan->nsites_ref = E - S - ref_adjust;
-        if (n_reads > a.cap_reads) plan->table_overflow = 1;
+        plan->read_index_base = index_base;
+        plan->total_reads = reads_all;
 
         // ---- ladder, image.py:669-695 in integers
-        const uint64_t nsites = a.p.nsites_override ? a.p.nsites_override : (E - S - ref_adjust);
+        const uint64_t nsites = nsites_all;
         plan->nsites_ladder = nsites;
         int nl = 0;
         int status = VK_LADDER_OK;

@@ -194,6 +194,51 @@ class Engine:
         nl = r.n_levels
         return _result_from(r, canon[:nl] if canon is not None else None, pixels[:nl])
 
+    # ------------------------------------------------------------------ read-sharded samples
+    def comm_init(self, group=None):
+        """Give this context an NCCL communicator over the ranks of a torch.distributed group (collective).  The 128-byte
+        id is made by rank 0 and handed round with the group's own broadcast; after that the library talks to NCCL itself,
+        on its own stream (vk_sharded_reads_to_images)."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [None]
+        if rank == 0:
+            buf = C.create_string_buffer(128)
+            self._check(self._L.vk_comm_unique_id(buf))
+            box[0] = buf.raw
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        uid = C.create_string_buffer(box[0], 128)
+        self._check(self._L.vk_comm_init(self._ctx, uid, rank, world))
+        self.comm_world, self.comm_rank = world, rank
+
+    def comm_destroy(self):
+        self._check(self._L.vk_comm_destroy(self._ctx))
+        self.comm_world = None
+
+    def sharded_reads_to_images(self, text, params: Params, table: PixelTable, on_device=False, n_bytes=None,
+                                max_levels=16, want_canon=False):
+        """collective form of reads_to_images for ONE sample whose records are spread over the ranks (this rank passes its
+        shard): framing, all-gather of the shard sizes, counting, ONE all-reduce of the histograms, images -- a single
+        enqueue on the context's stream, one host synchronisation at the end.  Needs comm_init() first."""
+        slot = self.mapping_slot(table)
+        if on_device:
+            ptr, n, keep = int(text), int(n_bytes), None
+        else:
+            ptr, n, keep = _host_ptr(text)
+        nk = 4 ** params.k
+        L = _lib.VK_MAX_LEVELS
+        pixels = np.empty((L, table.side, table.side), dtype=np.uint8)
+        canon = np.empty((L, nk), dtype=np.uint64) if want_canon else None
+        r = _lib.VkResult()
+        p = params.to_c()
+        self.text_generation += 1
+        self._check(self._L.vk_sharded_reads_to_images(self._ctx, ptr, n, 1 if on_device else 0, C.byref(p), slot,
+                                                       int(max_levels), C.byref(r),
+                                                       canon.ctypes.data if canon is not None else None, pixels.ctypes.data))
+        del keep
+        nl = r.n_levels
+        return _result_from(r, canon[:nl] if canon is not None else None, pixels[:nl])
+
     def remap(self, images, src0, src1, mult, n_out_shape, sum_rc=False):
         """batch of uint8 images [n, H_in, W_in] -> [n, H_out, W_out] through a remap plan (mapping.remap_plan)"""
         imgs = np.ascontiguousarray(images, dtype=np.uint8)

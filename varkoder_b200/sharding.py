@@ -127,9 +127,25 @@ def sharded_count(engine, shard_bytes, params: Params, seg_hist, group=None):
                   level_bases=[int(x) for x in tot[M:M + nl]])
 
 
+def fused_sharded_reads_to_images(engine, shard, params: Params, table, group=None, on_device=False, n_bytes=None,
+                                  max_levels=16, want_canon=False):
+    """The read-sharded path as ONE enqueue per rank: the CUDA library issues both exchange steps itself, through NCCL,
+    on its own stream between its kernels (vk_sharded_reads_to_images) -- no host synchronisation until the images are
+    back.  ``shard``: this rank's records (host bytes, or a device pointer with ``on_device`` / ``n_bytes``).
+    The engine's communicator is created on first use (collective: every rank of ``group`` must call this)."""
+    import torch.distributed as dist
+    if getattr(engine, "comm_world", None) != dist.get_world_size(group):
+        engine.comm_init(group)
+    return engine.sharded_reads_to_images(shard, params, table, on_device=on_device, n_bytes=n_bytes,
+                                          max_levels=max_levels, want_canon=want_canon)
+
+
 def sharded_reads_to_images(engine, shard_bytes, params: Params, table, seg_hist=None, group=None,
                             render_on_all_ranks=True, want_canon=False):
-    """Read-sharded form of ``Engine.reads_to_images`` for ONE sample spread over the ranks of ``group``.
+    """Read-sharded form of ``Engine.reads_to_images`` for ONE sample spread over the ranks of ``group``, built from the
+    staged calls (parse / count / render) with ``torch.distributed`` collectives between them: works with any engine and
+    any backend (the CPU tests run it under gloo), at the price of a host synchronisation around every exchange.
+    On GPUs prefer :func:`fused_sharded_reads_to_images`.
     Every rank passes its own shard (see :func:`split_records`); returns the whole-sample :class:`Result`
     (pixels on every rank, or only on rank 0 when ``render_on_all_ranks`` is false)."""
     import torch
