@@ -134,6 +134,9 @@ struct vk_ctx {
     int graph_failed = 0;           // capture or instantiation failed once: stay on plain launches
     bool capturing = false;
     uint32_t captured_kernels = 0;
+    struct TraceEv { cudaEvent_t e; const void* fn; unsigned grid, block; };
+    std::vector<TraceEv> trace;
+    bool trace_each = false;        // VK_TRACE_EACH=1
 
     // read-sharded samples: an NCCL communicator of this context's own (vk_comm_init), collectives on the context's stream
     ncclComm_t comm = nullptr;
@@ -183,6 +186,31 @@ void launch(vk_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     cfg.numAttrs = c->use_pdl ? 1 : 0;
     CU(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
     if (c->capturing) ++c->captured_kernels; else ++c->launches;
+    if (c->trace_each && !c->capturing) {                 // VK_TRACE_EACH=1: an event behind every launch (debugging aid)
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        CU(cudaEventRecord(e, c->stream));
+        c->trace.push_back({e, (const void*)kernel, grid.x, block.x});
+    }
+}
+
+void trace_dump(vk_ctx* c)
+{
+    if (!c->trace_each || c->trace.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    float prev = 0.f;
+    for (size_t i = 0; i < c->trace.size(); ++i) {
+        float t = 0.f;
+        if (c->ev_valid[EV_START]) cudaEventElapsedTime(&t, c->ev[EV_START], c->trace[i].e);
+        cudaFuncAttributes fa;
+        const char* nm = "?";
+        (void)fa;
+        fprintf(stderr, "[vk trace] %2zu  +%8.1f us  (at %8.1f us)  grid %u x %u  fn %p %s\n", i, (t - prev) * 1e3, t * 1e3,
+                c->trace[i].grid, c->trace[i].block, c->trace[i].fn, nm);
+        prev = t;
+        cudaEventDestroy(c->trace[i].e);
+    }
+    c->trace.clear();
 }
 
 
@@ -719,6 +747,7 @@ int vk_ctx_create(int device, vk_ctx** out)
         if (const char* e = getenv("VK_COUNT_PAIRS")) c->use_pairs = atoi(e) != 0;
         if (const char* e = getenv("VK_PACKED")) c->use_packed = atoi(e) != 0;
         if (const char* e = getenv("VK_GRAPH")) c->use_graph = atoi(e) != 0;
+        if (const char* e = getenv("VK_TRACE_EACH")) { c->trace_each = atoi(e) != 0; if (c->trace_each) c->use_graph = false; }
         if (c->count_threads < 32 || c->count_threads > 1024 || c->count_threads % 32 || c->count_ctas_per_sm < 1 || c->count_ctas_per_sm > 3)
             throw ApiError{VK_EINVAL, "bad VK_COUNT_THREADS / VK_COUNT_CTAS"};
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -974,6 +1003,7 @@ int vk_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, int on_dev
             }
             c->mark(EV_DONE);
         });
+        trace_dump(c);
         if (c->plan_h->long_reads) throw ApiError{VK_ERANGE, "a read is longer than 2^24-1 bases"};
         c->parsed = c->counted = true;
         c->counted_k = k;

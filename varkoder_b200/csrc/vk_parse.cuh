@@ -134,10 +134,20 @@ parse_mask_kernel(const StepArgs* __restrict__ sa,
         uint64_t m = 0;
         if (tbyte < n_bytes) {
             uint4 w[kParseWordsPerThread];
+            // streaming loads: the text must not evict the masks.  A tile that lies wholly inside the text takes four
+            // unconditional loads, issued back to back (all 64 bytes of the thread in flight at once); only the last
+            // tile checks every word against the end.  (With one predicated form for both, ptxas once sank the third and
+            // fourth load behind the arithmetic of the second, halving the bytes in flight: 70 -> 117 us.)
+            if ((uint64_t)(tile + 1) * kParseTileBytes <= n_bytes) {
+                const uint4* const src = text16 + (tbyte >> 4);
 #pragma unroll
-            for (int i = 0; i < kParseWordsPerThread; ++i) {
-                const uint64_t b = tbyte + 16ull * i;
-                w[i] = (b < n_bytes) ? __ldcs(text16 + (b >> 4)) : make_uint4(0, 0, 0, 0);      // streaming: the text must not evict the masks
+                for (int i = 0; i < kParseWordsPerThread; ++i) w[i] = __ldcs(src + i);
+            } else {
+#pragma unroll
+                for (int i = 0; i < kParseWordsPerThread; ++i) {
+                    const uint64_t b = tbyte + 16ull * i;
+                    w[i] = (b < n_bytes) ? __ldcs(text16 + (b >> 4)) : make_uint4(0, 0, 0, 0);
+                }
             }
             if (PACK) {
                 uint32_t cw[4], vb[4], nb[4];      // per 16 bytes: 32 bits of codes, validity byte pair, newline byte pair

@@ -304,6 +304,35 @@ def _return_buffers(bufs):
                 q.append(b)
 
 
+def pigz_compress(raw, level=6, threads=None, block=128 * 1024):
+    """The stream ``pigz -p N`` writes -- what the reference's ``clean_reads`` leaves as ``<sample>.fq.gz``
+    (``cat ... | pigz -p``, image.py:534-540): ONE gzip member; every 128 KiB block is deflated on its own (primed with
+    the previous 32 KiB as dictionary) and ends with a sync flush (an empty stored block), so the blocks can be produced --
+    and, by :func:`gunzip_parallel`, decoded -- concurrently.  zlib releases the GIL, so this scales over threads.
+    The producer side of the host feed: tests and benches use it to make inputs of the reference's real format."""
+    raw = memoryview(raw).cast("B") if not isinstance(raw, (bytes, bytearray)) else raw
+    n = len(raw)
+    starts = list(range(0, max(n, 1), block))
+
+    def one(i):
+        zd = bytes(raw[max(0, i - 32768):i]) if i else b""
+        c = (zlib.compressobj(level, zlib.DEFLATED, -15, 8, zlib.Z_DEFAULT_STRATEGY, zd) if zd
+             else zlib.compressobj(level, zlib.DEFLATED, -15, 8))
+        return c.compress(raw[i:i + block]) + c.flush(zlib.Z_FINISH if i + block >= n else zlib.Z_SYNC_FLUSH)
+
+    threads = threads or len(os.sched_getaffinity(0))
+    if threads > 1 and len(starts) > 1:
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+            parts = list(pool.map(one, starts, chunksize=8))
+    else:
+        parts = [one(i) for i in starts]
+    crc = 0
+    for i in range(0, n, 1 << 26):
+        crc = zlib.crc32(raw[i:i + (1 << 26)], crc)
+    return b"".join([b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03"] + parts
+                    + [crc.to_bytes(4, "little") + (n & 0xFFFFFFFF).to_bytes(4, "little")])
+
+
 class SampleFeeder:
     """Iterate ``(index, item, PinnedBuffer, n_bytes)`` over samples in submission order, inflating up to ``depth``
     samples ahead on ``threads`` worker threads.  Buffers are recycled: hand one back with :meth:`release`."""
