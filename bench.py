@@ -418,72 +418,32 @@ def run_c4(args, world, rank, local, torch, dist):
 
 
 def run_c5(args, world, rank, local, torch, dist):
-    """BASELINE configs[4]: ONE sample of 30 Gbp (k = 7, CGR, -M 0: 16 levels), read-sharded over the ranks: every rank
-    frames and counts its contiguous shard of the records, two scalars are all-gathered (records, bases per shard: the
-    global read index base and the sample-wide nsites), ONE NCCL all-reduce sums the per-segment histograms and the
-    per-level totals, every rank renders.  Device-resident shards (generated on the device), wall clock between
-    barriers, max over ranks."""
-    import time as _t
-    from varkoder_b200 import sharding, synth
-    from varkoder_b200.engine import Engine, Params
-    from varkoder_b200.mapping import get_kmer_mapping
-    total_reads = (args.total_bases + READ_LEN - 1) // READ_LEN
-    first = total_reads * rank // world
-    last = total_reads * (rank + 1) // world
-    shard_bases = min((last - first) * READ_LEN, args.total_bases - first * READ_LEN)
-    eng = Engine(local)
-    table = get_kmer_mapping(7, "cgr")
-    nbytes = synth.fixed_total_bytes(shard_bases, READ_LEN)
-    dev = torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda")
-    assert eng.synth_fastq(dev.data_ptr(), dev.numel(), shard_bases, READ_LEN, seed=20260118 + 5000, first_read=first) == nbytes
-    seg = torch.zeros(64 * 4 ** 7, dtype=torch.int64, device="cuda")
-    sp = Params(k=7, min_bp=MIN_BP, max_bp=None, seed=11)
-    parity = check_sharded_parity(eng, table, world, rank, torch, dist) if world > 1 else None
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step():
-        if world > 1:
-            return sharding.fused_sharded_reads_to_images(eng, dev.data_ptr(), sp, table, on_device=True, n_bytes=nbytes,
-                                                          max_levels=18)
-        return eng.reads_to_images(dev.data_ptr(), sp, table, on_device=True, n_bytes=nbytes, max_levels=18)
-
-    for _ in range(max(2, min(args.warmup, 3))):
-        rs = step()
-    assert rs.levels[0] == args.total_bases and rs.level_bases[0] == args.total_bases and rs.n_reads == total_reads
-    steps = max(1, min(args.steps, 20))
+    parity = check_sharded_parity_fresh(local, world, rank, torch, dist) if world > 1 else None
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier()
-    t0 = _t.perf_counter()
-    for _ in range(steps):
-        rs = step()
-    barrier()
-    ms = 1e3 * (_t.perf_counter() - t0) / steps
+    r = c5_leg(args, world, rank, local, torch, dist, steps=max(1, min(args.steps, 20)))
     clocks = sampler.stop() if rank == 0 else None
-    tm = eng.timings()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.cpu()[0])
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": args.total_bases / (ms * 1e-3) / 1e9, "unit": "Gbases/s", "n_gpus": world, "steps": steps,
-            "warmup": max(2, min(args.warmup, 3)), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"configs[4]: ONE sample of {args.total_bases} bases (read length 150), k=7, cgr, -M 0 "
-                                   f"({len(rs.levels)} levels), read-sharded over {world} GPU(s): shards of {shard_bases} bases "
-                                   f"({nbytes / 1e9:.1f} GB of text) resident per GPU; per step and rank ONE enqueue on the library's stream: "
-                                   f"framing, ncclAllGather(2 x u64), ladder, count, ONE ncclAllReduce(u64 x {18 * 4 ** 7 + 130}), images",
-                       "bases_per_step": args.total_bases, "levels": len(rs.levels),
+            "metric": METRIC, "value": r["value"], "unit": "Gbases/s", "n_gpus": world, "steps": r["steps"], "warmup": 3,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
+            "config": {"workload": r["workload"], "bases_per_step": r["bases"], "levels": r["levels"],
                        "l2_policy": "shards are far larger than L2"},
-            "levels": rs.levels, "level_bases": rs.level_bases, "sharded_parity": parity,
-            "kernel_ms_last_step_rank0": tm, "clocks": clocks}), flush=True)
-    eng.close()
+            "level_bases": r["level_bases"], "sharded_parity": parity, "clocks": clocks}), flush=True)
+
+
+def check_sharded_parity_fresh(local, world, rank, torch, dist):
+    from varkoder_b200.engine import Engine
+    from varkoder_b200.mapping import get_kmer_mapping
+    eng = Engine(local)
+    try:
+        return check_sharded_parity(eng, get_kmer_mapping(K, MAPPING), world, rank, torch, dist)
+    finally:
+        if getattr(eng, "comm_world", None):
+            eng.comm_destroy()
+        eng.close()
 
 
 def check_sharded_parity(eng, table, world, rank, torch, dist, n_bases=5_000_000):
@@ -523,6 +483,127 @@ def check_sharded_parity(eng, table, world, rank, torch, dist, n_bases=5_000_000
             "compared": "canonical counts of every level (uint64, bit-exact) and every pixel"}
 
 
+def e2e_gz_leg(eng, local, torch, n_big=200_000_000, n_small=25_000_000, n_files=16):
+    """The reference's real input format, end to end on this box: pigz-written ``.fq.gz`` files on local disk (what
+    clean_reads leaves, image.py:529-540) -> stages.images_for_samples -> PNG files on disk.  Two cases: ONE 200 Mbp
+    sample (configs[1]; the spare inflate threads split the single gzip member at pigz's sync points) and a batch of
+    `n_files` x 25 Mbp.  All host threads the process may use inflate; wall clock, best of three; rank 0's GPU only --
+    from files the path is bound by DEFLATE decoding on the host cores, not by the GPU."""
+    import shutil
+    import tempfile
+    from varkoder_b200 import feed, stages
+    from varkoder_b200.mapping import get_kmer_mapping
+    threads = len(os.sched_getaffinity(0))
+    tmp = tempfile.mkdtemp(prefix="vk_e2e_gz_")
+    out = {"inflate_threads": threads, "gzip": "pigz-style single member, 128 KiB blocks, zlib level 6",
+           "decoder": "libvk_feed.so (own DEFLATE)" if feed.feed_lib() is not None else "zlib"}
+    try:
+        table = get_kmer_mapping(K, MAPPING)
+
+        def make(name, n_bases, first_read):
+            total = synth_total(n_bases)
+            d = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+            assert eng.synth_fastq(d.data_ptr(), d.numel(), n_bases, READ_LEN, seed=20260118 + 6000, first_read=first_read) == total
+            raw = d[:total].cpu().numpy()
+            del d
+            comp = feed.pigz_compress(raw, 6, threads)
+            p = os.path.join(tmp, name + ".fq.gz")
+            with open(p, "wb") as f:
+                f.write(comp)
+            return p, total, len(comp)
+
+        def timed(samples, n_bases_total, text_bytes, gz_bytes, workers, min_bp, max_bp):
+            times = []
+            for rep in range(3):
+                o = os.path.join(tmp, "images")
+                shutil.rmtree(o, ignore_errors=True)
+                t0 = time.perf_counter()
+                st = stages.images_for_samples(samples, o, table, k=K, mapping_code=MAPPING, min_bp=min_bp, max_bp=max_bp,
+                                               threads=threads, gpu_workers=workers, device=local)
+                times.append(time.perf_counter() - t0)
+                assert len(st) == len(samples) and all("failed_step" not in v for v in st.values())
+            n_png = sum(len(fs) for _, _, fs in os.walk(os.path.join(tmp, "images")))
+            best = min(times)
+            return {"seconds": best, "all_runs_s": [round(x, 3) for x in times], "value": n_bases_total / best / 1e9,
+                    "unit": "Gbases/s", "text_gb_per_s": text_bytes / best / 1e9, "gz_mb": round(gz_bytes / 1e6, 1),
+                    "text_mb": round(text_bytes / 1e6, 1), "png_files": n_png, "gpu_workers": workers}
+        p, total, gz = make("BIG", n_big, 0)
+        out["one_sample"] = dict(timed([dict(sample="BIG", path=p, labels=["x"], base_sd=0.0)], n_big, total, gz, 1,
+                                       MIN_BP, 200_000_000), bases=n_big, levels=len(LEVELS))
+        os.remove(p)
+        samples, tot_text, tot_gz = [], 0, 0
+        for i in range(n_files):
+            p, total, gz = make(f"S{i:02d}", n_small, (i + 1) * 2_000_000)
+            samples.append(dict(sample=f"S{i:02d}", path=p, labels=["x"], base_sd=0.0))
+            tot_text += total
+            tot_gz += gz
+        out["batch"] = dict(timed(samples, n_small * n_files, tot_text, tot_gz, 2, MIN_BP, 200_000_000),
+                            files=n_files, bases_per_file=n_small)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
+def c5_leg(args, world, rank, local, torch, dist, total_bases=None, steps=8):
+    """BASELINE configs[4]: ONE sample of 30 Gbp (k = 7, CGR, -M 0: 16 levels), read-sharded over the ranks: per step and
+    rank one enqueue on the library's stream (framing, ncclAllGather of the shard sizes, ladder, count, ONE ncclAllReduce
+    of the histograms, images), one host synchronisation.  Shards generated on the devices.  Wall clock between
+    barriers, max over ranks.  Result dict on rank 0."""
+    import time as _t
+    from varkoder_b200 import sharding, synth
+    from varkoder_b200.engine import Engine, Params
+    from varkoder_b200.mapping import get_kmer_mapping
+    total_bases = total_bases or args.total_bases
+    total_reads = (total_bases + READ_LEN - 1) // READ_LEN
+    first = total_reads * rank // world
+    last = total_reads * (rank + 1) // world
+    shard_bases = min((last - first) * READ_LEN, total_bases - first * READ_LEN)
+    eng = Engine(local)
+    table = get_kmer_mapping(7, "cgr")
+    nbytes = synth.fixed_total_bytes(shard_bases, READ_LEN)
+    dev = torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda")
+    assert eng.synth_fastq(dev.data_ptr(), dev.numel(), shard_bases, READ_LEN, seed=20260118 + 5000, first_read=first) == nbytes
+    sp = Params(k=7, min_bp=MIN_BP, max_bp=None, seed=11)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        if world > 1:
+            return sharding.fused_sharded_reads_to_images(eng, dev.data_ptr(), sp, table, on_device=True, n_bytes=nbytes,
+                                                          max_levels=18)
+        return eng.reads_to_images(dev.data_ptr(), sp, table, on_device=True, n_bytes=nbytes, max_levels=18)
+
+    for _ in range(3):
+        rs = step()
+    assert rs.levels[0] == total_bases and rs.level_bases[0] == total_bases and rs.n_reads == total_reads
+    barrier()
+    t0 = _t.perf_counter()
+    for _ in range(steps):
+        rs = step()
+    barrier()
+    ms = 1e3 * (_t.perf_counter() - t0) / steps
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.cpu()[0])
+    if world > 1:
+        eng.comm_destroy()
+    eng.close()
+    del dev
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {"value": total_bases / (ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": ms, "steps": steps, "n_gpus": world,
+            "bases": total_bases, "levels": len(rs.levels), "level_bases": rs.level_bases,
+            "workload": f"configs[4]: ONE sample of {total_bases} bases (read length 150), k=7, cgr, -M 0 ({len(rs.levels)} levels), "
+                        f"read-sharded over {world} GPU(s): {shard_bases} bases ({nbytes / 1e9:.1f} GB of text) resident per GPU"
+                        + ("; exchange = ncclAllGather(2 x u64) + ONE ncclAllReduce(u64 x %d), issued by the library on its own "
+                           "stream between its kernels" % (18 * 4 ** 7 + 130) if world > 1 else "")}
+
+
 # ----------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -532,6 +613,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-legs", action="store_true", help="skip the c4 / c5 / e2e_gz side measurements")
     ap.add_argument("--in-flight", type=int, default=4,
                     help="samples in flight per GPU in the timed region: one context + host thread each (1 = one stream)")
     ap.add_argument("--no-concurrent", action="store_true", help="same as --in-flight 1")
@@ -711,6 +793,7 @@ def main():
         h.copy_(samples[t][0][:total])
         hosts.append(h)
     host = hosts[0]
+    host_keep = None
     torch.cuda.synchronize()
     r2s = [None] * Te
     for t in range(Te):
@@ -779,6 +862,27 @@ def main():
     dev_ms, wall_ms, e2e_ms, count_ms = [float(x) for x in t.cpu()]
 
     probe_gbs = hbm_probe(torch) if rank == 0 else None
+    # ---- side legs (recorded in the same line; none of them feeds `value`): the other BASELINE configurations and the
+    # reference's real input format.  Each frees what the main leg holds first; a leg that fails is reported, not fatal.
+    side = {}
+    if not args.no_side_legs and args.bases == N_BASES and args.workload == "c2":
+        if world > 1 and getattr(eng, "comm_world", None):
+            eng.comm_destroy()
+        for e in engs[1:]:
+            e.close()
+        del samples, devs, dev, hosts, host_keep
+        torch.cuda.empty_cache()
+        for name, fn in (("c4", lambda: c4_leg(args, world, rank, local, torch, dist, reps=3, in_flight=max(T, 4))),
+                         ("c5", lambda: c5_leg(args, world, rank, local, torch, dist, steps=6)),
+                         ("e2e_gz", lambda: e2e_gz_leg(eng, local, torch) if rank == 0 else None)):
+            try:
+                r_leg = fn()
+            except Exception as exc:                       # noqa: BLE001 -- recorded in the line
+                r_leg = {"error": f"{type(exc).__name__}: {exc}"}
+            if world > 1:
+                dist.barrier()
+            if rank == 0 and r_leg is not None:
+                side[name] = r_leg
     if rank == 0:
         peak, peak_src = measured_peaks()
         steps = args.steps
@@ -820,6 +924,7 @@ def main():
             out["read_sharded"] = sharded
             out["sharded_parity"] = sharded_parity
         out["one_context"] = one_stream
+        out.update(side)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = run_cpu_baseline(host.numpy())
         print(json.dumps(out), flush=True)
