@@ -193,6 +193,10 @@ int vk_graph_stats(vk_ctx* ctx, uint64_t* launches, uint64_t* captures, int32_t*
  * expected share (8 sigma + slack): always 0 in practice; tests force it with VK_TEST_TIGHT_BUCKETS=1. */
 uint64_t vk_bucket_retries(vk_ctx* ctx);
 
+/* How often a count had to be repeated with the exact kernel because a 16-bit shared-memory bin of the fire-and-forget
+ * kernel wrapped (k = 8, k = 7 in pair mode; a flood of one k-mer): 0 on ordinary reads. */
+uint64_t vk_count_fallbacks(vk_ctx* ctx);
+
 /* Deterministic synthetic FASTQ (bench / tests): fills a DEVICE buffer.
  * Fixed read length L: record r occupies bytes [r*(2L+17), (r+1)*(2L+17)); returns bytes written in *n_out. */
 int vk_synth_fastq(vk_ctx* ctx, void* dev_bytes, uint64_t capacity, uint64_t n_bases, int read_len, uint64_t seed,

@@ -425,9 +425,34 @@ def test_low_complexity_flood_16bit_bins(monkeypatch, k):
     buf = fastq([reads[i] for i in order])
     _, res, canon, _ = gpu_counts(engine, buf, Params(k=k, min_bp=0, max_bp=None, is_query=True))
     expect = dsk.canonical_counts(buf, k)
+    fallbacks = engine.count_fallbacks()
+    table = get_kmer_mapping(k, "cgr")
+    r2 = engine.reads_to_images(buf, Params(k=k, min_bp=0, max_bp=None, is_query=True), table, want_canon=True)
+    fallbacks2 = engine.count_fallbacks()
     engine.close()
     assert int(expect.max()) > 500_000                       # far beyond a 16-bit bin
     assert (canon[0] == expect).all()
+    assert (r2.canon[0] == expect).all()                     # the fused (graph) path repeats the count the same way
+    if k in (7, 8):
+        # the fire-and-forget kernel noticed the wrapped bins (its low halves no longer sum to its increments) and the
+        # count was repeated with the exact kernel
+        assert fallbacks >= 1 and fallbacks2 >= fallbacks + 1
+
+
+@pytest.mark.parametrize("k", [7, 8])
+def test_exact_16bit_kernels_without_fallback(monkeypatch, k):
+    """VK_COUNT_FAST=0: the returning-add + drain kernels count floods exactly in one go"""
+    from varkoder_b200.engine import Engine
+    monkeypatch.setenv("VK_COUNT_PAIRS", "1")
+    monkeypatch.setenv("VK_COUNT_FAST", "0")
+    engine = Engine(0)
+    rng = np.random.default_rng(31 + k)
+    reads = ["A" * 150] * 5000 + ["GT" * 70] * 2000 + rand_reads(rng, 2000, 0, 200, p_n=0.01)
+    buf = fastq([reads[i] for i in rng.permutation(len(reads))])
+    _, res, canon, _ = gpu_counts(engine, buf, Params(k=k, min_bp=0, max_bp=None, is_query=True))
+    n = engine.count_fallbacks()
+    engine.close()
+    assert (canon[0] == dsk.canonical_counts(buf, k)).all() and n == 0
 
 
 def test_pair_counting_ladder_exact(monkeypatch):

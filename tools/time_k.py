@@ -5,6 +5,7 @@ from varkoder_b200 import synth
 from varkoder_b200.engine import Engine, Params
 from varkoder_b200.mapping import get_kmer_mapping
 eng = Engine(0)
+eng.set_fine_timing(True)
 n = int(os.environ.get("VK_N", "200000000"))
 total = synth.fixed_total_bytes(n, 150)
 dev = torch.empty(total + 64, dtype=torch.uint8, device='cuda')

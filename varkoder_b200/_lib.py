@@ -18,7 +18,7 @@ SYMBOLS = [
     "vk_abi_version", "vk_last_error", "vk_ctx_create", "vk_ctx_destroy", "vk_set_mapping", "vk_upload",
     "vk_attach", "vk_parse", "vk_count", "vk_render", "vk_render_counts", "vk_reads_to_images", "vk_device_pixels", "vk_remap",
     "vk_base_content",
-    "vk_last_timings", "vk_set_fine_timing", "vk_launch_count", "vk_bucket_retries", "vk_synth_fastq",
+    "vk_last_timings", "vk_set_fine_timing", "vk_launch_count", "vk_bucket_retries", "vk_count_fallbacks", "vk_synth_fastq",
     "vk_synth_fastq_variable", "vk_graph_stats",
     "vk_comm_unique_id", "vk_comm_init", "vk_comm_destroy", "vk_sharded_reads_to_images",
 ]
@@ -81,6 +81,8 @@ def load():
     L.vk_launch_count.restype = C.c_uint64
     L.vk_bucket_retries.argtypes = [vp]
     L.vk_bucket_retries.restype = C.c_uint64
+    L.vk_count_fallbacks.argtypes = [vp]
+    L.vk_count_fallbacks.restype = C.c_uint64
     L.vk_synth_fastq.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64,
                                  C.POINTER(C.c_uint64)]
     L.vk_synth_fastq_variable.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
@@ -93,7 +95,7 @@ def load():
     L.vk_graph_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if name not in ("vk_last_error", "vk_launch_count", "vk_bucket_retries"):
+        if name not in ("vk_last_error", "vk_launch_count", "vk_bucket_retries", "vk_count_fallbacks"):
             fn.restype = C.c_int
     _lib = L
     return L

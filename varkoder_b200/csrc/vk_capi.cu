@@ -107,6 +107,9 @@ struct vk_ctx {
     bool use_count16 = true;        // VK_COUNT16=0: k = 8 with global atomics instead of 16-bit shared-memory bins
     bool use_pairs = false;         // VK_COUNT_PAIRS=1: k = 7 through 8-mer pairs in 16-bit bins (exact; halves the
                                     // shared-memory traffic but costs more instructions: 168 vs 143 us, profiles/r01_notes.md)
+    bool use_fast = true;           // VK_COUNT_FAST=0: 16-bit bins always through returning adds + drains (exact in one go)
+    bool count_safe = false;        // set for the repeat of a step whose fire-and-forget count reported a wrapped bin
+    uint64_t count_fallbacks = 0;
     bool use_pdl = true;            // VK_PDL=0 disables programmatic dependent launch
     bool test_tight = false;        // VK_TEST_TIGHT_BUCKETS=1: undersized regions, exercises the retry (tests only)
     uint64_t bucket_retries = 0;
@@ -325,8 +328,10 @@ void prepare_count_kernels()
     }
     if constexpr (K == 7 || K == 8) {
         const int smem = (int)((size_t)(32768 + (K == 7 ? 16384 : 0)) * sizeof(uint32_t));
-        CU(cudaFuncSetAttribute(count16_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CU(cudaFuncSetAttribute(count16_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute((count16_kernel<K, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute((count16_kernel<K, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute((count16_kernel<K, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute((count16_kernel<K, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     if constexpr (K == 9) {
         const int smem = (int)((size_t)32768 * sizeof(uint32_t) + 2048);
@@ -357,10 +362,13 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
     const StepArgs* sa = c->args_d;
     const PackedSrc pk = {reinterpret_cast<const uint2*>(c->codes.p), reinterpret_cast<const uint32_t*>(c->valid.p)};
     if constexpr (K == 7 || K == 8) {
-        if (K == 8 ? c->use_count16 : c->use_pairs) {
-            // 16-bit bins in shared memory: k = 8 directly, k = 7 through pairs (vk_count.cuh)
+        // 16-bit bins in shared memory: k = 8 directly, k = 7 through pairs (vk_count.cuh).  The fire-and-forget form by
+        // default; after it reported a wrapped bin (count_safe) the exact form -- for k = 7 that is the u32 kernel below.
+        const bool fast = c->use_fast && !c->count_safe;
+        if (K == 8 ? c->use_count16 : (c->use_pairs && (fast || !c->use_fast))) {
             const size_t smem = (size_t)(32768 + (K == 7 ? 16384 : 0)) * sizeof(uint32_t);
-            launch(c, (count16_kernel<K, PACKED>), grid, block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p);
+            if (fast) launch(c, (count16_kernel<K, PACKED, true>), grid, block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p);
+            else launch(c, (count16_kernel<K, PACKED, false>), grid, block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p);
             c->mark(EV_COUNT);
             launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist);
             return;
@@ -635,9 +643,14 @@ void with_table_retry(vk_ctx* c, F&& body)
         body();
         CU(cudaStreamSynchronize(c->stream));
         const bool t_over = c->plan_h->table_overflow != 0, b_over = c->plan_h->bucket_overflow != 0;
-        if (!t_over && !b_over) { c->exact_layout = false; return; }
-        if (attempt == 2) throw ApiError{VK_ERANGE, "read table overflow after resize"};
-        if (t_over) ensure_tables_for(c, c->plan_h->n_reads + 16);          // exact size is known now
+        const bool c_over = c->plan_h->count_overflow != 0 && !t_over && !b_over;
+        if (!t_over && !b_over && !c_over) { c->exact_layout = false; c->count_safe = false; return; }
+        if (attempt == 2) { c->count_safe = false; throw ApiError{VK_ERANGE, "read table overflow after resize"}; }
+        if (c_over) {
+            // a 16-bit bin of the fire-and-forget count kernel wrapped (a flood of one k-mer): count again, exactly
+            c->count_safe = true;
+            ++c->count_fallbacks;
+        } else if (t_over) ensure_tables_for(c, c->plan_h->n_reads + 16);          // exact size is known now
         else {
             // a segment outgrew its expected-size region (or the table was too small for the layout): give every
             // segment room for every read
@@ -678,7 +691,7 @@ vk_ctx::StepGraph* step_graph(vk_ctx* c, const Mapping& m, int slot, int k, int 
     if (!c->use_graph || c->graph_failed || c->fine_timing) return nullptr;
     for (auto& g : c->graphs)
         if (g.k == k && g.slot == slot && g.side == m.side && g.max_levels == max_levels_out && g.exact == (int)c->exact_layout &&
-            g.packed == (int)c->use_packed && g.generation == c->generation)
+            g.packed == ((int)c->use_packed | (c->count_safe ? 2 : 0)) && g.generation == c->generation)
             return &g;
     // stale graphs (a buffer moved) are of no use any more
     for (size_t i = 0; i < c->graphs.size();) {
@@ -710,7 +723,7 @@ vk_ctx::StepGraph* step_graph(vk_ctx* c, const Mapping& m, int slot, int k, int 
         return nullptr;
     }
     ++c->graph_captures;
-    c->graphs.push_back({k, slot, m.side, max_levels_out, (int)c->exact_layout, (int)c->use_packed, c->generation, exec,
+    c->graphs.push_back({k, slot, m.side, max_levels_out, (int)c->exact_layout, (int)c->use_packed | (c->count_safe ? 2 : 0), c->generation, exec,
                          c->captured_kernels});
     return &c->graphs.back();
 }
@@ -745,6 +758,7 @@ int vk_ctx_create(int device, vk_ctx** out)
         if (const char* e = getenv("VK_PDL")) c->use_pdl = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT16")) c->use_count16 = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT_PAIRS")) c->use_pairs = atoi(e) != 0;
+        if (const char* e = getenv("VK_COUNT_FAST")) c->use_fast = atoi(e) != 0;
         if (const char* e = getenv("VK_PACKED")) c->use_packed = atoi(e) != 0;
         if (const char* e = getenv("VK_GRAPH")) c->use_graph = atoi(e) != 0;
         if (const char* e = getenv("VK_TRACE_EACH")) { c->trace_each = atoi(e) != 0; if (c->trace_each) c->use_graph = false; }
@@ -1127,6 +1141,7 @@ int vk_graph_stats(vk_ctx* c, uint64_t* launches, uint64_t* captures, int32_t* s
     return VK_OK;
 }
 uint64_t vk_bucket_retries(vk_ctx* c) { return c ? c->bucket_retries : 0; }
+uint64_t vk_count_fallbacks(vk_ctx* c) { return c ? c->count_fallbacks : 0; }
 
 int vk_synth_fastq(vk_ctx* c, void* dev_bytes, uint64_t capacity, uint64_t n_bases, int read_len, uint64_t seed,
                    uint64_t first_read, uint64_t* n_out)

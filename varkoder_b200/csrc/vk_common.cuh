@@ -49,6 +49,8 @@ struct Plan {
     uint32_t bucket_overflow;                    // a segment received more reads than its region holds (retry, exact layout)
     uint64_t seg_cap[kMaxLevels];                // entries each segment's region of the sorted array can hold
     unsigned long long seg_next2[kMaxLevels];    // second set of unit counters (k = 9: the other half of every CTA pair)
+    uint32_t count_overflow;                     // a 16-bit bin of a FAST count kernel wrapped (vk_count.cuh): exact recount
+    uint32_t reserved0;
     uint64_t read_index_base;                    // global index of this buffer's first record (plan_kernel -> scatter)
     uint64_t total_reads;                        // records of the whole sample (= n_reads unless read-sharded)
 };

@@ -73,6 +73,10 @@ __device__ __forceinline__ void smem_inc(uint32_t shared_addr)
 {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(shared_addr) : "memory");      // SASS: ATOMS.POPC.INC
 }
+__device__ __forceinline__ void smem_add(uint32_t shared_addr, uint32_t v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(shared_addr), "r"(v) : "memory");      // SASS: ATOMS.ADD, nothing comes back
+}
 __device__ __forceinline__ uint32_t smem_add_ret(uint32_t shared_addr, uint32_t v)
 {
     uint32_t old;
@@ -518,7 +522,13 @@ __device__ __forceinline__ void count16_flush(uint32_t* __restrict__ h8, uint32_
     }
 }
 
-template <int K, bool PACKED>
+// FAST: the increments are fire-and-forget (red.shared.add, no value comes back, nothing is watched in the loop) and the
+// bins are checked ONCE, when the CTA is done: every increment adds 1 to the low half of its word, so the low halves must
+// sum to the number of increments the CTA made; a low half that passed 2^16 carried into its high half and the sum
+// comes out 2^16 short.  A mismatch raises plan->count_overflow and the host repeats the count with the exact kernel
+// (returning adds + drains, below; for k = 7 the u32 kernel).  It takes a word that receives more than 65 535 of one
+// CTA's increments -- a flood of one k-mer (poly-A libraries); ordinary reads never get near it.
+template <int K, bool PACKED, bool FAST>
 __global__ void __launch_bounds__(kCountThreads)
 count16_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __restrict__ sorted, Plan* __restrict__ plan,
                uint32_t* __restrict__ slabs)
@@ -544,21 +554,65 @@ count16_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __
     const uint32_t h8_addr = (uint32_t)__cvta_generic_to_shared(s_raw);
     const uint32_t h7_addr = h8_addr + 32768u * 4u;
     uint32_t* const slab = slabs + (size_t)logical_cta() * NK;
+    __shared__ unsigned long long s_chk[2];                            // FAST: increments made / sum of the low halves
     for (uint32_t i = tid; i < kWords; i += nthr) s_raw[i] = 0;
     for (uint32_t i = tid; i < NK; i += nthr) slab[i] = 0;             // drains and the final fold ADD to the slab
+    if (tid < 2) s_chk[tid] = 0;
     __syncthreads();
 
     ChunkStream<PACKED> cs;
     cs.init(text16, pk, sorted + plan->seg_begin[seg], seg_len, &plan->seg_next[seg], lane, plan->n_bytes,
             (plan->seg_cta_begin[seg + 1] - plan->seg_cta_begin[seg]) * (blockDim.x >> 5));
     uint32_t carry = 0;
+    uint32_t made = 0;                                                 // FAST: increments of this lane (< 2^32: < 2^37 bases per lane)
     Chunk cur = cs.fetch();
     while (__ballot_sync(FULL, cur.range != 0) != 0) {
         const Chunk nxt = cs.fetch();
         const Decoded d = decode_chunk<K, PACKED>(cur, carry, lane, breaklen, one);
         const uint64_t Wa = ((uint64_t)d.Cc | ((uint64_t)d.Plo << (2 * KM1))) << 2;
         const uint64_t Wb = ((uint64_t)(d.Plo >> (32 - 2 * KM1)) | ((uint64_t)d.Phi << (2 * KM1))) << 2;
-        if (K == 8) {
+        if (K == 8 && FAST) {
+            made += __popc(d.E);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint64_t W4 = h ? Wb : Wa;
+                const uint32_t Wl = (uint32_t)W4, Wh = (uint32_t)(W4 >> 32), E = h ? d.E >> 16 : d.E & 0xFFFFu;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t sh = __funnelshift_r(Wl, Wh, 2 * j);
+                    const uint32_t inc = ((sh >> 1) & 0x10000u) | 1u;           // 1, or 0x10001 for the upper bin of the word
+                    smem_add(h8_addr + (sh & 0x1FFFCu), (E >> j) & 1u ? inc : 0u);
+                }
+            }
+        } else if (K == 7 && FAST) {
+            // pairs: positions (2m, 2m+1); Eb: both 7-mers countable -> one 8-mer; Es: exactly one -> a single 7-mer
+            const uint32_t Ee = d.E & 0x55555555u, Eo = (d.E >> 1) & 0x55555555u;
+            const uint32_t Eb = Ee & Eo;
+            uint32_t Es = Ee ^ Eo;                                      // bit 2m: pair m holds exactly one 7-mer
+            made += __popc(Eb);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint64_t W4 = h ? Wb : Wa;
+                const uint32_t Wl = (uint32_t)W4, Wh = (uint32_t)(W4 >> 32), E = h ? Eb >> 16 : Eb & 0xFFFFu;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const uint32_t sh = __funnelshift_r(Wl, Wh, 4 * m);
+                    const uint32_t inc = ((sh >> 1) & 0x10000u) | 1u;
+                    smem_add(h8_addr + (sh & 0x1FFFCu), (E >> (2 * m)) & 1u ? inc : 0u);
+                }
+            }
+            while (__ballot_sync(FULL, Es != 0) != 0) {                 // single 7-mers (read ends, N, break points)
+                if (Es != 0) {
+                    const uint32_t b2 = __ffs(Es) - 1;                  // = 2m
+                    Es &= Es - 1;
+                    const uint64_t W4 = b2 >= 16 ? Wb : Wa;
+                    const uint32_t sh = (uint32_t)(W4 >> (2 * (b2 & 15u)));
+                    const bool second = (Eo >> b2) & 1u;
+                    const uint32_t off7 = (second ? sh >> 2 : sh) & 0xFFFCu;
+                    smem_inc(h7_addr + off7);
+                }
+            }
+        } else if (K == 8) {
             // every 8-mer: window position j holds the 8-mer that ends at base j (7 carried codes in front).  A lane
             // without an 8-mer at j adds 0 to whatever word the window names (always inside the table).
 #pragma unroll
@@ -617,6 +671,19 @@ count16_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __
         cur = nxt;
     }
     __syncthreads();
+    if (FAST) {
+        unsigned long long low = 0;
+        for (uint32_t w = tid; w < 32768u; w += nthr) low += h8[w] & 0xFFFFu;
+        unsigned long long mine = made;
+#pragma unroll
+        for (int dlt = 16; dlt > 0; dlt >>= 1) {
+            low += __shfl_xor_sync(FULL, low, dlt);
+            mine += __shfl_xor_sync(FULL, mine, dlt);
+        }
+        if (lane == 0) { atomicAdd(&s_chk[0], mine); atomicAdd(&s_chk[1], low); }
+        __syncthreads();
+        if (tid == 0 && s_chk[0] != s_chk[1]) atomicOr(&plan->count_overflow, 1u);
+    }
     count16_flush<K>(h8, h7, slab, tid, nthr);
 }
 
@@ -796,7 +863,7 @@ reduce_slabs_kernel(const uint32_t* __restrict__ slabs, const Plan* __restrict__
 // read-sharded samples: the per-segment reads / bases and the two overflow flags of this shard ride in the all-reduce of
 // the histograms, right behind the rows that are exchanged (pack before, unpack after: the Plan then holds sample-wide
 // totals and "some shard overflowed" flags, and the host code that reads it does not care whether the sample was sharded)
-constexpr uint32_t kShardTail = 2 * kMaxLevels + 2;
+constexpr uint32_t kShardTail = 2 * kMaxLevels + 3;
 __global__ void __launch_bounds__(kShardTail <= 256 ? 256 : 512)
 shard_tail_kernel(Plan* __restrict__ plan, unsigned long long* __restrict__ tail, int unpack)
 {
@@ -807,14 +874,15 @@ shard_tail_kernel(Plan* __restrict__ plan, unsigned long long* __restrict__ tail
         unsigned long long v;
         if (i < (uint32_t)kMaxLevels) v = plan->seg_reads[i];
         else if (i < 2u * kMaxLevels) v = plan->seg_bases[i - kMaxLevels];
-        else v = i == 2u * kMaxLevels ? plan->table_overflow : plan->bucket_overflow;
+        else v = i == 2u * kMaxLevels ? plan->table_overflow : (i == 2u * kMaxLevels + 1 ? plan->bucket_overflow : plan->count_overflow);
         tail[i] = v;
     } else {
         const unsigned long long v = tail[i];
         if (i < (uint32_t)kMaxLevels) plan->seg_reads[i] = v;
         else if (i < 2u * kMaxLevels) plan->seg_bases[i - kMaxLevels] = v;
         else if (i == 2u * kMaxLevels) plan->table_overflow = v ? 1u : 0u;
-        else plan->bucket_overflow = v ? 1u : 0u;
+        else if (i == 2u * kMaxLevels + 1) plan->bucket_overflow = v ? 1u : 0u;
+        else plan->count_overflow = v ? 1u : 0u;
     }
 }
 

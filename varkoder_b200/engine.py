@@ -298,6 +298,9 @@ class Engine:
         self._check(self._L.vk_graph_stats(self._ctx, C.byref(a), C.byref(b), C.byref(st)))
         return int(a.value), int(b.value), int(st.value)
 
+    def count_fallbacks(self):
+        return int(self._L.vk_count_fallbacks(self._ctx))
+
     def bucket_retries(self):
         return int(self._L.vk_bucket_retries(self._ctx))
 
