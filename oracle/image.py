@@ -1,7 +1,7 @@
 """numpy restatement of the Python half of the reference hot path -- TEST INFRASTRUCTURE ONLY.
 
 PINNED: every function here is checked against the imported, unmodified reference
-(``oracle/make_golden.py`` -> ``tests/golden``; ``tests/test_oracle_vs_reference.py`` when
+(``oracle/make_golden.py`` -> ``tests/golden``; ``tests/test_oracle.py`` when
 ``/root/reference`` is mounted) and against the properties of the reference's shipped ``docs/*.png``.
 
 Follows (reference file:line):

@@ -45,6 +45,8 @@ def main():
     from PIL import Image
     rng = np.random.default_rng(20260119)
     for k in (5, 6, 7):
+        if os.path.exists(os.path.join(GOLD, f"remap_k{k}.npz")) and "--all" not in sys.argv:
+            continue                           # committed fixture: only --all makes it again
         luts = {m: oimg.lut_from_table(utils.get_kmer_mapping(k, m)) for m in ("varKode", "cgr")}
         out = {}
         for src, dst in (("varKode", "cgr"), ("cgr", "varKode")):
@@ -63,6 +65,21 @@ def main():
             key = f"varKode_to_cgr__arbitrary__{'sum' if sum_rc else 'plain'}"
             out[key + "__in"] = arb
             out[key + "__out"] = res.astype(np.uint8)
+        np.savez_compressed(os.path.join(GOLD, f"remap_k{k}.npz"), **out)
+        print("k", k, "cases", len(out) // 2)
+    # k = 8, 9 (images of 182^2 / 256^2 and 363^2 / 512^2 pixels): fewer cases, small values (the fixtures stay small)
+    for k in (8, 9):
+        rng = np.random.default_rng(20260119 + k)          # own stream: independent of whether k = 5..7 were made in this run
+        luts = {m: oimg.lut_from_table(utils.get_kmer_mapping(k, m)) for m in ("varKode", "cgr")}
+        out = {}
+        for src, dst in (("varKode", "cgr"), ("cgr", "varKode")):
+            img = consistent_image(luts[src], k, rng, "small")
+            for sum_rc in (False, True):
+                with np.errstate(all="ignore"):
+                    res = np.array(convert.remap(Image.fromarray(img, mode="L"), k, src, dst, sum_rc=sum_rc))
+                key = f"{src}_to_{dst}__small__{'sum' if sum_rc else 'plain'}"
+                out[key + "__in"] = img
+                out[key + "__out"] = res.astype(np.uint8)
         np.savez_compressed(os.path.join(GOLD, f"remap_k{k}.npz"), **out)
         print("k", k, "cases", len(out) // 2)
 

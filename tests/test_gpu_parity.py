@@ -705,7 +705,7 @@ def test_query_mode_device_handoff(engine):
     assert float(x.max()) == 1.0
 
 
-@pytest.mark.parametrize("k", [5, 6, 7])
+@pytest.mark.parametrize("k", [5, 6, 7, 8, 9])
 def test_remap_matches_reference_golden(engine, golden_dir, k):
     """vk_remap (convert.remap on the GPU) against the outputs of the imported reference, both directions, with and
     without sum_rc, one image at a time and as a batch"""

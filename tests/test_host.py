@@ -139,7 +139,7 @@ def test_synthetic_generator_shape_and_determinism():
     assert pv["n_reads"] == 500 and pv["lens"].min() < 7 and pv["lens"].max() <= 280
 
 
-@pytest.mark.parametrize("k", [5, 6, 7])
+@pytest.mark.parametrize("k", [5, 6, 7, 8])
 def test_remap_plan_matches_oracle(golden_dir, k):
     """the product's join of the two pixel tables (mapping.remap_plan) against the oracle's restatement, which is
     pinned to the reference's convert.remap by tests/golden/remap_k*.npz (test_oracle.py)"""

@@ -154,6 +154,22 @@ def test_remap_golden(golden_dir, k):
         assert (got == z[key + "__out"]).all(), key
 
 
+@pytest.mark.parametrize("k", [8, 9])
+def test_remap_golden_large_k(golden_dir, k):
+    """the same for the large images (182^2 / 256^2, 363^2 / 512^2); their pixel tables are not stored as fixtures --
+    the product's tables are used, which the make_image goldens of k = 8, 9 pin"""
+    from varkoder_b200.mapping import get_kmer_mapping
+    z = np.load(os.path.join(golden_dir, f"remap_k{k}.npz"))
+    luts = {m: get_kmer_mapping(k, m).lut for m in ("varKode", "cgr")}
+    keys = sorted(set(n.rsplit("__", 1)[0] for n in z.files))
+    assert len(keys) == 4
+    for key in keys:
+        d, _, mode = key.split("__")
+        src, dst = d.split("_to_")
+        got = oimg.remap_exact(z[key + "__in"], luts[src], luts[dst], k, src == "cgr", dst == "cgr", mode == "sum")
+        assert (got == z[key + "__out"]).all(), key
+
+
 def test_quality_flag_golden(golden_dir):
     """get_basefrequency_sd (image.py:49-88) run on fastp-shaped reports built from the oracle's counts
     (oracle/make_golden_quality.py): the numpy restatement of the counts and the host arithmetic of
