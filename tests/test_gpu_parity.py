@@ -859,15 +859,16 @@ def test_base_content_argument_and_state_errors():
 
 
 # ------------------------------------------------------------------- step variants: graph / plain, packed / text
-@pytest.mark.parametrize("packed,graph", [("1", "1"), ("1", "0"), ("0", "1"), ("0", "0")])
-def test_step_variants_bit_exact(monkeypatch, packed, graph):
-    """The fused call in its four forms -- submitted as one CUDA graph or kernel by kernel, count kernels fed by the 2-bit
-    pack of the framing pass or classifying the text themselves -- on samples of very different sizes through ONE
+@pytest.mark.parametrize("packed,graph,chunks", [("1", "1", "1"), ("1", "0", "1"), ("0", "1", "1"), ("0", "0", "1"), ("0", "1", "0")])
+def test_step_variants_bit_exact(monkeypatch, packed, graph, chunks):
+    """The fused call in its forms -- submitted as one CUDA graph or kernel by kernel, count kernels fed by the 2-bit
+    pack of the framing pass or classifying the text themselves, from the chunk table or from the read table -- on samples of very different sizes through ONE
     context (a graph captured for the first sample must serve the others: everything that differs travels in the
     device-resident argument block), for every k: bit-exact against the oracle each time."""
     from varkoder_b200.engine import Engine
     monkeypatch.setenv("VK_PACKED", packed)
     monkeypatch.setenv("VK_GRAPH", graph)
+    monkeypatch.setenv("VK_CHUNKS", chunks)      # k <= 7: chunk table written by the scatter kernel / chunk stream in the count kernel
     eng = Engine(0)
     try:
         rng = np.random.default_rng(17)

@@ -22,7 +22,7 @@ constexpr int kBucketItems = 4;      // reads per thread and iteration of the sc
 // raises plan->bucket_overflow and the host repeats the step with regions that hold every read.
 __global__ void __launch_bounds__(kBucketThreads)
 bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __restrict__ ends, const StepArgs* __restrict__ sa,
-                      uint64_t text_base, uint64_t* __restrict__ sorted, Plan* __restrict__ plan)
+                      uint64_t text_base, uint64_t* __restrict__ sorted, uint64_t* __restrict__ chunks, Plan* __restrict__ plan)
 {
     pdl_wait();
     const int k = sa->pa.p.k;
@@ -33,11 +33,19 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
     __shared__ unsigned long long s_base[kMaxLevels];
     __shared__ uint64_t s_thr[kMaxLevels], s_begin[kMaxLevels], s_cap[kMaxLevels];
     __shared__ uint32_t s_long;
+    // chunk mode (k <= 7, chunks != nullptr): instead of one entry per read, one descriptor per 32-byte chunk of the read
+    // goes into the segment's region of the chunk table (vk_common.cuh make_chunk_desc); the count kernel then walks
+    // descriptors, coalesced, with nothing to work out per chunk
+    __shared__ uint32_t s_ccnt[kMaxLevels];
+    __shared__ unsigned long long s_cbase[kMaxLevels];
+    __shared__ uint64_t s_cbegin[kMaxLevels], s_ccap[kMaxLevels];
+    const bool chunk_mode = chunks != nullptr;
+    const uint32_t breaklen = (uint32_t)sa->pa.p.breaklength;
     // the tables do not fit (plan_kernel): the step is repeated with larger ones, nothing here may be dereferenced.
     // (bucket_overflow can also be raised by this kernel itself, below; a CTA that starts late and sees it only skips
     // work whose result is thrown away.)
     __shared__ uint32_t s_abort;
-    if (threadIdx.x == 0) s_abort = plan->table_overflow | plan->bucket_overflow;      // one reader: the branch is block-uniform
+    if (threadIdx.x == 0) s_abort = plan->table_overflow | plan->bucket_overflow | plan->chunk_table_small;      // one reader: the branch is block-uniform
     __syncthreads();
     if (s_abort) return;
     const int nl = plan->n_levels;
@@ -49,12 +57,14 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
         s_all[threadIdx.x] = plan->level_all[threadIdx.x];
         s_begin[threadIdx.x] = plan->seg_begin[threadIdx.x];
         s_cap[threadIdx.x] = plan->seg_cap[threadIdx.x];
+        s_cbegin[threadIdx.x] = plan->seg_cbegin[threadIdx.x];
+        s_ccap[threadIdx.x] = plan->seg_ccap[threadIdx.x];
     }
     if (threadIdx.x == 0) s_long = 0;
     // kBucketItems reads per thread and iteration: their table loads are in flight together, and one round trip of the
     // global cursors serves 1024 reads (the kernel is latency-bound: ~1 iteration per CTA at 200 Mbp)
     for (uint64_t r0 = (uint64_t)blockIdx.x * (blockDim.x * kBucketItems); r0 < n_reads; r0 += per_iter * kBucketItems) {
-        if (threadIdx.x < kMaxLevels) { s_cnt[threadIdx.x] = 0; s_len[threadIdx.x] = 0; }
+        if (threadIdx.x < kMaxLevels) { s_cnt[threadIdx.x] = 0; s_len[threadIdx.x] = 0; s_ccnt[threadIdx.x] = 0; }
         __syncthreads();
         uint64_t st[kBucketItems], en[kBucketItems];
 #pragma unroll
@@ -66,6 +76,7 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
         int seg[kBucketItems];
         uint32_t rank[kBucketItems];
         uint64_t entry[kBucketItems];
+        uint32_t nchunk[kBucketItems], crank[kBucketItems];
 #pragma unroll
         for (int i = 0; i < kBucketItems; ++i) {
             const uint64_t r = r0 + (uint64_t)i * blockDim.x + threadIdx.x;
@@ -103,20 +114,62 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
             }
             wbase = __shfl_sync(peers, wbase, leader);
             rank[i] = wbase + __popc(peers & ((1u << lane) - 1u));
+            nchunk[i] = 0;
+            crank[i] = 0;
+            if (chunk_mode) {
+                // chunks of this read, and its offset among the chunks of the warp's reads of the same segment: one plain
+                // warp scan per segment present in the warp (a handful: the segments halve in size down the ladder)
+                const uint32_t rlo = (uint32_t)(entry[i] >> kEntryLenBits) & 15u;
+                const uint32_t n = seg[i] >= 0 ? (rlo + len32 + 31u) >> 5 : 0u;
+                nchunk[i] = n;
+                uint32_t todo = __ballot_sync(FULL, seg[i] >= 0);
+                while (todo) {
+                    const int cur = __shfl_sync(FULL, seg[i], __ffs(todo) - 1);
+                    const bool mine = seg[i] == cur;
+                    uint32_t incl = mine ? n : 0u;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                        if (lane >= (uint32_t)d) incl += t;
+                    }
+                    const uint32_t total = __shfl_sync(FULL, incl, 31);
+                    uint32_t cb = 0;
+                    if (mine && (int)lane == leader) cb = atomicAdd(&s_ccnt[cur], total);      // leader = lowest lane of the segment
+                    cb = __shfl_sync(FULL, cb, __ffs(todo) - 1);
+                    if (mine) crank[i] = cb + incl - n;
+                    todo &= ~__ballot_sync(FULL, mine);
+                }
+            }
         }
         __syncthreads();
         if (threadIdx.x < kMaxLevels && s_cnt[threadIdx.x]) {
             s_base[threadIdx.x] = atomicAdd(&plan->seg_reads[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
             atomicAdd(&plan->seg_bases[threadIdx.x], s_len[threadIdx.x]);
+            if (chunk_mode) s_cbase[threadIdx.x] = atomicAdd(&plan->seg_chunks[threadIdx.x], (unsigned long long)s_ccnt[threadIdx.x]);
         }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < kBucketItems; ++i) {
-            if (seg[i] >= 0) {
+            if (seg[i] >= 0 && !chunk_mode) {
                 const uint64_t slot = s_base[seg[i]] + rank[i];
                 VK_ASSERT(seg[i] < nl && s_begin[seg[i]] + s_cap[seg[i]] <= plan->seg_begin[kMaxLevels]);
                 if (slot < s_cap[seg[i]]) sorted[s_begin[seg[i]] + slot] = entry[i];
                 else plan->bucket_overflow = 1u;
+            }
+            if (seg[i] >= 0 && chunk_mode) {
+                const uint64_t first = s_cbase[seg[i]] + crank[i];
+                const uint32_t n = nchunk[i];
+                if (first + n <= s_ccap[seg[i]]) {
+                    const uint64_t rstart = entry[i] >> kEntryLenBits;
+                    const uint32_t rlen = (uint32_t)(entry[i] & kEntryLenMask);
+                    const uint32_t rlo = (uint32_t)rstart & 15u;
+                    const bool is_long = breaklen != 0 && rlen > breaklen;
+                    uint64_t* const dst = chunks + s_cbegin[seg[i]] + first;
+                    for (uint32_t j = 0; j < n; ++j) {
+                        const uint32_t endrel = rlo + rlen - 32u * j;               // > 0
+                        dst[j] = make_chunk_desc((rstart >> 4) + 2ull * j, rlo, endrel < 32u ? endrel : 32u, j, is_long);
+                    }
+                } else plan->bucket_overflow = 1u;
             }
         }
         __syncthreads();

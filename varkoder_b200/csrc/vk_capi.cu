@@ -121,6 +121,10 @@ struct vk_ctx {
     vk::StepArgs* args_h = nullptr;
     bool use_packed = false;        // VK_PACKED=1 (measured, a net loss); 0: the count kernels classify the text themselves (round-1 path) instead of
                                     // reading the 2-bit codes + validity bits the framing pass writes
+    bool use_chunks = true;         // VK_CHUNKS=0: k <= 7 counts from the segment-sorted READ table (chunk stream worked out in
+                                    // the count kernel) instead of the chunk table the scatter kernel writes
+    DevBuf<uint64_t> chunks;        // chunk table: one descriptor per 32-byte chunk of every selected read
+    bool chunk_mode(int k) const { return use_chunks && k <= 7 && !use_packed && !(k == 7 && use_pairs); }
     DevBuf<uint4> codes;            // 2-bit codes of every text byte, 16 B per 64 text bytes (parse_mask_kernel<true>)
     DevBuf<uint2> valid;            // validity bits, 8 B per 64 text bytes
     // one step = one CUDA graph: captured once per (k, pixel table, levels, layout) and replayed for every sample
@@ -239,6 +243,7 @@ void enqueue_args(vk_ctx* c, const vk_params* params)
     a.pa.exact_layout = c->exact_layout ? 1u : 0u;
     a.pa.test_tight = c->test_tight ? 1u : 0u;
     a.pa.shard_table = nullptr;
+    a.pa.cap_chunks = (params && c->chunk_mode(params->k)) ? c->chunks.cap : 0;
 }
 // first kernel of a step: StepArgs host -> device, and (rescan) the framing accumulators cleared (vk_parse.cuh K0)
 void enqueue_begin(vk_ctx* c, bool rescan)
@@ -310,6 +315,9 @@ void ensure_tables_for(vk_ctx* c, uint64_t n_reads_hint)
 void ensure_count_buffers(vk_ctx* c, int k)
 {
     const uint32_t nk = 1u << (2 * k);
+    // chunk table: ~ one descriptor per 32 bases + two per read with the 8-sigma slack of every region; from the text
+    // size alone (half of it bases, records of ~300 bytes) -- a sample that needs more says so (chunk_table_small)
+    if (c->chunk_mode(k)) c->generation += c->chunks.ensure((size_t)(c->n_bytes / 40) + (1u << 18));
     if (k <= 7 || (k == 8 && c->use_count16)) c->generation += c->slabs.ensure((size_t)c->count_grid() * nk);
     if (k == 9 && c->use_count16)
         c->generation += c->slabs.ensure((size_t)2 * (c->n_sms * c->count_ctas_per_sm / 2 + c->count_extra9) * 65536u);
@@ -325,6 +333,7 @@ void prepare_count_kernels()
         const int smem = (int)(0x10000 + (size_t)(NK + 32) * sizeof(uint32_t));
         CU(cudaFuncSetAttribute(count_kernel<K, kSmem32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CU(cudaFuncSetAttribute(count_kernel<K, kSmem32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(countd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     if constexpr (K == 7 || K == 8) {
         const int smem = (int)((size_t)(32768 + (K == 7 ? 16384 : 0)) * sizeof(uint32_t));
@@ -388,7 +397,8 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
     if constexpr (K <= 7) {
         // the histogram sits at a 64 KiB-aligned shared address (vk_count.cuh): up to 64 KiB of padding in front
         const size_t smem = 0x10000 + (size_t)(NK + 32) * sizeof(uint32_t);
-        launch(c, (count_kernel<K, kSmem32, PACKED>), grid, block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p, seg_hist);
+        if (c->chunk_mode(K)) launch(c, countd_kernel<K>, grid, block, smem, sa, (const uint64_t*)c->chunks.p, c->plan_d, c->slabs.p);
+        else launch(c, (count_kernel<K, kSmem32, PACKED>), grid, block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p, seg_hist);
         c->mark(EV_COUNT);
         launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist);
     } else {
@@ -404,7 +414,7 @@ void enqueue_count(vk_ctx* c, int k, unsigned long long* seg_hist)
     using namespace vk;
     const int bgrid = c->n_sms * 8;
     launch(c, bucket_scatter_kernel, dim3(bgrid), dim3(kBucketThreads), 0, c->starts.p, c->ends.p, (const StepArgs*)c->args_d, 0,
-           c->sorted.p, c->plan_d);
+           c->sorted.p, c->chunk_mode(k) ? c->chunks.p : (uint64_t*)nullptr, c->plan_d);
     CU(cudaGetLastError());
     c->mark(EV_BUCKET);
     const bool pk = c->use_packed;
@@ -639,24 +649,29 @@ int guarded(F&& f)
 template <typename F>
 void with_table_retry(vk_ctx* c, F&& body)
 {
-    for (int attempt = 0; attempt < 3; ++attempt) {
+    for (int attempt = 0; attempt < 4; ++attempt) {
         body();
         CU(cudaStreamSynchronize(c->stream));
         const bool t_over = c->plan_h->table_overflow != 0, b_over = c->plan_h->bucket_overflow != 0;
-        const bool c_over = c->plan_h->count_overflow != 0 && !t_over && !b_over;
-        if (!t_over && !b_over && !c_over) { c->exact_layout = false; c->count_safe = false; return; }
-        if (attempt == 2) { c->count_safe = false; throw ApiError{VK_ERANGE, "read table overflow after resize"}; }
+        const bool k_small = c->plan_h->chunk_table_small != 0 && !t_over;
+        const bool c_over = c->plan_h->count_overflow != 0 && !t_over && !b_over && !k_small;
+        if (!t_over && !b_over && !c_over && !k_small) { c->exact_layout = false; c->count_safe = false; return; }
+        if (attempt == 3) { c->count_safe = false; throw ApiError{VK_ERANGE, "read table overflow after resize"}; }
         if (c_over) {
             // a 16-bit bin of the fire-and-forget count kernel wrapped (a flood of one k-mer): count again, exactly
             c->count_safe = true;
             ++c->count_fallbacks;
         } else if (t_over) ensure_tables_for(c, c->plan_h->n_reads + 16);          // exact size is known now
+        else if (k_small) c->generation += c->chunks.ensure((size_t)c->plan_h->chunks_needed + 256);
         else {
             // a segment outgrew its expected-size region (or the table was too small for the layout): give every
             // segment room for every read
             c->exact_layout = true;
             ++c->bucket_retries;
             c->generation += c->sorted.ensure(sorted_need(c->plan_h->n_reads, (uint64_t)std::max(c->plan_h->n_levels, 1), true));
+            if (c->plan_h->chunks_needed)       // chunk table in use: every region then holds every chunk (plan_kernel's bound)
+                c->generation += c->chunks.ensure((size_t)std::max(c->plan_h->n_levels, 1) *
+                                                  (size_t)(c->plan_h->nsites_true / 32 + 2 * c->plan_h->n_reads + 4608));
         }
     }
 }
@@ -760,6 +775,7 @@ int vk_ctx_create(int device, vk_ctx** out)
         if (const char* e = getenv("VK_COUNT_PAIRS")) c->use_pairs = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT_FAST")) c->use_fast = atoi(e) != 0;
         if (const char* e = getenv("VK_PACKED")) c->use_packed = atoi(e) != 0;
+        if (const char* e = getenv("VK_CHUNKS")) c->use_chunks = atoi(e) != 0;
         if (const char* e = getenv("VK_GRAPH")) c->use_graph = atoi(e) != 0;
         if (const char* e = getenv("VK_TRACE_EACH")) { c->trace_each = atoi(e) != 0; if (c->trace_each) c->use_graph = false; }
         if (c->count_threads < 32 || c->count_threads > 1024 || c->count_threads % 32 || c->count_ctas_per_sm < 1 || c->count_ctas_per_sm > 3)
@@ -789,6 +805,7 @@ int vk_ctx_destroy(vk_ctx* c)
     if (c->args_h) cudaFreeHost(c->args_h);
     c->codes.release();
     c->valid.release();
+    c->chunks.release();
     c->text_own.release();
     c->tile_status.release();
     c->masks.release();

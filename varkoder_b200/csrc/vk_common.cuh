@@ -49,8 +49,13 @@ struct Plan {
     uint32_t bucket_overflow;                    // a segment received more reads than its region holds (retry, exact layout)
     uint64_t seg_cap[kMaxLevels];                // entries each segment's region of the sorted array can hold
     unsigned long long seg_next2[kMaxLevels];    // second set of unit counters (k = 9: the other half of every CTA pair)
+    // chunk table (k <= 7): the reads of a segment cut into 32-byte text chunks, one 8-byte descriptor each (vk_bucket.cuh)
+    unsigned long long seg_chunks[kMaxLevels];   // chunks scattered into each segment's region
+    uint64_t seg_cbegin[kMaxLevels + 1];         // offsets of the regions in the chunk table
+    uint64_t seg_ccap[kMaxLevels];               // descriptors each region holds
+    uint64_t chunks_needed;                      // table size the layout asked for (host grows the table and repeats)
+    uint32_t chunk_table_small;                  // the layout does not fit the table
     uint32_t count_overflow;                     // a 16-bit bin of a FAST count kernel wrapped (vk_count.cuh): exact recount
-    uint32_t reserved0;
     uint64_t read_index_base;                    // global index of this buffer's first record (plan_kernel -> scatter)
     uint64_t total_reads;                        // records of the whole sample (= n_reads unless read-sharded)
 };
@@ -68,6 +73,7 @@ struct PlanArgs {
     // read-sharded sample (vk_sharded_reads_to_images): the shards' (records, bases) pairs as the all-gather left them on
     // the device, [shard_world][2]; nullptr for an unsharded sample.  The sample-wide base count and this shard's global
     // read index then come from the table instead of p.nsites_override / p.read_index_base.
+    uint64_t cap_chunks;    // descriptors the chunk table holds (0: the count kernel reads the sorted read table instead)
     const unsigned long long* shard_table;
     uint32_t shard_rank, shard_world;
 };
@@ -121,6 +127,19 @@ __host__ __device__ __forceinline__ uint32_t internal_revcomp(uint32_t i, int k)
         r |= (c ^ 2u) << (2 * j);            // complement under the dsk code is XOR 2
     }
     return r;
+}
+
+// ---- chunk descriptor (k <= 7 count path): one 32-byte text chunk of one read --------------------------------------
+//   bits  0..33  index of the 16-byte text word the chunk starts at (texts up to 2^38 bytes)
+//   bits 34..37  rlo: offset of the read's first base inside its first 16-byte word (every chunk of the read carries it)
+//   bits 38..42  hi - 1: the chunk's bytes [lo, hi) belong to the read, lo = rlo in the read's first chunk and 0 after it
+//   bits 43..61  j: number of the chunk inside its read (reads of up to 2^24 - 1 bases have fewer than 2^19 chunks)
+//   bit  62      the read is longer than the break length (reformat.sh breaklength; cut points have to be masked)
+//   bit  63      set in every descriptor (0 = empty slot)
+constexpr uint64_t kChunkValid = 1ull << 63;
+__host__ __device__ __forceinline__ uint64_t make_chunk_desc(uint64_t word16, uint32_t rlo, uint32_t hi, uint32_t j, bool is_long)
+{
+    return kChunkValid | word16 | ((uint64_t)rlo << 34) | ((uint64_t)(hi - 1u) << 38) | ((uint64_t)j << 43) | ((uint64_t)(is_long ? 1u : 0u) << 62);
 }
 
 // programmatic dependent launch: block until the preceding kernel of the stream has completed and its writes are

@@ -455,6 +455,157 @@ count_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __re
     }
 }
 
+// ------------------------------------------------------------------------------ chunk-table kernels (k <= 7)
+// The chunk stream above works out, in every iteration, which read and which of its chunks a lane is looking at (~80
+// of the ~250 ALU-pipe instructions of an iteration).  With the chunk TABLE (vk_bucket.cuh, chunk mode) that work is done
+// once, by the scatter kernel, which knows it anyway: a segment is a flat array of 8-byte descriptors, a warp claims
+// ranges of it from the segment's counter and lane l simply takes descriptor pos + l (one coalesced 8-byte load,
+// requested an iteration ahead of the text it points at).  The chunks of a read are consecutive in the table, so the K-1
+// bases to the left still come from the lane to the left; lane 0 of the first window of a claimed range reads the 8 text
+// bytes in front of its chunk itself.
+struct DescStream {
+    const uint4* text16;
+    const uint64_t* seg_chunks;
+    unsigned long long* seg_counter;
+    uint32_t n_chunks, lane, n_warps;
+    uint32_t pos, end;          // lane 0's descriptor of the next fetch / end of the claimed range
+    uint32_t nbase, nsize;      // the range after this one, claimed one range ahead
+    uint32_t claimed_upto;      // counter value after our last claim (guides the claim size)
+    uint64_t dnext;             // descriptor of the next fetch (its load was issued one fetch ago)
+    uint64_t text_words;        // VK_ASSERT only
+    bool at_start;              // the next window opens a claimed range
+
+    // guided: 16 iterations per claim while the segment has plenty left, fewer towards its end, so that the warps of a
+    // segment finish within an iteration or two of each other
+    __device__ __forceinline__ void claim()
+    {
+        const uint32_t left = claimed_upto < n_chunks ? n_chunks - claimed_upto : 0u;
+        const uint32_t per_warp = left / (32u * n_warps);                 // windows still unclaimed per warp, roughly
+        const uint32_t its = per_warp >= 64u ? 16u : per_warp >= 8u ? 4u : 1u;
+        unsigned long long r0 = 0;
+        if (lane == 0) r0 = atomicAdd(seg_counter, (unsigned long long)(its * 32u));
+        r0 = __shfl_sync(0xffffffffu, r0, 0);
+        nbase = r0 < 0xffffffe0ull ? (uint32_t)r0 : 0xffffffe0u;          // a range at or beyond n_chunks is empty
+        nsize = its * 32u;
+        claimed_upto = nbase + nsize;
+    }
+    __device__ __forceinline__ uint64_t load_desc(uint32_t idx) const { return idx < n_chunks ? __ldg(seg_chunks + idx) : 0ull; }
+    __device__ __forceinline__ void init(const uint4* t, const uint64_t* sc, uint32_t n, unsigned long long* ctr, uint32_t ln,
+                                         uint64_t n_bytes, uint32_t n_warps_seg)
+    {
+        text16 = t; seg_chunks = sc; n_chunks = n; seg_counter = ctr; lane = ln;
+        text_words = (n_bytes + 15) >> 4;
+        n_warps = n_warps_seg ? n_warps_seg : 1u;
+        claimed_upto = 0;
+        claim();
+        pos = nbase; end = nbase + nsize;
+        at_start = true;
+        dnext = load_desc(pos + lane);
+        claim();
+    }
+    // this lane's chunk of the coming window (c.range == 0: none).  first: the window opens a claimed range; left8: for
+    // lane 0 of such a window, the 8 text bytes in front of its chunk (when the chunk is not its read's first)
+    __device__ __forceinline__ Chunk fetch(bool& first, uint2& left8)
+    {
+        Chunk c;
+        const uint64_t d = dnext;
+        first = at_start;
+        c.wa = make_uint4(0, 0, 0, 0);
+        c.wb = c.wa;
+        left8 = make_uint2(0, 0);
+        const bool act = (d & kChunkValid) != 0;
+        const uint64_t word16 = d & ((1ull << 34) - 1);
+        const uint32_t rlo = (uint32_t)(d >> 34) & 15u, hi = ((uint32_t)(d >> 38) & 31u) + 1u, j = (uint32_t)(d >> 43) & 0x7FFFFu;
+        const uint32_t lo = j == 0 ? rlo : 0u;
+        if (act) {
+            const uint4* const ptr = text16 + word16;
+            VK_ASSERT(word16 + (hi > 16u ? 1 : 0) < text_words && hi > lo);
+            c.wa = __ldg(ptr);
+            if (hi > 16u) c.wb = __ldg(ptr + 1);
+            if (at_start && lane == 0 && j != 0) left8 = __ldg(reinterpret_cast<const uint2*>(ptr) - 1);
+        }
+        c.range = act ? (0xffffffffu >> (32u - hi)) & (0xffffffffu << lo) : 0u;
+        c.j = j;
+        c.rlen = ((uint32_t)(d >> 62) & 1u) ? 0xFFFFFFu : 0u;          // only "longer than the break length" is known here
+        c.q0 = (int32_t)(32u * j) - (int32_t)rlo;
+        c.last = 31u;
+        pos += 32u;
+        at_start = false;
+        if (pos >= end) {                    // this range is used up: go on in the one claimed a range ago, claim another
+            pos = nbase;
+            end = nbase + nsize;
+            at_start = true;
+            claim();
+        }
+        dnext = load_desc(pos + lane);
+        return c;
+    }
+};
+
+// the K-1 bases (and their validity) in front of a chunk, from the 8 text bytes in front of it: the `tail` format of
+// decode_chunk (codes of the last K-1 bases from bit 0, their validity bits from bit 16)
+template <int K>
+__device__ __forceinline__ uint32_t tail_from_left8(uint2 l8, uint32_t one)
+{
+    constexpr int KM1 = K - 1;
+    const Cls4z a = classify4z(l8.x, one), b = classify4z(l8.y, one);
+    const uint32_t codes16 = (a.packed_hi >> 24) | ((b.packed_hi >> 24) << 8);      // base -8 at bits 0-1 ... base -1 at bits 14-15
+    const uint32_t v8 = gather8(a.z, b.z) >> 24;                                    // bit 0 = byte -8 ... bit 7 = byte -1
+    return (codes16 >> (16 - 2 * KM1)) | ((v8 >> (8 - KM1)) << 16);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kCountThreads)
+countd_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ chunks, Plan* __restrict__ plan,
+              uint32_t* __restrict__ slabs)
+{
+    pdl_wait();
+    static_assert(K <= 7, "u32 bins of 4^K fit shared memory up to k = 7");
+    const uint4* __restrict__ text16 = reinterpret_cast<const uint4*>(sa->text);
+    const int breaklen = sa->pa.p.breaklength;
+    const uint32_t one = (uint32_t)(sa->n_bytes >> 62) + 1u;          // 1 (texts are shorter than 2^40), but not to ptxas
+    constexpr uint32_t NK = 1u << (2 * K);
+    constexpr int KM1 = K - 1;
+    constexpr uint32_t FULL = 0xffffffffu;
+    extern __shared__ uint32_t s_raw[];           // [pad to a 64 KiB shared address][NK bins][trash word]
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+
+    const int seg = cta_segment(plan, lane);
+    if (seg < 0) return;
+    const unsigned long long nc64 = plan->seg_chunks[seg] < plan->seg_ccap[seg] ? plan->seg_chunks[seg] : plan->seg_ccap[seg];
+    const uint32_t n_chunks = nc64 < 0xffffff00ull ? (uint32_t)nc64 : 0xffffff00u;
+
+    const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(s_raw);
+    const uint32_t hist_addr = (raw_addr + 0xFFFFu) & ~0xFFFFu;
+    uint32_t* const s_hist = s_raw + ((hist_addr - raw_addr) >> 2);
+    const uint32_t trash_addr = hist_addr + NK * 4u;
+    for (uint32_t i = tid; i < NK + 32; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+
+    DescStream ds;
+    ds.init(text16, chunks + plan->seg_cbegin[seg], n_chunks, &plan->seg_next[seg], lane, plan->n_bytes,
+            (plan->seg_cta_begin[seg + 1] - plan->seg_cta_begin[seg]) * (blockDim.x >> 5));
+    uint32_t carry = 0;
+    bool cur_first, nxt_first;
+    uint2 cur_left, nxt_left;
+    Chunk cur = ds.fetch(cur_first, cur_left);
+    while (__ballot_sync(FULL, cur.range != 0) != 0) {
+        const Chunk nxt = ds.fetch(nxt_first, nxt_left);
+        if (cur_first) carry = tail_from_left8<K>(cur_left, one);      // warp-uniform; only lane 0's value is used
+        const Decoded d = decode_chunk<K, false>(cur, carry, lane, breaklen, one);
+        const uint64_t Wa = ((uint64_t)d.Cc | ((uint64_t)d.Plo << (2 * KM1))) << 2;
+        const uint64_t Wb = ((uint64_t)(d.Plo >> (32 - 2 * KM1)) | ((uint64_t)d.Phi << (2 * KM1))) << 2;
+        emit16<K, kSmem32>(Wa, d.E & 0xFFFFu, hist_addr, trash_addr, nullptr);
+        emit16<K, kSmem32>(Wb, d.E >> 16, hist_addr, trash_addr, nullptr);
+        cur = nxt;
+        cur_first = nxt_first;
+        cur_left = nxt_left;
+    }
+    __syncthreads();
+    uint32_t* slab = slabs + (size_t)logical_cta() * NK;
+    for (uint32_t i = tid; i < NK; i += blockDim.x) slab[i] = s_hist[i];
+}
+
 // ------------------------------------------------------------------------------------------ kSmem16
 // 4^8 bins of 16 bits, two per 32-bit word: bin b lives in word (b & 0x7FFF); bins with bit 15 clear are counted
 // by adding 1, bins with bit 15 set by adding 0x10001.  So the LOW half of a word is the total of its two bins and

@@ -525,6 +525,7 @@ plan_kernel(const StepArgs* __restrict__ sa, uint64_t* __restrict__ starts, uint
         plan->seg_bases[l] = 0;
         plan->seg_next[l] = 0;
         plan->seg_next2[l] = 0;
+        plan->seg_chunks[l] = 0;
         s_frac[l] = all ? 1.0 : (double)thr * 5.421010862427522e-20;      // thr / 2^64
     }
     __syncthreads();
@@ -564,8 +565,31 @@ plan_kernel(const StepArgs* __restrict__ sa, uint64_t* __restrict__ starts, uint
                 off += s_cap[s];
             }
             s_off = off;
-            plan->bucket_overflow = off > a.cap_sorted ? 1u : 0u;
+            plan->bucket_overflow = (a.cap_chunks == 0 && off > a.cap_sorted) ? 1u : 0u;
             s_wsum = wsum;
+            // chunk table (k <= 7): a read of len bases whose first base sits rlo bytes into its 16-byte word has
+            // (rlo + len + 31) / 32 chunks, at most len / 32 + 2; regions from the same expected shares
+            uint64_t coff = 0;
+            if (a.cap_chunks) {
+                const double B = (double)plan->nsites_true / 32.0 + 2.0 * (double)n_reads;      // upper bound on all chunks
+                const double per_read = n_reads ? B / (double)n_reads : 0.0;
+                for (int s2 = 0; s2 < nl; ++s2) {
+                    const double e = (double)n_reads * s_w[s2];
+                    double capd = a.test_tight ? 0.5 * e * per_read + 1.0 : (e + 8.0 * sqrt(e) + 1024.0) * per_read + 4096.0;
+                    if (a.exact_layout || capd > B + 4096.0) capd = B + 4096.0;
+                    const uint64_t cap = ((uint64_t)capd + 255u) & ~255ull;
+                    plan->seg_cbegin[s2] = coff;
+                    plan->seg_ccap[s2] = cap;
+                    coff += cap;
+                }
+                plan->chunks_needed = coff;
+                plan->chunk_table_small = coff > a.cap_chunks ? 1u : 0u;
+            } else {
+                plan->chunks_needed = 0;
+                plan->chunk_table_small = 0;
+            }
+            for (int s2 = a.cap_chunks ? nl : 0; s2 < kMaxLevels; ++s2) { plan->seg_cbegin[s2] = coff; plan->seg_ccap[s2] = 0; }
+            plan->seg_cbegin[kMaxLevels] = coff;
         }
         __syncthreads();
         if (l >= nl) plan->seg_begin[l] = s_off;           // empty regions at the end
@@ -612,10 +636,12 @@ plan_kernel(const StepArgs* __restrict__ sa, uint64_t* __restrict__ starts, uint
         // capacity were never written, regions would lie outside `sorted`.  No CTA gets a segment, no region has room;
         // bucket_scatter_kernel and base_content_kernel return at once when they see either flag.
         __syncthreads();
-        if (plan->table_overflow || plan->bucket_overflow) {
+        if (plan->table_overflow || plan->bucket_overflow || plan->chunk_table_small) {
             plan->seg_cta_begin[l] = 0;
             plan->seg_cap[l] = 0;
             plan->seg_begin[l] = 0;
+            plan->seg_ccap[l] = 0;
+            plan->seg_cbegin[l] = 0;
             if (l == 0) { plan->seg_cta_begin[kMaxLevels] = 0; plan->seg_begin[kMaxLevels] = 0; }
         }
     }
