@@ -445,7 +445,8 @@ def test_fire_and_forget_bins_fall_back_when_they_wrap(monkeypatch, k):
     monkeypatch.setenv("VK_COUNT_PAIRS", "1")
     engine = Engine(0)
     rng = np.random.default_rng(77 + k)
-    reads = ["A" * 150] * 100_000 + rand_reads(rng, 3000, 0, 200, p_n=0.01) + ["C" * 149] * 2500
+    # one CTA of the 148 must see more than 65 535 increments of one word: k = 7 counts 7-mer PAIRS, so twice the reads
+    reads = ["A" * 150] * (220_000 if k == 7 else 100_000) + rand_reads(rng, 3000, 0, 200, p_n=0.01) + ["C" * 149] * 2500
     buf = fastq([reads[i] for i in rng.permutation(len(reads))])
     p = Params(k=k, min_bp=0, max_bp=None, is_query=True)
     _, res, canon, _ = gpu_counts(engine, buf, p)
@@ -477,6 +478,40 @@ def test_exact_16bit_kernels_without_fallback(monkeypatch, k):
     n = engine.count_fallbacks()
     engine.close()
     assert (canon[0] == dsk.canonical_counts(buf, k)).all() and n == 0
+
+
+def test_read_aligned_pairs_every_parity_and_edge(monkeypatch):
+    """k = 7 pair kernel on the chunk table (countp_kernel): reads of every length 0..75 at every text alignment (the
+    header lengths walk the 16-byte phase), N at every position of a read, runs of N, reads that end exactly on a chunk
+    boundary (the dangling first 7-mer of a last chunk), long reads with break points, lowercase and IUPAC bytes -- bit-exact
+    against the oracle, with and without the break length."""
+    from varkoder_b200.engine import Engine
+    monkeypatch.setenv("VK_COUNT_PAIRS", "1")
+    eng = Engine(0)
+    try:
+        rng = np.random.default_rng(2718)
+        reads, headers = [], []
+        for L in range(0, 76):
+            for rep in range(3):
+                reads.append("".join(rng.choice(list("ACGT"), L)))
+                headers.append("@" + "h" * int(rng.integers(1, 34)))
+        base = "".join(rng.choice(list("ACGT"), 90))
+        for pos in range(90):
+            reads.append(base[:pos] + "N" + base[pos + 1:])
+            headers.append("@" + "x" * (pos % 17 + 1))
+        reads += [base[:20] + "NNNNNNN" + base[27:], "N" * 40, "acgtacgtacgtRYKMacgtacgtacgtnACGTACGTAC", "ACGTAC" * 200, "G" * 1001, "A" * 500,
+                  "C" * 501, "T" * 499, "ACGGTCA" * 150]
+        headers += ["@q%d" % i for i in range(9)]
+        reads += rand_reads(rng, 1500, 0, 300, p_n=0.01)
+        headers += ["@" + "r" * int(rng.integers(1, 40)) for _ in range(1500)]
+        order = rng.permutation(len(reads))
+        buf = fastq([reads[i] for i in order], headers=[headers[i] for i in order])
+        for bl in (500, 0, 64):
+            _, res, canon, _ = gpu_counts(eng, buf, Params(k=7, min_bp=0, max_bp=None, is_query=True, breaklength=bl))
+            assert (canon[0] == dsk.canonical_counts(buf, 7, breaklen=bl)).all(), bl
+        assert eng.count_fallbacks() == 0
+    finally:
+        eng.close()
 
 
 def test_pair_counting_ladder_exact(monkeypatch):
@@ -859,8 +894,10 @@ def test_base_content_argument_and_state_errors():
 
 
 # ------------------------------------------------------------------- step variants: graph / plain, packed / text
-@pytest.mark.parametrize("packed,graph,chunks", [("1", "1", "1"), ("1", "0", "1"), ("0", "1", "1"), ("0", "0", "1"), ("0", "1", "0")])
-def test_step_variants_bit_exact(monkeypatch, packed, graph, chunks):
+@pytest.mark.parametrize("packed,graph,chunks,pairs", [("1", "1", "1", "0"), ("1", "0", "1", "0"), ("0", "1", "1", "0"),
+                                                       ("0", "0", "1", "0"), ("0", "1", "0", "0"), ("0", "1", "1", "1"),
+                                                       ("0", "0", "0", "1")])
+def test_step_variants_bit_exact(monkeypatch, packed, graph, chunks, pairs):
     """The fused call in its forms -- submitted as one CUDA graph or kernel by kernel, count kernels fed by the 2-bit
     pack of the framing pass or classifying the text themselves, from the chunk table or from the read table -- on samples of very different sizes through ONE
     context (a graph captured for the first sample must serve the others: everything that differs travels in the
@@ -869,6 +906,7 @@ def test_step_variants_bit_exact(monkeypatch, packed, graph, chunks):
     monkeypatch.setenv("VK_PACKED", packed)
     monkeypatch.setenv("VK_GRAPH", graph)
     monkeypatch.setenv("VK_CHUNKS", chunks)      # k <= 7: chunk table written by the scatter kernel / chunk stream in the count kernel
+    monkeypatch.setenv("VK_COUNT_PAIRS", pairs)  # k = 7: one shared-memory increment per base pair (read-aligned pairs with the chunk table)
     eng = Engine(0)
     try:
         rng = np.random.default_rng(17)

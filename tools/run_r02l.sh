@@ -12,7 +12,7 @@ except Exception as e:
     print("ERR", e); print(open(sys.argv[1].replace(".json",".err")).read()[-1500:])
 PY
 }
-for C in 1 0; do
-VK_CHUNKS=$C timeout 300 python bench.py --steps 400 --warmup 3 --no-cpu-baseline --no-side-legs --e2e-steps 4 > gpurun_out/r02l_bench_chunks$C.json 2> gpurun_out/r02l_bench_chunks$C.err; echo chunks=$C; show gpurun_out/r02l_bench_chunks$C.json
+for C in 1 0 P; do
+if [ $C = P ]; then export VK_COUNT_PAIRS=1; C=1; fi; VK_CHUNKS=$C timeout 300 python bench.py --steps 400 --warmup 3 --no-cpu-baseline --no-side-legs --e2e-steps 4 > gpurun_out/r02l_bench_chunks${C}_p${VK_COUNT_PAIRS:-0}.json 2> gpurun_out/r02l_bench_chunks${C}_p${VK_COUNT_PAIRS:-0}.err; echo chunks=$C; show gpurun_out/r02l_bench_chunks${C}_p${VK_COUNT_PAIRS:-0}.json
 done
-VK_TRACE_EACH=1 python tools/trace_step.py 2> gpurun_out/r02l_trace.log; tail -12 gpurun_out/r02l_trace.log | cut -c1-110
+VK_COUNT_PAIRS=1 VK_TRACE_EACH=1 python tools/trace_step.py 2> gpurun_out/r02l_trace.log; tail -12 gpurun_out/r02l_trace.log | cut -c1-110

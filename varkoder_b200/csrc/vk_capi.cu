@@ -124,7 +124,7 @@ struct vk_ctx {
     bool use_chunks = true;         // VK_CHUNKS=0: k <= 7 counts from the segment-sorted READ table (chunk stream worked out in
                                     // the count kernel) instead of the chunk table the scatter kernel writes
     DevBuf<uint64_t> chunks;        // chunk table: one descriptor per 32-byte chunk of every selected read
-    bool chunk_mode(int k) const { return use_chunks && k <= 7 && !use_packed && !(k == 7 && use_pairs); }
+    bool chunk_mode(int k) const { return use_chunks && k <= 7 && !use_packed && n_bytes < vk::kChunkMaxText; }
     DevBuf<uint4> codes;            // 2-bit codes of every text byte, 16 B per 64 text bytes (parse_mask_kernel<true>)
     DevBuf<uint2> valid;            // validity bits, 8 B per 64 text bytes
     // one step = one CUDA graph: captured once per (k, pixel table, levels, layout) and replayed for every sample
@@ -334,6 +334,8 @@ void prepare_count_kernels()
         CU(cudaFuncSetAttribute(count_kernel<K, kSmem32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CU(cudaFuncSetAttribute(count_kernel<K, kSmem32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CU(cudaFuncSetAttribute(countd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if constexpr (K == 7)
+            CU(cudaFuncSetAttribute(countp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((32768 + 16384) * sizeof(uint32_t))));
     }
     if constexpr (K == 7 || K == 8) {
         const int smem = (int)((size_t)(32768 + (K == 7 ? 16384 : 0)) * sizeof(uint32_t));
@@ -355,6 +357,8 @@ void prepare_kernels()
     prepare_count_kernels<7>();
     prepare_count_kernels<8>();
     prepare_count_kernels<9>();
+    CU(cudaFuncSetAttribute(vk::bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(vk::kStageChunks * sizeof(uint64_t))));
     // the cluster image kernel: up to 8 slices of 2048 keys
     CU(cudaFuncSetAttribute(vk::image_kernel_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)((size_t)vk::kImgCluster * 2048 * sizeof(unsigned long long))));
@@ -370,11 +374,21 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
     const uint64_t total = (uint64_t)kMaxLevels * NK;
     const StepArgs* sa = c->args_d;
     const PackedSrc pk = {reinterpret_cast<const uint2*>(c->codes.p), reinterpret_cast<const uint32_t*>(c->valid.p)};
+    if constexpr (K == 7) {
+        // k = 7 in read-aligned pairs from the chunk table (countp_kernel); a wrapped bin repeats the count with the u32 kernel
+        if (c->use_pairs && c->chunk_mode(7) && c->use_fast && !c->count_safe) {
+            const size_t smem = (size_t)(32768 + 16384) * sizeof(uint32_t);
+            launch(c, countp_kernel, grid, block, smem, sa, (const uint64_t*)c->chunks.p, c->plan_d, c->slabs.p);
+            c->mark(EV_COUNT);
+            launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist);
+            return;
+        }
+    }
     if constexpr (K == 7 || K == 8) {
         // 16-bit bins in shared memory: k = 8 directly, k = 7 through pairs (vk_count.cuh).  The fire-and-forget form by
         // default; after it reported a wrapped bin (count_safe) the exact form -- for k = 7 that is the u32 kernel below.
         const bool fast = c->use_fast && !c->count_safe;
-        if (K == 8 ? c->use_count16 : (c->use_pairs && (fast || !c->use_fast))) {
+        if (K == 8 ? c->use_count16 : (c->use_pairs && !c->chunk_mode(7) && (fast || !c->use_fast))) {
             const size_t smem = (size_t)(32768 + (K == 7 ? 16384 : 0)) * sizeof(uint32_t);
             if (fast) launch(c, (count16_kernel<K, PACKED, true>), grid, block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p);
             else launch(c, (count16_kernel<K, PACKED, false>), grid, block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p);
@@ -413,7 +427,8 @@ void enqueue_count(vk_ctx* c, int k, unsigned long long* seg_hist)
 {
     using namespace vk;
     const int bgrid = c->n_sms * 8;
-    launch(c, bucket_scatter_kernel, dim3(bgrid), dim3(kBucketThreads), 0, c->starts.p, c->ends.p, (const StepArgs*)c->args_d, 0,
+    launch(c, bucket_scatter_kernel, dim3(bgrid), dim3(kBucketThreads), c->chunk_mode(k) ? kStageChunks * sizeof(uint64_t) : 0,
+           c->starts.p, c->ends.p, (const StepArgs*)c->args_d, 0,
            c->sorted.p, c->chunk_mode(k) ? c->chunks.p : (uint64_t*)nullptr, c->plan_d);
     CU(cudaGetLastError());
     c->mark(EV_BUCKET);

@@ -130,17 +130,28 @@ __host__ __device__ __forceinline__ uint32_t internal_revcomp(uint32_t i, int k)
 }
 
 // ---- chunk descriptor (k <= 7 count path): one 32-byte text chunk of one read --------------------------------------
-//   bits  0..33  index of the 16-byte text word the chunk starts at (texts up to 2^38 bytes)
-//   bits 34..37  rlo: offset of the read's first base inside its first 16-byte word (every chunk of the read carries it)
-//   bits 38..42  hi - 1: the chunk's bytes [lo, hi) belong to the read, lo = rlo in the read's first chunk and 0 after it
-//   bits 43..61  j: number of the chunk inside its read (reads of up to 2^24 - 1 bases have fewer than 2^19 chunks)
+//   bits  0..32  index of the 16-byte text word the chunk starts at (texts below 2^37 bytes = 137 GB; larger ones count
+//                from the read table)
+//   bits 33..36  rlo: offset of the read's first base inside its first 16-byte word (every chunk of the read carries it)
+//   bits 37..41  hi - 1: the chunk's bytes [lo, hi) belong to the read, lo = rlo in the read's first chunk and 0 after it
+//   bits 42..60  j: number of the chunk inside its read (reads of up to 2^24 - 1 bases have fewer than 2^19 chunks)
+//   bit  61      this is the read's last chunk
 //   bit  62      the read is longer than the break length (reformat.sh breaklength; cut points have to be masked)
 //   bit  63      set in every descriptor (0 = empty slot)
 constexpr uint64_t kChunkValid = 1ull << 63;
-__host__ __device__ __forceinline__ uint64_t make_chunk_desc(uint64_t word16, uint32_t rlo, uint32_t hi, uint32_t j, bool is_long)
+constexpr uint64_t kChunkMaxText = 1ull << 37;
+__host__ __device__ __forceinline__ uint64_t make_chunk_desc(uint64_t word16, uint32_t rlo, uint32_t hi, uint32_t j, bool is_last,
+                                                             bool is_long)
 {
-    return kChunkValid | word16 | ((uint64_t)rlo << 34) | ((uint64_t)(hi - 1u) << 38) | ((uint64_t)j << 43) | ((uint64_t)(is_long ? 1u : 0u) << 62);
+    return kChunkValid | word16 | ((uint64_t)rlo << 33) | ((uint64_t)(hi - 1u) << 37) | ((uint64_t)j << 42) |
+           ((uint64_t)(is_last ? 1u : 0u) << 61) | ((uint64_t)(is_long ? 1u : 0u) << 62);
 }
+__device__ __forceinline__ uint64_t chunk_word16(uint64_t d) { return d & ((1ull << 33) - 1); }
+__device__ __forceinline__ uint32_t chunk_rlo(uint64_t d) { return (uint32_t)(d >> 33) & 15u; }
+__device__ __forceinline__ uint32_t chunk_hi(uint64_t d) { return ((uint32_t)(d >> 37) & 31u) + 1u; }
+__device__ __forceinline__ uint32_t chunk_j(uint64_t d) { return (uint32_t)(d >> 42) & 0x7FFFFu; }
+__device__ __forceinline__ bool chunk_last(uint64_t d) { return (d >> 61) & 1u; }
+__device__ __forceinline__ bool chunk_long(uint64_t d) { return (d >> 62) & 1u; }
 
 // programmatic dependent launch: block until the preceding kernel of the stream has completed and its writes are
 // visible (no-op when the kernel was not launched with programmatic stream serialisation)

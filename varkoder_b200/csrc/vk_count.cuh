@@ -77,6 +77,12 @@ __device__ __forceinline__ void smem_add(uint32_t shared_addr, uint32_t v)
 {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(shared_addr), "r"(v) : "memory");      // SASS: ATOMS.ADD, nothing comes back
 }
+__device__ __forceinline__ uint32_t mad_hi_u32(uint32_t a, uint32_t b, uint32_t c)      // (a * b >> 32) + c, one IMAD.HI
+{
+    uint32_t d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ uint32_t smem_add_ret(uint32_t shared_addr, uint32_t v)
 {
     uint32_t old;
@@ -474,6 +480,7 @@ struct DescStream {
     uint64_t dnext;             // descriptor of the next fetch (its load was issued one fetch ago)
     uint64_t text_words;        // VK_ASSERT only
     bool at_start;              // the next window opens a claimed range
+    bool is_last;               // the chunk handed out by the last fetch() is its read's last
 
     // guided: 16 iterations per claim while the segment has plenty left, fewer towards its end, so that the warps of a
     // segment finish within an iteration or two of each other
@@ -514,8 +521,8 @@ struct DescStream {
         c.wb = c.wa;
         left8 = make_uint2(0, 0);
         const bool act = (d & kChunkValid) != 0;
-        const uint64_t word16 = d & ((1ull << 34) - 1);
-        const uint32_t rlo = (uint32_t)(d >> 34) & 15u, hi = ((uint32_t)(d >> 38) & 31u) + 1u, j = (uint32_t)(d >> 43) & 0x7FFFFu;
+        const uint64_t word16 = chunk_word16(d);
+        const uint32_t rlo = chunk_rlo(d), hi = chunk_hi(d), j = chunk_j(d);
         const uint32_t lo = j == 0 ? rlo : 0u;
         if (act) {
             const uint4* const ptr = text16 + word16;
@@ -526,7 +533,8 @@ struct DescStream {
         }
         c.range = act ? (0xffffffffu >> (32u - hi)) & (0xffffffffu << lo) : 0u;
         c.j = j;
-        c.rlen = ((uint32_t)(d >> 62) & 1u) ? 0xFFFFFFu : 0u;          // only "longer than the break length" is known here
+        c.rlen = chunk_long(d) ? 0xFFFFFFu : 0u;          // only "longer than the break length" is known here
+        is_last = chunk_last(d);
         c.q0 = (int32_t)(32u * j) - (int32_t)rlo;
         c.last = 31u;
         pos += 32u;
@@ -836,6 +844,158 @@ count16_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __
         if (tid == 0 && s_chk[0] != s_chk[1]) atomicOr(&plan->count_overflow, 1u);
     }
     count16_flush<K>(h8, h7, slab, tid, nthr);
+}
+
+// ---- k = 7 in PAIRS from the chunk table.  Two consecutive 7-mers are one 8-mer: one shared-memory increment per base
+// PAIR, into 4^8 16-bit bins (two per 32-bit word; count16_kernel below describes the bin format, its FAST form the
+// fire-and-forget increments and the end-of-kernel checksum that this kernel shares).  What makes pairs pay here:
+//   * pairs are aligned to the READ, not to the text: the first 7-mer of a read (or of a 500-base piece: the break length
+//     is even) ends at chunk position rlo + 6, so with parity = rlo & 1 every 7-mer of an N-free read has its partner and
+//     only an odd count of 7-mers leaves ONE single at the read's end -- text-aligned pairs left a single at one end of
+//     every other read and a loop over singles in every iteration;
+//   * a pair is owned by the chunk that holds its SECOND 7-mer: the chunk carries 7 bases (not 6) from its left neighbour
+//     and counts the pair (-1, 0) itself; a first 7-mer at position 31 is left to the next chunk, unless the chunk is its
+//     read's last (descriptor flag), then it is a single;
+//   * singles (read ends, around N) go to a 4^7 x u32 table in a loop that most iterations skip.
+// Per pair: funnel shift, address mask, half-select bit -> increment (multiply-add on the FMA pipe), one ATOMS.ADD.
+__global__ void __launch_bounds__(kCountThreads)
+countp_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ chunks, Plan* __restrict__ plan,
+              uint32_t* __restrict__ slabs)
+{
+    pdl_wait();
+    constexpr int K = 7;
+    constexpr uint32_t NK = 1u << (2 * K);
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint4* __restrict__ text16 = reinterpret_cast<const uint4*>(sa->text);
+    const int breaklen = sa->pa.p.breaklength;
+    const uint32_t zero = (uint32_t)(sa->n_bytes >> 62);              // 0 (texts are shorter than 2^40), but not to ptxas
+    const uint32_t one = zero + 1u, two31 = 0x80000000u >> zero;
+    extern __shared__ uint32_t s_raw[];           // [h8: 32768 words][h7: 16384 words]
+    __shared__ unsigned long long s_chk[2];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
+
+    const int seg = cta_segment(plan, lane);
+    if (seg < 0) return;
+    const unsigned long long nc64 = plan->seg_chunks[seg] < plan->seg_ccap[seg] ? plan->seg_chunks[seg] : plan->seg_ccap[seg];
+    const uint32_t n_chunks = nc64 < 0xffffff00ull ? (uint32_t)nc64 : 0xffffff00u;
+
+    uint32_t* const h8 = s_raw;
+    uint32_t* const h7 = s_raw + 32768;
+    const uint32_t h8_addr = (uint32_t)__cvta_generic_to_shared(s_raw);
+    const uint32_t h7_addr = h8_addr + 32768u * 4u;
+    uint32_t* const slab = slabs + (size_t)logical_cta() * NK;
+    for (uint32_t i = tid; i < 32768u + 16384u; i += nthr) s_raw[i] = 0;
+    for (uint32_t i = tid; i < NK; i += nthr) slab[i] = 0;
+    if (tid < 2) s_chk[tid] = 0;
+    __syncthreads();
+
+    DescStream ds;
+    ds.init(text16, chunks + plan->seg_cbegin[seg], n_chunks, &plan->seg_next[seg], lane, plan->n_bytes,
+            (plan->seg_cta_begin[seg + 1] - plan->seg_cta_begin[seg]) * (blockDim.x >> 5));
+    uint32_t carry = 0;             // tail of lane 31 of the previous window: 7 codes (bits 0..13) + 7 validity bits (16..22)
+    uint32_t made = 0;              // pair increments of this lane
+    bool cur_first, nxt_first;
+    uint2 cur_left, nxt_left;
+    Chunk cur = ds.fetch(cur_first, cur_left);
+    bool cur_last = ds.is_last;
+    while (__ballot_sync(FULL, cur.range != 0) != 0) {
+        const Chunk nxt = ds.fetch(nxt_first, nxt_left);
+        const bool nxt_last = ds.is_last;
+        // ---- codes and validity of the 32 bytes (as decode_chunk), 7 bases of left context
+        const Cls4z c0 = classify4z(cur.wa.x, one), c1 = classify4z(cur.wa.y, one), c2 = classify4z(cur.wa.z, one), c3 = classify4z(cur.wa.w, one);
+        const Cls4z c4 = classify4z(cur.wb.x, one), c5 = classify4z(cur.wb.y, one), c6 = classify4z(cur.wb.z, one), c7 = classify4z(cur.wb.w, one);
+        const uint32_t v01 = gather8(c0.z, c1.z), v23 = gather8(c2.z, c3.z), v45 = gather8(c4.z, c5.z), v67 = gather8(c6.z, c7.z);
+        const uint32_t V = __byte_perm(__byte_perm(v01, v23, 0x0073), __byte_perm(v45, v67, 0x0073), 0x5410) & cur.range;
+        const uint32_t Plo = __byte_perm(__byte_perm(c0.packed_hi, c1.packed_hi, 0x0073), __byte_perm(c2.packed_hi, c3.packed_hi, 0x0073), 0x5410);
+        const uint32_t Phi = __byte_perm(__byte_perm(c4.packed_hi, c5.packed_hi, 0x0073), __byte_perm(c6.packed_hi, c7.packed_hi, 0x0073), 0x5410);
+        if (cur_first) {            // warp-uniform; only lane 0's value is used: the 8 text bytes in front of its chunk
+            const Cls4z a = classify4z(cur_left.x, one), b = classify4z(cur_left.y, one);
+            const uint32_t codes16 = (a.packed_hi >> 24) | ((b.packed_hi >> 24) << 8);
+            carry = (codes16 >> 2) | (((gather8(a.z, b.z) >> 24) >> 1) << 16);
+        }
+        const uint32_t tail = (Phi >> 18) | ((V >> 25) << 16);
+        uint32_t hist = __shfl_up_sync(FULL, tail, 1);
+        if (lane == 0) hist = carry;
+        if (cur.j == 0) hist = 0;
+        carry = __shfl_sync(FULL, tail, 31);
+        const uint32_t C7 = hist & 0x3FFFu;
+        const uint64_t VW = (uint64_t)(hist >> 16) | ((uint64_t)V << 7);        // bit i <-> base i - 7 of the chunk
+        uint64_t EE = runs_of_k64<K>(VW) & 0x1FFFFFFFFull;                      // bit p + 1: the 7-mer that ends at base p, p = -1..31
+        if (breaklen > 0 && __ballot_sync(FULL, cur.rlen != 0) != 0) {
+            // reformat.sh breaklength: no 7-mer may span a multiple of breaklen counted from the read's first base
+            uint64_t dead = 0;
+            if (cur.rlen != 0 && cur.range != 0) {
+                const int32_t q0 = cur.q0;
+                int32_t cpos = (q0 > 0 ? q0 / breaklen : 0) * breaklen;
+                if (cpos < breaklen) cpos = breaklen;
+                for (; cpos - q0 < 32; cpos += breaklen) {
+                    const int32_t b = cpos - q0;                        // chunk byte that starts the new piece: ends b .. b+5 are dead
+                    if (b + 1 > -(K - 1)) dead |= b + 1 >= 0 ? (uint64_t)((1u << (K - 1)) - 1u) << (b + 1) : (uint64_t)((1u << (K - 1)) - 1u) >> (-(b + 1));
+                }
+            }
+            EE &= ~dead;
+        }
+        // ---- pairs in read parity
+        const uint32_t par = (uint32_t)(-cur.q0) & 1u;                 // rlo & 1: first elements sit at chunk positions of this parity
+        const uint32_t Q = par ? (uint32_t)EE : (uint32_t)(EE >> 1);   // bit 2m: first, bit 2m + 1: second 7-mer of pair slot m
+        const uint32_t F = Q & 0x55555555u, S = (Q >> 1) & 0x55555555u;
+        const uint32_t both = F & S;
+        uint32_t s1 = F & ~S, s2 = S & ~F;                             // singles: first without second / second without first
+        const bool dangling = par && ((EE >> 32) & 1u) && cur_last;    // a first 7-mer at position 31 of a read's last chunk
+        made += __popc(both);
+        // window with 7 bases of context, shifted so that pair slot m is the 16-bit field at bit 4m; times 4 (byte offsets)
+        const uint32_t sft = par ? 0u : 2u;
+        const uint64_t WA = (((uint64_t)C7 | ((uint64_t)Plo << 14)) >> sft) << 2;
+        const uint64_t WB = ((((uint64_t)(Plo >> 18)) | ((uint64_t)Phi << 14)) >> sft) << 2;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint64_t W4 = h ? WB : WA;
+            const uint32_t Wl = (uint32_t)W4, Wh = (uint32_t)(W4 >> 32), B = h ? both >> 16 : both & 0xFFFFu;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const uint32_t sh = __funnelshift_r(Wl, Wh, 4 * m);
+                uint32_t inc = 0;
+                if ((B >> (2 * m)) & 1u) inc = mad_hi_u32(sh & 0x20000u, two31, 1u);      // 1, or 0x10001 for the upper bin of the word
+                smem_add(h8_addr + (sh & 0x1FFFCu), inc);
+            }
+        }
+        // ---- singles: rare (read ends with an odd number of 7-mers, neighbours of N)
+        uint32_t sing = s1 | (s2 << 1);                                // bit 2m: first of slot m, bit 2m + 1: second
+        bool dang = dangling;
+        while (__ballot_sync(FULL, sing != 0 || dang) != 0) {
+            if (sing != 0) {
+                const uint32_t bit = __ffs(sing) - 1;
+                sing &= sing - 1;
+                const uint32_t m = bit >> 1;
+                const uint64_t W4 = m >= 8 ? WB : WA;
+                const uint32_t f16 = (uint32_t)(W4 >> (4 * (m & 7u)));          // (8-mer of slot m) << 2
+                const uint32_t off7 = ((bit & 1u) ? f16 >> 2 : f16) & 0xFFFCu;   // its last / its first 7 bases
+                smem_inc(h7_addr + off7);
+            } else if (dang) {
+                smem_inc(h7_addr + ((Phi >> 18) << 2));                          // the 7-mer that ends at position 31
+                dang = false;
+            }
+        }
+        cur = nxt;
+        cur_first = nxt_first;
+        cur_left = nxt_left;
+        cur_last = nxt_last;
+    }
+    __syncthreads();
+    {
+        unsigned long long low = 0;
+        for (uint32_t w = tid; w < 32768u; w += nthr) low += h8[w] & 0xFFFFu;
+        unsigned long long mine = made;
+#pragma unroll
+        for (int dlt = 16; dlt > 0; dlt >>= 1) {
+            low += __shfl_xor_sync(FULL, low, dlt);
+            mine += __shfl_xor_sync(FULL, mine, dlt);
+        }
+        if (lane == 0) { atomicAdd(&s_chk[0], mine); atomicAdd(&s_chk[1], low); }
+        __syncthreads();
+        if (tid == 0 && s_chk[0] != s_chk[1]) atomicOr(&plan->count_overflow, 1u);
+    }
+    count16_flush<7>(h8, h7, slab, tid, nthr);
 }
 
 // ------------------------------------------------------------------------------------------ k = 9: canonical halves
