@@ -15,12 +15,14 @@
 namespace vk {
 
 constexpr int kBucketThreads = 256;
-constexpr int kBucketItems = 4;      // reads per thread and iteration of the scatter kernel
-constexpr uint32_t kStageChunks = 8192;      // chunk descriptors a block stages in (dynamic) shared memory, 64 KiB: 1024 reads of up to ~230 bases
+constexpr int kBucketItems = 4;      // reads per thread and iteration of the scatter kernel (read-table mode)
+constexpr int kBucketItemsChunk = 2; // chunk mode: half as many, so that the staging area stays small enough for 8 blocks per SM
+constexpr uint32_t kStageChunks = 3072;      // chunk descriptors a block stages in (dynamic) shared memory, 24 KiB: 512 reads of up to ~170 bases
 
 // One pass: scatter (start, len) entries into their segment's region, count reads and bases per segment.
 // Regions were sized from the expected segment shares by plan_kernel (vk_parse.cuh); a read that does not fit
 // raises plan->bucket_overflow and the host repeats the step with regions that hold every read.
+template <int kBucketItems>
 __global__ void __launch_bounds__(kBucketThreads)
 bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __restrict__ ends, const StepArgs* __restrict__ sa,
                       uint64_t text_base, uint64_t* __restrict__ sorted, uint64_t* __restrict__ chunks, Plan* __restrict__ plan)

@@ -121,8 +121,9 @@ struct vk_ctx {
     vk::StepArgs* args_h = nullptr;
     bool use_packed = false;        // VK_PACKED=1 (measured, a net loss); 0: the count kernels classify the text themselves (round-1 path) instead of
                                     // reading the 2-bit codes + validity bits the framing pass writes
-    bool use_chunks = true;         // VK_CHUNKS=0: k <= 7 counts from the segment-sorted READ table (chunk stream worked out in
-                                    // the count kernel) instead of the chunk table the scatter kernel writes
+    bool use_chunks = false;        // VK_CHUNKS=1: k <= 7 counts from a chunk table the scatter kernel writes (one descriptor per
+                                    // 32-byte chunk) instead of working the chunk stream out of the segment-sorted READ table in
+                                    // the count kernel.  Measured (profiles/r02_notes.md): count 139 -> 135 us, scatter 23 -> 51 us: off
     DevBuf<uint64_t> chunks;        // chunk table: one descriptor per 32-byte chunk of every selected read
     bool chunk_mode(int k) const { return use_chunks && k <= 7 && !use_packed && n_bytes < vk::kChunkMaxText; }
     DevBuf<uint4> codes;            // 2-bit codes of every text byte, 16 B per 64 text bytes (parse_mask_kernel<true>)
@@ -357,7 +358,7 @@ void prepare_kernels()
     prepare_count_kernels<7>();
     prepare_count_kernels<8>();
     prepare_count_kernels<9>();
-    CU(cudaFuncSetAttribute(vk::bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(vk::bucket_scatter_kernel<vk::kBucketItemsChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(vk::kStageChunks * sizeof(uint64_t))));
     // the cluster image kernel: up to 8 slices of 2048 keys
     CU(cudaFuncSetAttribute(vk::image_kernel_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -427,9 +428,12 @@ void enqueue_count(vk_ctx* c, int k, unsigned long long* seg_hist)
 {
     using namespace vk;
     const int bgrid = c->n_sms * 8;
-    launch(c, bucket_scatter_kernel, dim3(bgrid), dim3(kBucketThreads), c->chunk_mode(k) ? kStageChunks * sizeof(uint64_t) : 0,
-           c->starts.p, c->ends.p, (const StepArgs*)c->args_d, 0,
-           c->sorted.p, c->chunk_mode(k) ? c->chunks.p : (uint64_t*)nullptr, c->plan_d);
+    if (c->chunk_mode(k))
+        launch(c, bucket_scatter_kernel<kBucketItemsChunk>, dim3(2 * bgrid), dim3(kBucketThreads), kStageChunks * sizeof(uint64_t),
+               c->starts.p, c->ends.p, (const StepArgs*)c->args_d, 0, c->sorted.p, c->chunks.p, c->plan_d);
+    else
+        launch(c, bucket_scatter_kernel<kBucketItems>, dim3(bgrid), dim3(kBucketThreads), 0, c->starts.p, c->ends.p,
+               (const StepArgs*)c->args_d, 0, c->sorted.p, (uint64_t*)nullptr, c->plan_d);
     CU(cudaGetLastError());
     c->mark(EV_BUCKET);
     const bool pk = c->use_packed;

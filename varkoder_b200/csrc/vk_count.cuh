@@ -69,6 +69,16 @@ __device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c)
     asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+// 16 text bytes through the read-only path, asking L2 to fetch the whole 128-byte line on a miss.  A lane's chunk is 32
+// bytes of a ~150-byte sequence line in a 400 MB text: with sector-sized (32-byte) fills the count kernel's DRAM
+// accesses are scattered 32-byte pieces and the HBM delivers 2.7 TB/s of them however many are in flight; the other
+// sectors of the line are wanted a moment later by the neighbouring lanes anyway.
+__device__ __forceinline__ uint4 ldg_text(const uint4* p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L2::128B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void smem_inc(uint32_t shared_addr)
 {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(shared_addr) : "memory");      // SASS: ATOMS.POPC.INC
@@ -292,8 +302,8 @@ struct ChunkStream {
             const uint4* const ptr = text16 + (rstart >> 4) + 2ull * j;
             if (act) {
                 VK_ASSERT((uint64_t)(ptr - text16) + (hi > 16u ? 1 : 0) < text_words && rlen != 0 && j < ((rlo + rlen + 31u) >> 5));
-                c.wa = __ldg(ptr);
-                if (hi > 16u) c.wb = __ldg(ptr + 1);
+                c.wa = ldg_text(ptr);
+                if (hi > 16u) c.wb = ldg_text(ptr + 1);
             }
         }
         c.range = act ? (0xffffffffu >> (32u - hi)) & (0xffffffffu << lo) : 0u;
@@ -474,16 +484,18 @@ struct DescStream {
     const uint64_t* seg_chunks;
     unsigned long long* seg_counter;
     uint32_t n_chunks, lane, n_warps;
-    uint32_t pos, end;          // lane 0's descriptor of the next fetch / end of the claimed range
-    uint32_t nbase, nsize;      // the range after this one, claimed one range ahead
+    uint32_t pos, end;          // where the descriptor loads are (two windows ahead of the window handed out) / end of that range
+    uint32_t nbase, nsize;      // the range after that one, claimed a range ahead
     uint32_t claimed_upto;      // counter value after our last claim (guides the claim size)
-    uint64_t dnext;             // descriptor of the next fetch (its load was issued one fetch ago)
+    uint64_t dA, dB;            // descriptors of the next window and of the one after it
     uint64_t text_words;        // VK_ASSERT only
-    bool at_start;              // the next window opens a claimed range
+    bool fA, fB, fpos;          // "opens a claimed range" of dA, dB and of the window at pos
     bool is_last;               // the chunk handed out by the last fetch() is its read's last
 
-    // guided: 16 iterations per claim while the segment has plenty left, fewer towards its end, so that the warps of a
-    // segment finish within an iteration or two of each other
+    // The kernel's speed is set by how many text bytes it keeps in flight: a lane's 32 bytes sit somewhere in a 400 MB
+    // text, and with ONE window requested ahead (32 KB per SM) the loads' DRAM latency capped the kernel at 2.7 TB/s
+    // whatever the arithmetic did.  The descriptors therefore run two windows ahead, and the text of the window after
+    // next is pulled into L2 (prefetch.global.L2: no register waits for it) while the next window's demand loads fly.
     __device__ __forceinline__ void claim()
     {
         const uint32_t left = claimed_upto < n_chunks ? n_chunks - claimed_upto : 0u;
@@ -497,6 +509,25 @@ struct DescStream {
         claimed_upto = nbase + nsize;
     }
     __device__ __forceinline__ uint64_t load_desc(uint32_t idx) const { return idx < n_chunks ? __ldg(seg_chunks + idx) : 0ull; }
+    __device__ __forceinline__ void advance()
+    {
+        pos += 32u;
+        fpos = false;
+        if (pos >= end) {                    // the range is used up: go on in the one claimed a range ago, claim another
+            pos = nbase;
+            end = nbase + nsize;
+            fpos = true;
+            claim();
+        }
+    }
+    __device__ __forceinline__ void prefetch_text(uint64_t d) const
+    {
+        if (d & kChunkValid) {
+            const uint4* const ptr = text16 + chunk_word16(d);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+            if (chunk_hi(d) > 16u) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 1));
+        }
+    }
     __device__ __forceinline__ void init(const uint4* t, const uint64_t* sc, uint32_t n, unsigned long long* ctr, uint32_t ln,
                                          uint64_t n_bytes, uint32_t n_warps_seg)
     {
@@ -506,17 +537,20 @@ struct DescStream {
         claimed_upto = 0;
         claim();
         pos = nbase; end = nbase + nsize;
-        at_start = true;
-        dnext = load_desc(pos + lane);
+        fpos = true;
         claim();
+        dA = load_desc(pos + lane); fA = fpos; advance();
+        dB = load_desc(pos + lane); fB = fpos; advance();
+        prefetch_text(dA);
+        prefetch_text(dB);
     }
     // this lane's chunk of the coming window (c.range == 0: none).  first: the window opens a claimed range; left8: for
     // lane 0 of such a window, the 8 text bytes in front of its chunk (when the chunk is not its read's first)
     __device__ __forceinline__ Chunk fetch(bool& first, uint2& left8)
     {
         Chunk c;
-        const uint64_t d = dnext;
-        first = at_start;
+        const uint64_t d = dA;
+        first = fA;
         c.wa = make_uint4(0, 0, 0, 0);
         c.wb = c.wa;
         left8 = make_uint2(0, 0);
@@ -527,25 +561,21 @@ struct DescStream {
         if (act) {
             const uint4* const ptr = text16 + word16;
             VK_ASSERT(word16 + (hi > 16u ? 1 : 0) < text_words && hi > lo);
-            c.wa = __ldg(ptr);
-            if (hi > 16u) c.wb = __ldg(ptr + 1);
-            if (at_start && lane == 0 && j != 0) left8 = __ldg(reinterpret_cast<const uint2*>(ptr) - 1);
+            c.wa = ldg_text(ptr);
+            if (hi > 16u) c.wb = ldg_text(ptr + 1);
+            if (first && lane == 0 && j != 0) left8 = __ldg(reinterpret_cast<const uint2*>(ptr) - 1);
         }
         c.range = act ? (0xffffffffu >> (32u - hi)) & (0xffffffffu << lo) : 0u;
         c.j = j;
         c.rlen = chunk_long(d) ? 0xFFFFFFu : 0u;          // only "longer than the break length" is known here
-        is_last = chunk_last(d);
         c.q0 = (int32_t)(32u * j) - (int32_t)rlo;
         c.last = 31u;
-        pos += 32u;
-        at_start = false;
-        if (pos >= end) {                    // this range is used up: go on in the one claimed a range ago, claim another
-            pos = nbase;
-            end = nbase + nsize;
-            at_start = true;
-            claim();
-        }
-        dnext = load_desc(pos + lane);
+        is_last = chunk_last(d);
+        // shift the pipeline: the window after next gets its text pulled into L2, a new descriptor is requested
+        dA = dB; fA = fB;
+        dB = load_desc(pos + lane); fB = fpos;
+        advance();
+        prefetch_text(dA);
         return c;
     }
 };
