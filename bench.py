@@ -889,10 +889,13 @@ def main():
         value = world * n_bases * steps / (dev_ms * 1e-3) / 1e9
         count_s = count_ms * 1e-3
         achieved = n_bases * BYTES_PER_BASE / count_s / 1e9
-        traffic = None
+        kernel_name = "count_kernel<7,smem>" if K <= 7 else ("count9h_kernel" if K == 9 else f"count16_kernel<{K}>")
+        traffic = traffic_src = None
         try:
-            with open(os.path.join(ROOT, "profiles", "count_kernel_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+            with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
+                ent = json.load(f).get(kernel_name)
+            if ent and n_bases == N_BASES:
+                traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
         except Exception:
             pass
         out = {
@@ -907,8 +910,8 @@ def main():
                             "two contexts so that uploads overlap kernels"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "count_kernel<7,smem>" if K <= 7 else ("count9h_kernel" if K == 9 else f"count16_kernel<{K}>"), "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n_bases * BYTES_PER_BASE,
                          "hbm_copy_probe_this_box_gbs": probe_gbs,
                          "kernel_ms": count_s * 1e3,

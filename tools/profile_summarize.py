@@ -49,9 +49,11 @@ for r in rows[2:]:
     if "count_kernel<" in r[idx["Kernel Name"]]:
         rd = to_bytes(r[idx["dram__bytes_read.sum"]], rows[1][idx["dram__bytes_read.sum"]])
         wr = to_bytes(r[idx["dram__bytes_write.sum"]], rows[1][idx["dram__bytes_write.sum"]])
-        json.dump({"kernel": r[idx["Kernel Name"]][:60], "dram_bytes_read": rd, "dram_bytes_write": wr,
-                   "dram_bytes_per_launch": rd + wr, "source": f"profiles/{tag}_ncu_full.txt (ncu --set full, tag {tag})"},
-                  open(os.path.join(P, "count_kernel_traffic.json"), "w"), indent=1)
+        kt = os.path.join(P, "kernel_traffic.json")          # per-kernel table that bench.py's roofline.traffic reads
+        table = json.load(open(kt)) if os.path.exists(kt) else {}
+        table["count_kernel<7,smem>"] = {"dram_bytes_per_launch": rd + wr, "read": rd, "write": wr, "workload": "c2: 200 Mbp, k=7",
+                                         "source": f"profiles/{tag}_ncu_full.txt (ncu --set full, tag {tag})"}
+        json.dump(table, open(kt, "w"), indent=1)
         break
 b = os.path.join(G, f"bench_{tag}.json")
 if os.path.exists(b):
