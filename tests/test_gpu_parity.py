@@ -894,10 +894,10 @@ def test_base_content_argument_and_state_errors():
 
 
 # ------------------------------------------------------------------- step variants: graph / plain, packed / text
-@pytest.mark.parametrize("packed,graph,chunks,pairs", [("1", "1", "1", "0"), ("1", "0", "1", "0"), ("0", "1", "1", "0"),
-                                                       ("0", "0", "1", "0"), ("0", "1", "0", "0"), ("0", "1", "1", "1"),
-                                                       ("0", "0", "0", "1")])
-def test_step_variants_bit_exact(monkeypatch, packed, graph, chunks, pairs):
+@pytest.mark.parametrize("packed,graph,chunks,pairs,lanes", [("1", "1", "1", "0", "0"), ("1", "0", "1", "0", "0"), ("0", "1", "1", "0", "0"),
+                                                             ("0", "0", "1", "0", "0"), ("0", "1", "0", "0", "0"), ("0", "1", "1", "1", "0"),
+                                                             ("0", "0", "0", "1", "0"), ("0", "1", "0", "0", "1"), ("0", "0", "0", "0", "1")])
+def test_step_variants_bit_exact(monkeypatch, packed, graph, chunks, pairs, lanes):
     """The fused call in its forms -- submitted as one CUDA graph or kernel by kernel, count kernels fed by the 2-bit
     pack of the framing pass or classifying the text themselves, from the chunk table or from the read table -- on samples of very different sizes through ONE
     context (a graph captured for the first sample must serve the others: everything that differs travels in the
@@ -907,6 +907,7 @@ def test_step_variants_bit_exact(monkeypatch, packed, graph, chunks, pairs):
     monkeypatch.setenv("VK_GRAPH", graph)
     monkeypatch.setenv("VK_CHUNKS", chunks)      # k <= 7: chunk table written by the scatter kernel / chunk stream in the count kernel
     monkeypatch.setenv("VK_COUNT_PAIRS", pairs)  # k = 7: one shared-memory increment per base pair (read-aligned pairs with the chunk table)
+    monkeypatch.setenv("VK_COUNT_LANES", lanes)  # k = 7: one read per lane, pairs, uniform fast path (countu_kernel)
     eng = Engine(0)
     try:
         rng = np.random.default_rng(17)

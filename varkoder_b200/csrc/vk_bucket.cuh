@@ -35,7 +35,7 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
     __shared__ unsigned long long s_len[kMaxLevels];
     __shared__ unsigned long long s_base[kMaxLevels];
     __shared__ uint64_t s_thr[kMaxLevels], s_begin[kMaxLevels], s_cap[kMaxLevels];
-    __shared__ uint32_t s_long;
+    __shared__ uint32_t s_long, s_lmin, s_lmax;
     // chunk mode (k <= 7, chunks != nullptr): instead of one entry per read, one descriptor per 32-byte chunk of the read
     // goes into the segment's region of the chunk table (vk_common.cuh make_chunk_desc); the count kernel then walks
     // descriptors, coalesced, with nothing to work out per chunk
@@ -64,7 +64,8 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
         s_cbegin[threadIdx.x] = plan->seg_cbegin[threadIdx.x];
         s_ccap[threadIdx.x] = plan->seg_ccap[threadIdx.x];
     }
-    if (threadIdx.x == 0) s_long = 0;
+    if (threadIdx.x == 0) { s_long = 0; s_lmin = 0xFFFFFFFFu; s_lmax = 0; }
+    uint32_t my_min = 0xFFFFFFFFu, my_max = 0;
     // kBucketItems reads per thread and iteration: their table loads are in flight together, and one round trip of the
     // global cursors serves 1024 reads (the kernel is latency-bound: ~1 iteration per CTA at 200 Mbp)
     for (uint64_t r0 = (uint64_t)blockIdx.x * (blockDim.x * kBucketItems); r0 < n_reads; r0 += per_iter * kBucketItems) {
@@ -103,6 +104,8 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
                     seg[i] = lo - 1;
                     if (seg[i] >= 0) {
                         len32 = (uint32_t)len;
+                        my_min = len32 < my_min ? len32 : my_min;
+                        my_max = len32 > my_max ? len32 : my_max;
                         entry[i] = ((st[i] - text_base) << kEntryLenBits) | len;
                     }
                 }
@@ -204,6 +207,13 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
         }
         __syncthreads();
     }
+    // shortest / longest counted read of the sample (which count kernel pays off depends on it, vk_countu.cuh)
+    my_min = __reduce_min_sync(FULL, my_min);
+    my_max = __reduce_max_sync(FULL, my_max);
+    __syncthreads();
+    if (lane == 0 && my_max != 0u) { atomicMin(&s_lmin, my_min); atomicMax(&s_lmax, my_max); }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_lmax != 0u) { atomicMin(&plan->len_min, s_lmin); atomicMax(&plan->len_max, s_lmax); }
     if (threadIdx.x == 0 && s_long) atomicAdd(&plan->long_reads, s_long);
 }
 

@@ -12,6 +12,7 @@
 #include "vk_bucket.cuh"
 #include "vk_common.cuh"
 #include "vk_count.cuh"
+#include "vk_countu.cuh"
 #include "vk_image.cuh"
 #include "vk_parse.cuh"
 #include "vk_quality.cuh"
@@ -107,6 +108,7 @@ struct vk_ctx {
     bool use_count16 = true;        // VK_COUNT16=0: k = 8 with global atomics instead of 16-bit shared-memory bins
     bool use_pairs = false;         // VK_COUNT_PAIRS=1: k = 7 through 8-mer pairs in 16-bit bins (exact; halves the
                                     // shared-memory traffic but costs more instructions: 168 vs 143 us, profiles/r01_notes.md)
+    bool use_lanes = false;         // VK_COUNT_LANES=1: k = 7 with one read per lane, pairs, uniform fast path (countu_kernel)
     bool use_fast = true;           // VK_COUNT_FAST=0: 16-bit bins always through returning adds + drains (exact in one go)
     bool count_safe = false;        // set for the repeat of a step whose fire-and-forget count reported a wrapped bin
     uint64_t count_fallbacks = 0;
@@ -335,8 +337,10 @@ void prepare_count_kernels()
         CU(cudaFuncSetAttribute(count_kernel<K, kSmem32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CU(cudaFuncSetAttribute(count_kernel<K, kSmem32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CU(cudaFuncSetAttribute(countd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        if constexpr (K == 7)
+        if constexpr (K == 7) {
             CU(cudaFuncSetAttribute(countp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((32768 + 16384) * sizeof(uint32_t))));
+            CU(cudaFuncSetAttribute(countu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countu_smem_bytes()));
+        }
     }
     if constexpr (K == 7 || K == 8) {
         const int smem = (int)((size_t)(32768 + (K == 7 ? 16384 : 0)) * sizeof(uint32_t));
@@ -376,6 +380,14 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
     const StepArgs* sa = c->args_d;
     const PackedSrc pk = {reinterpret_cast<const uint2*>(c->codes.p), reinterpret_cast<const uint32_t*>(c->valid.p)};
     if constexpr (K == 7) {
+        // k = 7, one read per lane, pairs (vk_countu.cuh); a wrapped bin repeats the count with the u32 kernel
+        if (c->use_lanes && !PACKED && !c->chunk_mode(7) && c->use_fast && !c->count_safe) {
+            const size_t smem = countu_smem_bytes();
+            launch(c, countu_kernel, grid, block, smem, sa, (const uint64_t*)c->sorted.p, c->plan_d, c->slabs.p, 1u);
+            c->mark(EV_COUNT);
+            launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist);
+            return;
+        }
         // k = 7 in read-aligned pairs from the chunk table (countp_kernel); a wrapped bin repeats the count with the u32 kernel
         if (c->use_pairs && c->chunk_mode(7) && c->use_fast && !c->count_safe) {
             const size_t smem = (size_t)(32768 + 16384) * sizeof(uint32_t);
@@ -792,6 +804,7 @@ int vk_ctx_create(int device, vk_ctx** out)
         if (const char* e = getenv("VK_PDL")) c->use_pdl = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT16")) c->use_count16 = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT_PAIRS")) c->use_pairs = atoi(e) != 0;
+        if (const char* e = getenv("VK_COUNT_LANES")) c->use_lanes = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT_FAST")) c->use_fast = atoi(e) != 0;
         if (const char* e = getenv("VK_PACKED")) c->use_packed = atoi(e) != 0;
         if (const char* e = getenv("VK_CHUNKS")) c->use_chunks = atoi(e) != 0;

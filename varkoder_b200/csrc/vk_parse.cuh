@@ -507,6 +507,8 @@ plan_kernel(const StepArgs* __restrict__ sa, uint64_t* __restrict__ starts, uint
         plan->status = status;
         plan->n_levels = nl;
         plan->long_reads = 0;
+        plan->len_min = 0xFFFFFFFFu;
+        plan->len_max = 0;
         s_nl = nl;
         s_nsites = nsites;
     }
