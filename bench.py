@@ -186,8 +186,8 @@ def cpu_path_once(buf, threads):
     p = dsk.parse_fastq(buf)
     nsites = p["nsites_ref"]
     levels = oimg.ladder(nsites, MIN_BP_CPU, MAX_BP)
-    thr = [0 if bp >= nsites else dsk.threshold(bp, nsites) for bp in levels]
-    take_all = [1 if bp >= nsites else 0 for bp in levels]
+    # level thresholds fitted to the base targets (what reformat.sh samplebasestarget amounts to), as the GPU path does
+    thr, take_all = dsk.level_thresholds(levels, nsites, 1, lens=p["lens"])
     _, canon = dsk.count_levels(buf, K, 1, thr, take_all, threads=threads)
     imgs = [oimg.image_exact(c, lut) for c in canon]
     dt = time.perf_counter() - t0
@@ -470,8 +470,8 @@ def check_sharded_parity(eng, table, world, rank, torch, dist, n_bases=5_000_000
     what = "sharded (library-issued NCCL on the engine's stream; and the staged torch.distributed form) == unsharded on every rank"
     if rank == 0:
         from oracle import dsk, image as oimg                            # checker only
-        thr = [0 if bp >= n_bases else dsk.threshold(bp, n_bases) for bp in rs.levels]
-        _, expect = dsk.count_levels(buf, K, parse_seed(1234), thr, [1 if bp >= n_bases else 0 for bp in rs.levels], threads=0)
+        thr, take_all = dsk.level_thresholds(rs.levels, n_bases, parse_seed(1234), lens=dsk.parse_fastq(buf)["lens"])
+        _, expect = dsk.count_levels(buf, K, parse_seed(1234), thr, take_all, threads=0)
         ok = ok and bool((rs.canon == expect).all()) and all(
             bool((rs.pixels[l] == oimg.image_exact(expect[l], table.lut)).all()) for l in range(len(rs.levels)))
         what += " == CPU oracle (rank 0)"

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VK_ABI_VERSION 1
+#define VK_ABI_VERSION 2
 #define VK_MAX_LEVELS 64 /* ladder levels: 3 per decade, far more than any real sample needs */
 #define VK_MIN_K 5       /* ImageCommand.__init__ accepts k in [5, 9] (image.py:1209) */
 #define VK_MAX_K 9
@@ -57,7 +57,20 @@ typedef struct vk_params {
     uint64_t seed;         /* split_fastq(seed=...) reduced mod 2^64 */
     uint64_t read_index_base; /* global index of this buffer's first record (read-sharded samples) */
     uint64_t nsites_override; /* 0: ladder from this buffer's own base count; else the sample-wide total */
+    /* How a level's reads are drawn (reformat.sh samplebasestarget=<bp>, image.py:582-596, writes reads until the base
+     * target is met).  VK_SAMPLING_CALIBRATED (default of the Python layer): the level's priority threshold is fitted to
+     * the sample -- a histogram of the reads' bases over 2^16 priority buckets gives the bucket in which the cumulative
+     * base count reaches the target, the threshold is interpolated inside it -- so the realised bases meet the target to
+     * within a couple of reads.  VK_SAMPLING_EXPECTED: threshold = bp * 2^64 / nsites, met in expectation only (round 1). */
+    int32_t sampling;
+    int32_t reserved0;
+    /* read-sharded samples: device pointer to the histogram (VK_PRIO_BUCKETS uint64) of the WHOLE sample (vk_prio_hist of every shard,
+     * summed by the caller); 0: the histogram of this buffer's own reads */
+    uint64_t prio_hist;
 } vk_params;
+#define VK_SAMPLING_EXPECTED 0
+#define VK_SAMPLING_CALIBRATED 1
+#define VK_PRIO_BUCKETS 65536
 
 /* What parsing found; mirrors the first loop of split_fastq (image.py:662-667). */
 typedef struct vk_stats {
@@ -113,6 +126,15 @@ int vk_parse(vk_ctx* ctx, vk_stats* out);
  * all-reduce between vk_count and vk_render).  NULL uses a context-owned buffer.  Synchronises.
  */
 int vk_count(vk_ctx* ctx, const vk_params* params, uint64_t* seg_hist_dev, vk_result* out);
+
+/*
+ * Read-sharded samples with VK_SAMPLING_CALIBRATED: the base histogram over the priority buckets of THIS buffer's reads
+ * (after vk_parse; params->seed and params->read_index_base name the reads' global indices), ADDED to
+ * hist_dev[VK_PRIO_BUCKETS] (caller-owned device memory, zeroed by the caller).  The caller sums the shards' histograms
+ * (all-reduce) and passes the result to vk_count as params->prio_hist.  Stands in for the first half of what reformat.sh
+ * samplebasestarget does (image.py:582-596): knowing how many bases the reads drawn so far hold.  Synchronises.
+ */
+int vk_prio_hist(vk_ctx* ctx, const vk_params* params, uint64_t* hist_dev);
 
 /*
  * Canonical fold + pixel mapping + rank scaling for n_levels levels (stands in for dsk2ascii and

@@ -88,15 +88,79 @@ def parse_fastq(buf):
                 n_lines=nl.value, n_reads=int(n))
 
 
-def select_reads(n_reads, seed, target, nsites, read_index_base=0):
-    """the project's sub-sampling rule: read r is kept iff prio(seed, base+r) < floor(target*2^64/nsites);
-    target >= nsites keeps everything."""
-    if target >= nsites:
+PRIO_BUCKETS = 1 << 16          # include/varkoder_b200.h VK_PRIO_BUCKETS
+PRIO_SHIFT = 48
+
+
+def prio_array(seed, first, count):
+    """prio64(seed, r) for r = first .. first + count - 1, vectorised (uint64 arithmetic wraps)."""
+    with np.errstate(over="ignore"):
+        r = np.arange(first + 1, first + 1 + count, dtype=np.uint64)
+        z = np.uint64(seed & MASK64) + r * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def prio_hist(lens, seed, read_index_base=0):
+    """bases of the reads (ALL records of the buffer, whatever their length) per priority bucket, prio >> 48
+    (varkoder_b200/csrc/vk_sample.cuh K1h).  Shards of one sample: add their histograms."""
+    lens = np.asarray(lens, dtype=np.int64)
+    b = (prio_array(seed, read_index_base, lens.size) >> np.uint64(PRIO_SHIFT)).astype(np.int64)
+    # float64 weights are exact here: a bucket holds far fewer than 2^53 bases
+    return np.bincount(b, weights=lens.astype(np.float64), minlength=PRIO_BUCKETS).astype(np.int64)
+
+
+def calibrated_thresholds(hist, levels, nsites):
+    """the thresholds fitted to the base targets (vk_sample.cuh K1t), in exact integers:
+    level with target T -> first bucket b whose cumulative base count reaches T, C = bases before it,
+    thr = (b << 48) + floor((T - C) * 2^48 / hist[b]).  -> (thr[], take_all[])."""
+    hist = np.asarray(hist, dtype=np.int64)
+    cum = np.cumsum(hist)
+    total = int(cum[-1])
+    thr, take_all = [], []
+    for T in levels:
+        T = int(T)
+        if T >= nsites or T >= total:
+            thr.append(0)
+            take_all.append(1)
+            continue
+        b = int(np.searchsorted(cum, T, side="left"))          # first b with cum[b] >= T
+        C = int(cum[b - 1]) if b else 0
+        W = int(hist[b])
+        rem = T - C
+        if rem >= W:
+            t = (b + 1) << PRIO_SHIFT
+        else:
+            t = (b << PRIO_SHIFT) + (((rem << 64) // W) >> (64 - PRIO_SHIFT))
+        if t > MASK64:
+            thr.append(0)
+            take_all.append(1)
+        else:
+            thr.append(t)
+            take_all.append(0)
+    return thr, take_all
+
+
+def level_thresholds(levels, nsites, seed=0, lens=None, hist=None, read_index_base=0):
+    """(thr[], take_all[]) of the ladder levels.  With ``lens`` (all records of the sample, in order) or ``hist`` (their
+    prio_hist, summed over shards): the calibrated rule, the product's default (VK_SAMPLING_CALIBRATED).  With neither:
+    thr = floor(bp * 2^64 / nsites) (VK_SAMPLING_EXPECTED)."""
+    if hist is None and lens is not None:
+        hist = prio_hist(lens, seed, read_index_base)
+    if hist is not None:
+        return calibrated_thresholds(hist, levels, nsites)
+    return ([0 if bp >= nsites else threshold(bp, nsites) for bp in levels], [1 if bp >= nsites else 0 for bp in levels])
+
+
+def select_reads(n_reads, seed, target, nsites, read_index_base=0, lens=None, hist=None):
+    """the project's sub-sampling rule: read r is kept iff prio(seed, base + r) < thr(target); target >= nsites keeps
+    everything.  ``lens`` (all records of the SAMPLE, so that ``n_reads`` == len(lens) for an unsharded buffer) or ``hist``
+    select the calibrated threshold; without them thr = floor(target * 2^64 / nsites)."""
+    (thr,), (all_,) = level_thresholds([target], nsites, seed, lens, hist, 0 if lens is None else 0)
+    if all_:
         return np.ones(n_reads, dtype=np.uint8)
-    thr = threshold(target, nsites)
-    L = lib()
-    return np.fromiter((L.vko_prio(seed & MASK64, read_index_base + r) < thr for r in range(n_reads)),
-                       dtype=np.uint8, count=n_reads)
+    return (prio_array(seed, read_index_base, n_reads) < np.uint64(thr)).astype(np.uint8)
 
 
 def count_forward(buf, starts, lens, k, select=None, breaklen=BREAKLENGTH, threads=1):

@@ -25,12 +25,16 @@ def rand_reads(rng, n, lmin, lmax, p_n=0.01, alphabet="ACGT"):
     return reads
 
 
-def oracle_levels(buf, k, seed, levels, nsites, read_index_base=0):
-    """canon_full per level with the project's selection rule, computed by the CPU oracle."""
+def oracle_levels(buf, k, seed, levels, nsites, read_index_base=0, hist=None, calibrated=True):
+    """canon_full per level with the project's selection rule, computed by the CPU oracle.  ``calibrated`` (the product's
+    default, VK_SAMPLING_CALIBRATED): thresholds fitted to the base targets from the histogram of the WHOLE sample -- the
+    buffer's own reads, or ``hist`` when the buffer is a shard."""
     p = dsk.parse_fastq(buf)
+    if calibrated and hist is None:
+        hist = dsk.prio_hist(p["lens"], seed, read_index_base)
     out = []
     for bp in levels:
-        sel = dsk.select_reads(p["n_reads"], seed, bp, nsites, read_index_base)
+        sel = dsk.select_reads(p["n_reads"], seed, bp, nsites, read_index_base, hist=hist if calibrated else None)
         fwd = dsk.count_forward(buf, p["starts"], p["lens"], k, sel)
         out.append(dsk.fold_canonical(fwd, k))
     return np.stack(out) if out else np.zeros((0, 4 ** k), dtype=np.uint64)
@@ -71,6 +75,13 @@ class OracleEngine:
         return np.ctypeslib.as_array(ctypes.cast(seg_hist_ptr, ctypes.POINTER(ctypes.c_uint64)),
                                      shape=(_lib.VK_MAX_LEVELS, nk))
 
+    def prio_hist(self, params, hist_ptr):
+        import ctypes
+        from varkoder_b200 import _lib
+        from varkoder_b200.ladder import parse_seed
+        h = np.ctypeslib.as_array(ctypes.cast(hist_ptr, ctypes.POINTER(ctypes.c_int64)), shape=(_lib.VK_PRIO_BUCKETS,))
+        h += dsk.prio_hist(self.p["lens"], parse_seed(params.seed), params.read_index_base)
+
     def count(self, params, seg_hist_ptr=None):
         from varkoder_b200 import _lib
         from varkoder_b200.engine import Result
@@ -84,7 +95,16 @@ class OracleEngine:
         except LessThanMinimumData:
             levels, status = [], _lib.VK_LADDER_LESS_THAN_MIN
         seed = parse_seed(params.seed)
-        member = [dsk.select_reads(p["n_reads"], seed, bp, nsites, params.read_index_base).astype(bool) for bp in levels]
+        hist = None
+        if params.sampling == _lib.VK_SAMPLING_CALIBRATED:
+            if params.prio_hist:
+                import ctypes
+                hist = np.ctypeslib.as_array(ctypes.cast(params.prio_hist, ctypes.POINTER(ctypes.c_int64)),
+                                             shape=(_lib.VK_PRIO_BUCKETS,)).copy()
+            else:
+                hist = dsk.prio_hist(p["lens"], seed, params.read_index_base)
+        member = [dsk.select_reads(p["n_reads"], seed, bp, nsites, params.read_index_base, hist=hist).astype(bool)
+                  for bp in levels]
         long_enough = p["lens"] >= k
         out = self._seg(seg_hist_ptr, nk)
         out[:] = 0

@@ -8,7 +8,7 @@ import pytest
 
 from oracle import dsk, image as oimg
 from tests.helpers import fastq, oracle_images, oracle_levels, rand_reads
-from varkoder_b200 import synth
+from varkoder_b200 import _lib, synth
 from varkoder_b200.engine import Params
 from varkoder_b200.mapping import get_kmer_mapping
 
@@ -109,10 +109,13 @@ def test_ladder_levels_bit_exact(engine, k, seed):
     # nested levels: counts are monotone down the ladder; realised bases are near the target
     assert (canon[:-1] >= canon[1:]).all()
     for lvl, bp in enumerate(res.levels):
-        sel = dsk.select_reads(p["n_reads"], parse_seed(seed), bp, p["nsites_ref"])
-        keep = sel.astype(bool) & (p["lens"] >= k)
+        sel = dsk.select_reads(p["n_reads"], parse_seed(seed), bp, p["nsites_ref"], lens=p["lens"]).astype(bool)
+        keep = sel & (p["lens"] >= k)
         assert res.level_reads[lvl] == int(keep.sum())
         assert res.level_bases[lvl] == int(p["lens"][keep].sum())
+        # thresholds fitted to the base targets (reformat.sh samplebasestarget, image.py:582-596): the reads drawn for a
+        # level hold its target to within one read (9000 reads: one per priority bucket)
+        assert bp >= p["nsites_ref"] or abs(int(p["lens"][sel].sum()) - bp) <= int(p["lens"].max())
 
 
 def test_ladder_golden_on_device(engine, golden_dir):
@@ -147,8 +150,17 @@ def test_read_sharding_sums_to_whole(engine):
     shards = [(buf[:cut], 0), (buf[cut:], cut_read)]
     assert dsk.parse_fastq(shards[0][0])["n_reads"] == cut_read
     total = np.zeros_like(whole)
+    # the thresholds are fitted to the WHOLE sample: the shards' base histograms over the priority buckets are summed first
+    import torch
+    hist = torch.zeros(_lib.VK_PRIO_BUCKETS, dtype=torch.int64, device="cuda")
     for sb, base in shards:
-        ps = Params(k=k, min_bp=20000, max_bp=None, seed=77, read_index_base=base, nsites_override=p["nsites_ref"])
+        engine.upload(sb)
+        engine.parse()
+        engine.prio_hist(Params(k=k, seed=77, read_index_base=base), hist.data_ptr())
+    assert (hist.cpu().numpy() == dsk.prio_hist(p["lens"], 77)).all()
+    for sb, base in shards:
+        ps = Params(k=k, min_bp=20000, max_bp=None, seed=77, read_index_base=base, nsites_override=p["nsites_ref"],
+                    prio_hist=hist.data_ptr())
         _, r2, c2, _ = gpu_counts(engine, sb, ps)
         assert r2.levels == res.levels
         total += c2
@@ -281,7 +293,9 @@ def test_full_size_properties_config2(engine):
     for lvl in range(len(res.levels)):
         assert windows[lvl] <= res.level_bases[lvl] - (k - 1) * res.level_reads[lvl]
         assert windows[lvl] >= 0.97 * (res.level_bases[lvl] - (k - 1) * res.level_reads[lvl])
-        assert abs(res.level_bases[lvl] - res.levels[lvl]) <= 0.05 * res.levels[lvl]
+        # thresholds fitted to the base targets: a level misses its target by the interpolation error inside ONE priority
+        # bucket (n_reads / 65536 = 20 reads here (config 2) or 102 (config 3), error a few reads); round 1's fixed thresholds were allowed 5 %
+        assert abs(res.level_bases[lvl] - res.levels[lvl]) <= 12 * L
     assert res.level_bases[0] == n_bases
     # images: rank transform invariants + agreement with the oracle image of the GPU counts
     assert (res.pixels.max(axis=(1, 2)) == 255).all()
@@ -295,11 +309,12 @@ def test_full_size_properties_config2(engine):
         assert (res.pixels[lvl] == oimg.image_exact(expect[lvl], table.lut)).all()
 
 
-def oracle_levels_fast(buf, k, seed, levels, nsites, read_index_base=0):
+def oracle_levels_fast(buf, k, seed, levels, nsites, read_index_base=0, calibrated=True):
     """canon_full per level by the CPU oracle's one-pass multi-level counter (C/OpenMP, all host threads): the same
-    rule as helpers.oracle_levels, fast enough for the BASELINE-size samples."""
-    thr = [0 if bp >= nsites else dsk.threshold(bp, nsites) for bp in levels]
-    take_all = [1 if bp >= nsites else 0 for bp in levels]
+    rule as helpers.oracle_levels (thresholds fitted to the base targets from the buffer's own reads), fast enough for
+    the BASELINE-size samples."""
+    lens = dsk.parse_fastq(buf)["lens"] if calibrated else None
+    thr, take_all = dsk.level_thresholds(levels, nsites, seed, lens=lens, read_index_base=read_index_base)
     _, canon = dsk.count_levels(buf, k, seed, thr, take_all, read_index_base=read_index_base, threads=0)
     return canon
 
@@ -645,7 +660,9 @@ def test_full_size_properties_config3(engine):
     for lvl in range(len(res.levels)):
         full = res.level_bases[lvl] - (k - 1) * res.level_reads[lvl]
         assert 0.96 * full <= windows[lvl] <= full
-        assert abs(res.level_bases[lvl] - res.levels[lvl]) <= 0.05 * res.levels[lvl]
+        # thresholds fitted to the base targets: a level misses its target by the interpolation error inside ONE priority
+        # bucket (n_reads / 65536 = 20 reads here (config 2) or 102 (config 3), error a few reads); round 1's fixed thresholds were allowed 5 %
+        assert abs(res.level_bases[lvl] - res.levels[lvl]) <= 40 * L
     assert res.level_bases[0] == n_bases
     assert res.pixels.shape == (11, 363, 363) and (res.pixels.max(axis=(1, 2)) == 255).all()
     for lvl in (0, 10):
@@ -656,12 +673,17 @@ def test_full_size_properties_config3(engine):
     cut = cut_reads * synth.record_size(L)
     nk = 4 ** k
     segs = []
+    hist = torch.zeros(_lib.VK_PRIO_BUCKETS, dtype=torch.int64, device="cuda")      # of the whole sample: shard by shard
+    for (off, nb, base) in ((0, cut, 0), (cut, total - cut, cut_reads)):
+        engine.attach(dev.data_ptr() + off, nb)
+        engine.parse()
+        engine.prio_hist(Params(k=k, seed=3, read_index_base=base), hist.data_ptr())
     for (off, nb, base) in ((0, cut, 0), (cut, total - cut, cut_reads)):
         engine.attach(dev.data_ptr() + off, nb)
         engine.parse()
         seg = torch.zeros(64 * nk, dtype=torch.int64, device="cuda")
-        r = engine.count(Params(k=k, min_bp=500_000, max_bp=None, seed=3, read_index_base=base, nsites_override=n_bases),
-                         seg.data_ptr())
+        r = engine.count(Params(k=k, min_bp=500_000, max_bp=None, seed=3, read_index_base=base, nsites_override=n_bases,
+                                prio_hist=hist.data_ptr()), seg.data_ptr())
         assert r.levels == res.levels
         segs.append(seg)
     both = segs[0] + segs[1]
@@ -700,14 +722,21 @@ def test_text_beyond_4_gib(engine):
     nk = 4 ** k
     both = torch.zeros(64 * nk, dtype=torch.int64, device="cuda")
     content_sum = np.zeros_like(content)
+    hist = torch.zeros(_lib.VK_PRIO_BUCKETS, dtype=torch.int64, device="cuda")      # of the whole sample: shard by shard
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        off, nb = a * rec, (b * rec if b < res.n_reads else total) - a * rec
+        engine.attach(dev.data_ptr() + off, nb)
+        engine.parse()
+        engine.prio_hist(Params(k=k, seed=5, read_index_base=a), hist.data_ptr())
+    assert int(hist.sum()) == n_bases
     for a, b in zip(cuts[:-1], cuts[1:]):
         off, nb = a * rec, (b * rec if b < res.n_reads else total) - a * rec
         assert nb < 2 ** 32
         engine.attach(dev.data_ptr() + off, nb)
         engine.parse()
         seg = torch.zeros(64 * nk, dtype=torch.int64, device="cuda")
-        r = engine.count(Params(k=k, min_bp=100_000_000, max_bp=None, seed=5, read_index_base=a, nsites_override=n_bases),
-                         seg.data_ptr())
+        r = engine.count(Params(k=k, min_bp=100_000_000, max_bp=None, seed=5, read_index_base=a, nsites_override=n_bases,
+                                prio_hist=hist.data_ptr()), seg.data_ptr())
         assert r.levels == res.levels
         content_sum += engine.base_content(0, 8)
         both += seg

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_loads_and_exports_every_declared_symbol():
     L = _lib.load()
-    assert L.vk_abi_version() == 1
+    assert L.vk_abi_version() == 2
     with open(os.path.join(ROOT, "include", "varkoder_b200.h")) as f:
         header = f.read()
     declared = set(re.findall(r"\b(vk_[a-z_0-9]+)\s*\(", header))
@@ -24,7 +24,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    assert ctypes.sizeof(_lib.VkParams) == 4 * 4 + 5 * 8
+    assert ctypes.sizeof(_lib.VkParams) == 4 * 4 + 5 * 8 + 2 * 4 + 8      # + sampling, reserved0, prio_hist (ABI 2)
     assert ctypes.sizeof(_lib.VkStats) == 5 * 8
     assert ctypes.sizeof(_lib.VkResult) == 5 * 8 + 8 + 3 * 64 * 8
 

@@ -12,11 +12,15 @@ VK_MAX_LEVELS = 64
 VK_BREAKLENGTH = 500
 VK_OK = 0
 VK_LADDER_LESS_THAN_MIN = 1
+VK_SAMPLING_EXPECTED = 0
+VK_SAMPLING_CALIBRATED = 1
+VK_PRIO_BUCKETS = 65536
+VK_ABI_VERSION = 2
 
 # every symbol include/varkoder_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "vk_abi_version", "vk_last_error", "vk_ctx_create", "vk_ctx_destroy", "vk_set_mapping", "vk_upload",
-    "vk_attach", "vk_parse", "vk_count", "vk_render", "vk_render_counts", "vk_reads_to_images", "vk_device_pixels", "vk_remap",
+    "vk_attach", "vk_parse", "vk_count", "vk_prio_hist", "vk_render", "vk_render_counts", "vk_reads_to_images", "vk_device_pixels", "vk_remap",
     "vk_base_content",
     "vk_last_timings", "vk_set_fine_timing", "vk_launch_count", "vk_bucket_retries", "vk_count_fallbacks", "vk_synth_fastq",
     "vk_synth_fastq_variable", "vk_graph_stats",
@@ -27,7 +31,8 @@ SYMBOLS = [
 class VkParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("is_query", C.c_int32), ("has_max_bp", C.c_int32), ("breaklength", C.c_int32),
                 ("min_bp", C.c_uint64), ("max_bp", C.c_uint64), ("seed", C.c_uint64),
-                ("read_index_base", C.c_uint64), ("nsites_override", C.c_uint64)]
+                ("read_index_base", C.c_uint64), ("nsites_override", C.c_uint64),
+                ("sampling", C.c_int32), ("reserved0", C.c_int32), ("prio_hist", C.c_uint64)]
 
 
 class VkStats(C.Structure):
@@ -68,6 +73,7 @@ def load():
     L.vk_attach.argtypes = [vp, vp, C.c_uint64]
     L.vk_parse.argtypes = [vp, C.POINTER(VkStats)]
     L.vk_count.argtypes = [vp, C.POINTER(VkParams), vp, C.POINTER(VkResult)]
+    L.vk_prio_hist.argtypes = [vp, C.POINTER(VkParams), vp]
     L.vk_render.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.vk_render_counts.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
     L.vk_reads_to_images.argtypes = [vp, vp, C.c_uint64, C.c_int, C.POINTER(VkParams), C.c_int, C.c_int,

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -16,6 +17,7 @@
 #include "vk_image.cuh"
 #include "vk_parse.cuh"
 #include "vk_quality.cuh"
+#include "vk_sample.cuh"
 #include "vk_synth.cuh"
 
 namespace {
@@ -160,6 +162,7 @@ struct vk_ctx {
     DevBuf<uint8_t> remap_in, remap_out, remap_mult;
     DevBuf<int32_t> remap_src;
     DevBuf<unsigned long long> content;
+    DevBuf<unsigned long long> prio_hist;        // bases per priority bucket of the current sample (vk_sample.cuh)
     DevBuf<uint64_t> synth_off;     // vk_synth_fastq_variable: record offsets
     Mapping maps[4];
 
@@ -252,7 +255,8 @@ void enqueue_args(vk_ctx* c, const vk_params* params)
 void enqueue_begin(vk_ctx* c, bool rescan)
 {
     launch(c, vk::step_begin_kernel, dim3(8), dim3(1024), 0, reinterpret_cast<const uint32_t*>(c->args_h),
-           reinterpret_cast<uint32_t*>(c->args_d), c->plan_d, c->tile_count.p, (uint32_t)c->tile_count.cap, rescan ? 1 : 0);
+           reinterpret_cast<uint32_t*>(c->args_d), c->plan_d, c->tile_count.p, (uint32_t)c->tile_count.cap, rescan ? 1 : 0,
+           c->prio_hist.p);
     CU(cudaGetLastError());
 }
 
@@ -436,10 +440,21 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
     }
 }
 
-void enqueue_count(vk_ctx* c, int k, unsigned long long* seg_hist)
+// between: what a read-sharded sample does between the histogram and the thresholds (sum the shards' histograms)
+void enqueue_count(vk_ctx* c, int k, unsigned long long* seg_hist, const std::function<void()>& between = nullptr)
 {
     using namespace vk;
     const int bgrid = c->n_sms * 8;
+    // thresholds fitted to the base targets (vk_sample.cuh; both kernels return at once for VK_SAMPLING_EXPECTED): the base
+    // histogram over the priority buckets, then the fit.  A read-sharded sample sums the shards' histograms in between;
+    // a caller that brings the sample's histogram (params.prio_hist) only needs the fit.
+    launch(c, prio_hist_kernel, dim3(c->n_sms * 4), dim3(kPrioHistThreads), 0, c->starts.p, c->ends.p, (const StepArgs*)c->args_d,
+           (const Plan*)c->plan_d, c->prio_hist.p, 0);
+    CU(cudaGetLastError());
+    if (between) between();
+    launch(c, thr_calibrate_kernel, dim3(kCalibCtas), dim3(1024), 0, (const StepArgs*)c->args_d, (const unsigned long long*)c->prio_hist.p,
+           c->prio_hist.p + VK_PRIO_BUCKETS, c->plan_d);
+    CU(cudaGetLastError());
     if (c->chunk_mode(k))
         launch(c, bucket_scatter_kernel<kBucketItemsChunk>, dim3(2 * bgrid), dim3(kBucketThreads), kStageChunks * sizeof(uint64_t),
                c->starts.p, c->ends.p, (const StepArgs*)c->args_d, 0, c->sorted.p, c->chunks.p, c->plan_d);
@@ -606,6 +621,7 @@ void check_params(const vk_params* p)
     if (!p) throw ApiError{VK_EINVAL, "params is NULL"};
     if (p->k < VK_MIN_K || p->k > VK_MAX_K) throw ApiError{VK_EINVAL, "k must be 5..9"};
     if (p->breaklength != 0 && p->breaklength < 32) throw ApiError{VK_EINVAL, "breaklength must be 0 or >= 32"};
+    if (p->sampling != VK_SAMPLING_EXPECTED && p->sampling != VK_SAMPLING_CALIBRATED) throw ApiError{VK_EINVAL, "sampling must be VK_SAMPLING_EXPECTED or VK_SAMPLING_CALIBRATED"};
 }
 
 uint64_t reads_bound(uint64_t n_bytes) { return n_bytes / 24 + 1024; }
@@ -816,6 +832,7 @@ int vk_ctx_create(int device, vk_ctx** out)
         for (int i = 0; i < EV_N; ++i) CU(cudaEventCreate(&c->ev[i]));
         ensure_outbox(c, 0);
         CU(cudaMalloc(&c->args_d, sizeof(vk::StepArgs)));
+        c->prio_hist.ensure(VK_PRIO_BUCKETS + 1024);      // + the block sums of thr_calibrate_kernel
         CU(cudaMallocHost(&c->args_h, sizeof(vk::StepArgs)));
         prepare_kernels();
         *out = c;
@@ -856,6 +873,7 @@ int vk_ctx_destroy(vk_ctx* c)
     c->remap_mult.release();
     c->remap_src.release();
     c->content.release();
+    c->prio_hist.release();
     c->synth_off.release();
     for (auto& m : c->maps) m.lut.release();
     if (c->out_h) cudaFreeHost(c->out_h);
@@ -969,6 +987,25 @@ int vk_count(vk_ctx* c, const vk_params* p, uint64_t* seg_hist_dev, vk_result* o
         c->counted = true;
         c->counted_k = p->k;
         fill_result(*c->plan_h, out);
+    });
+}
+
+// Base histogram over the priority buckets of this buffer's reads, added to the caller's device buffer (read-sharded
+// samples with calibrated thresholds: the caller sums the shards' histograms and hands the sum to vk_count).
+int vk_prio_hist(vk_ctx* c, const vk_params* p, uint64_t* hist_dev)
+{
+    return guarded([&] {
+        if (!c || !hist_dev) throw ApiError{VK_EINVAL, "NULL argument"};
+        check_params(p);
+        if (!c->have_text) throw ApiError{VK_ESTATE, "vk_prio_hist before vk_upload / vk_attach"};
+        if (!c->parsed) throw ApiError{VK_ESTATE, "vk_prio_hist before vk_parse"};
+        set_device(c);
+        enqueue_args(c, p);
+        enqueue_begin(c, false);
+        launch(c, vk::prio_hist_kernel, dim3(c->n_sms * 4), dim3(vk::kPrioHistThreads), 0, c->starts.p, c->ends.p, (const vk::StepArgs*)c->args_d,
+               (const vk::Plan*)c->plan_d, reinterpret_cast<unsigned long long*>(hist_dev), 1);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));
     });
 }
 
@@ -1302,7 +1339,12 @@ int vk_sharded_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, in
             launch(c, vk::plan_kernel, dim3(1), dim3(64), 0, (const vk::StepArgs*)c->args_d, c->starts.p, c->ends.p, c->plan_d);
             CU(cudaGetLastError());
             c->mark(EV_PARSE);
-            enqueue_count(c, k, c->seg_hist.p);
+            // calibrated thresholds: the shards' base histograms over the priority buckets are summed first (512 KiB)
+            const bool calibrated = p->sampling == VK_SAMPLING_CALIBRATED && p->prio_hist == 0;
+            enqueue_count(c, k, c->seg_hist.p, [&]() {
+                if (calibrated)
+                    NC(api.AllReduce(c->prio_hist.p, c->prio_hist.p, VK_PRIO_BUCKETS, ncclUint64, ncclSum, c->comm, c->stream));
+            });
             // exchange step 2: the histograms of every ladder segment + the per-segment totals, ONE all-reduce
             unsigned long long* const tail = c->seg_hist.p + n_hist;
             launch(c, vk::shard_tail_kernel, dim3(1), dim3(256), 0, c->plan_d, tail, 0);

@@ -58,6 +58,7 @@ struct Plan {
     uint32_t count_overflow;                     // a 16-bit bin of a FAST count kernel wrapped (vk_count.cuh): exact recount
     uint64_t read_index_base;                    // global index of this buffer's first record (plan_kernel -> scatter)
     uint64_t total_reads;                        // records of the whole sample (= n_reads unless read-sharded)
+    uint32_t hist_ticket;                        // CTAs of thr_calibrate_kernel that are done (the last one fits the thresholds)
     uint32_t len_min, len_max;                   // shortest / longest read that is counted (scatter kernel): one read per lane pays only for reads of one length
 };
 

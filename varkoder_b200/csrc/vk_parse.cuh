@@ -46,11 +46,12 @@ constexpr uint32_t kStepArgWords = (uint32_t)(sizeof(StepArgs) / 4);
 static_assert(sizeof(StepArgs) % 4 == 0, "StepArgs is copied as 32-bit words");
 __global__ void __launch_bounds__(1024)
 step_begin_kernel(const uint32_t* __restrict__ args_host, uint32_t* __restrict__ args_dev, Plan* __restrict__ plan,
-                  uint32_t* __restrict__ tile_count, uint32_t tile_cap, int rescan)
+                  uint32_t* __restrict__ tile_count, uint32_t tile_cap, int rescan, unsigned long long* __restrict__ prio_hist)
 {
     pdl_wait();
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < kStepArgWords) args_dev[g] = args_host[g];
+    for (uint32_t i = g; i < (uint32_t)VK_PRIO_BUCKETS; i += gridDim.x * blockDim.x) prio_hist[i] = 0;      // vk_sample.cuh
     if (!rescan) return;
     if (g < offsetof(Plan, n_lines) / 4) reinterpret_cast<uint32_t*>(plan)[g] = 0;        // parse fields: counters, sums, ticket
     for (uint32_t i = g; i < tile_cap; i += gridDim.x * blockDim.x) tile_count[i] = 0;
@@ -508,6 +509,7 @@ plan_kernel(const StepArgs* __restrict__ sa, uint64_t* __restrict__ starts, uint
         plan->n_levels = nl;
         plan->long_reads = 0;
         plan->len_min = 0xFFFFFFFFu;
+        plan->hist_ticket = 0;
         plan->len_max = 0;
         s_nl = nl;
         s_nsites = nsites;

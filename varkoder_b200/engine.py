@@ -28,6 +28,8 @@ class Params:
     breaklength: int = _lib.VK_BREAKLENGTH
     read_index_base: int = 0
     nsites_override: int = 0
+    sampling: int = _lib.VK_SAMPLING_CALIBRATED      # thresholds fitted to the base targets (reformat.sh samplebasestarget)
+    prio_hist: int = 0                               # read-sharded samples: device pointer of the sample-wide histogram
 
     def to_c(self):
         p = _lib.VkParams()
@@ -40,6 +42,8 @@ class Params:
         p.seed = parse_seed(self.seed)
         p.read_index_base = int(self.read_index_base)
         p.nsites_override = int(self.nsites_override)
+        p.sampling = int(self.sampling)
+        p.prio_hist = int(self.prio_hist)
         return p
 
 
@@ -147,6 +151,13 @@ class Engine:
         p = params.to_c()
         self._check(self._L.vk_count(self._ctx, C.byref(p), seg_hist_ptr, C.byref(r)))
         return _result_from(r)
+
+    def prio_hist(self, params: Params, hist_ptr):
+        """read-sharded samples, calibrated thresholds: ADD the base histogram of this buffer's reads over the 2^16 priority
+        buckets to ``hist_ptr`` (device memory, VK_PRIO_BUCKETS uint64, zeroed by the caller before the first shard); after
+        ``parse``.  The sum over the shards goes to ``count`` as ``Params.prio_hist``."""
+        p = params.to_c()
+        self._check(self._L.vk_prio_hist(self._ctx, C.byref(p), hist_ptr))
 
     def render(self, table: PixelTable | None, k, n_levels, seg_hist_ptr=None, want_canon=True):
         nk = 4 ** k

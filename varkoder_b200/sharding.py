@@ -99,6 +99,15 @@ def sharded_count(engine, shard_bytes, params: Params, seg_hist, group=None):
     st = engine.parse()
     base, total, per_rank = _exchange_shard_stats(st["n_reads"], st["nsites"], group)
     p = replace(params, read_index_base=base, nsites_override=total)      # 0 bases in total: every shard is empty too
+    if p.sampling == _lib.VK_SAMPLING_CALIBRATED and not p.prio_hist:
+        # thresholds fitted to the base targets need the base histogram of the WHOLE sample over the priority buckets:
+        # every rank builds its shard's, one more all_reduce (512 KiB) sums them
+        hist = torch.zeros(_lib.VK_PRIO_BUCKETS, dtype=torch.int64, device=seg_hist.device)
+        engine.prio_hist(p, hist.data_ptr())
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+        if hist.is_cuda:
+            torch.cuda.current_stream(hist.device).synchronize()          # the engine counts on its own stream
+        p = replace(p, prio_hist=hist.data_ptr())
     res = engine.count(p, seg_hist.data_ptr())
     # the one exchange step of the path; every rank derives the same ladder, so only its levels are exchanged.  The
     # realised reads / bases per level ride along in the first unused row of the table (same reduction, one collective)
