@@ -10,6 +10,10 @@ Contents
                                         dsk canonical counts, dsk2ascii text) -- PARITY UNPINNED at the
                                         dsk/reformat.sh boundary (binaries and sources absent, the
                                         reference's tests hold no expected counts).
+:mod:`oracle.dsk_numpy`                 a SECOND, independently written restatement of the same rules (flat
+                                        window enumeration + bincount in numpy instead of a rolling window in
+                                        C); the two must agree on every test input and on the BASELINE-size
+                                        sample (``tests/test_oracle.py``, ``tests/test_gpu_parity.py``).
 :mod:`oracle.image`                     restatement of the Python half (ladder, pixel tables, scatter,
                                         rank scaling) -- PINNED against the imported, unmodified
                                         reference (``tests/golden/*.npz`` made by ``oracle/make_golden.py``)

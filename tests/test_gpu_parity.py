@@ -305,6 +305,11 @@ def test_full_size_properties_config2(engine):
     host = dev[:total].cpu().numpy()
     expect = oracle_levels_fast(host, k, 1, res.levels, n_bases)
     assert (canon == expect).all()
+    # ... and against the SECOND, independently written restatement of the same rules (oracle/dsk_numpy.py: flat window
+    # enumeration + bincount instead of the C oracle's rolling window) -- at the BASELINE size, every level
+    from oracle import dsk_numpy
+    thr, take_all = dsk.level_thresholds(res.levels, n_bases, 1, lens=dsk.parse_fastq(host)["lens"])
+    assert (canon == dsk_numpy.count_levels(host, k, 1, thr, take_all)).all()
     for lvl in range(len(res.levels)):
         assert (res.pixels[lvl] == oimg.image_exact(expect[lvl], table.lut)).all()
 

@@ -27,6 +27,28 @@ def test_oracle_c_matches_bruteforce():
         assert int(c.sum()) == int(b.sum())
 
 
+def test_two_independent_restatements_agree():
+    """dsk_oracle.c (rolling window, C) and oracle/dsk_numpy.py (flat window enumeration + bincount, numpy) restate the same
+    rules with different algorithms: framing, membership, counts and fold must agree on every kind of input -- N, lower
+    case, reads longer than the break length, empty and too-short reads, no final newline, empty file, Bembidion-shaped and
+    fixed-length synthetic samples.  (The GPU suite repeats this at the BASELINE size, 200 Mbp.)"""
+    from oracle import dsk_numpy
+    from varkoder_b200 import synth
+    rng = np.random.default_rng(5)
+    bufs = [fastq(rand_reads(rng, 400, 0, 90, p_n=0.03) + ["acgtn" * 20, "ACGT" * 400, "G" * 700, "", "ACGTAC"], final_newline=False),
+            synth.variable(6000, seed=9).tobytes(), synth.fixed(3_000_000, 150, seed=2).tobytes(), b"", b"@x\n"]
+    for buf in bufs:
+        p = dsk.parse_fastq(buf)
+        s, l = dsk_numpy.frame(buf)
+        assert (s == p["starts"]).all() and (l == p["lens"]).all()
+        nsites = p["nsites_ref"]
+        levels = oimg.ladder(nsites, 3000, None) if nsites > 3000 else [max(nsites, 1)]
+        for k, calibrated in ((5, True), (7, True), (7, False), (8, True), (9, True)):
+            thr, take_all = dsk.level_thresholds(levels, nsites, 77, lens=p["lens"] if calibrated else None)
+            _, c = dsk.count_levels(buf, k, 77, thr, take_all, threads=0)
+            assert (c == dsk_numpy.count_levels(buf, k, 77, thr, take_all)).all(), (len(buf), k)
+
+
 def test_oracle_breaklength_and_selection():
     rng = np.random.default_rng(3)
     reads = rand_reads(rng, 8, 900, 1700, p_n=0.002)
