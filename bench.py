@@ -316,6 +316,8 @@ def c4_leg(args, world, rank, local, torch, dist, reps=None, in_flight=None):
     mine = sorted((i for i in range(len(targets)) if owner[i] == rank), key=lambda i: -targets[i])
     T = in_flight or (1 if args.no_concurrent else max(1, args.in_flight))
     engs = [Engine(local) for _ in range(T)]
+    for e in engs:
+        e.set_batch_mode(T > 1)                # as stages.images_for_samples does for its worker contexts
     table = get_kmer_mapping(7, "varKode")
     texts, sizes = {}, {}
     first = [0]
@@ -872,7 +874,7 @@ def main():
             e.close()
         del samples, devs, dev, hosts, host_keep
         torch.cuda.empty_cache()
-        for name, fn in (("c4", lambda: c4_leg(args, world, rank, local, torch, dist, reps=3, in_flight=max(T, 4))),
+        for name, fn in (("c4", lambda: c4_leg(args, world, rank, local, torch, dist, reps=3, in_flight=max(T, 8))),
                          ("c5", lambda: c5_leg(args, world, rank, local, torch, dist, steps=6)),
                          ("e2e_gz", lambda: e2e_gz_leg(eng, local, torch) if rank == 0 else None)):
             try:

@@ -202,6 +202,12 @@ int vk_last_timings(vk_ctx* ctx, float* ms8);
  * [7] total; the other entries read 0). */
 int vk_set_fine_timing(vk_ctx* ctx, int on);
 
+/* on: this context is one of several that push samples through the same GPU at once (ImageCommand.process_samples runs
+ * its samples through a pool, image.py:1236-1294).  A small sample then takes at most ceil(n_reads / 3000) count CTAs
+ * instead of one per SM: the SMs it could not keep busy anyway are left to the kernels of the other samples in flight
+ * (config 4, 96 samples of 10-50 Mbp: +8..12 % per batch).  Samples of 450 k reads and more are not affected.  off: default. */
+int vk_set_batch_mode(vk_ctx* ctx, int on);
+
 /* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
 uint64_t vk_launch_count(vk_ctx* ctx);
 

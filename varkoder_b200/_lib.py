@@ -22,7 +22,7 @@ SYMBOLS = [
     "vk_abi_version", "vk_last_error", "vk_ctx_create", "vk_ctx_destroy", "vk_set_mapping", "vk_upload",
     "vk_attach", "vk_parse", "vk_count", "vk_prio_hist", "vk_render", "vk_render_counts", "vk_reads_to_images", "vk_device_pixels", "vk_remap",
     "vk_base_content",
-    "vk_last_timings", "vk_set_fine_timing", "vk_launch_count", "vk_bucket_retries", "vk_count_fallbacks", "vk_synth_fastq",
+    "vk_last_timings", "vk_set_fine_timing", "vk_set_batch_mode", "vk_launch_count", "vk_bucket_retries", "vk_count_fallbacks", "vk_synth_fastq",
     "vk_synth_fastq_variable", "vk_graph_stats",
     "vk_comm_unique_id", "vk_comm_init", "vk_comm_destroy", "vk_sharded_reads_to_images",
 ]
@@ -83,6 +83,7 @@ def load():
     L.vk_base_content.argtypes = [vp, C.c_int32, C.c_int32, vp]
     L.vk_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.vk_set_fine_timing.argtypes = [vp, C.c_int]
+    L.vk_set_batch_mode.argtypes = [vp, C.c_int]
     L.vk_launch_count.argtypes = [vp]
     L.vk_launch_count.restype = C.c_uint64
     L.vk_bucket_retries.argtypes = [vp]

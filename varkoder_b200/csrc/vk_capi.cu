@@ -88,6 +88,7 @@ struct vk_ctx {
                                     // Measured at k = 7: 0 -> 139.0 us, 1 -> 138.4, 2 -> 139.3, 3 and more -> 155+: off.
     int count_extra9 = 6;           // k = 9: extra PAIRS (VK_COUNT_EXTRA9).  74 pairs over 11 segments leave six pairs with
                                     // 1.5 % of the work; 2.76 ms (0) -> 2.64 (2) -> 2.59 (6) -> 2.66 (10) per Gbp
+    int reads_per_cta_env = 0;      // what VK_COUNT_READS_PER_CTA asked for (vk_set_batch_mode(0) goes back to it)
     int reads_per_cta = 0;          // VK_COUNT_READS_PER_CTA: > 0 caps the count CTAs of a small sample (plan_kernel)
     int count_grid() const { return n_sms * count_ctas_per_sm + count_extra; }
 
@@ -816,6 +817,7 @@ int vk_ctx_create(int device, vk_ctx** out)
         if (const char* e = getenv("VK_COUNT_EXTRA")) c->count_extra = std::max(0, std::min(64, atoi(e)));
         if (const char* e = getenv("VK_COUNT_EXTRA9")) c->count_extra9 = std::max(0, std::min(64, atoi(e)));
         if (const char* e = getenv("VK_COUNT_READS_PER_CTA")) c->reads_per_cta = std::max(0, atoi(e));
+        c->reads_per_cta_env = c->reads_per_cta;
         if (const char* e = getenv("VK_TEST_TIGHT_BUCKETS")) c->test_tight = atoi(e) != 0;
         if (const char* e = getenv("VK_PDL")) c->use_pdl = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT16")) c->use_count16 = atoi(e) != 0;
@@ -1213,6 +1215,13 @@ int vk_set_fine_timing(vk_ctx* c, int on)
 {
     if (!c) return VK_EINVAL;
     c->fine_timing = on != 0;
+    return VK_OK;
+}
+
+int vk_set_batch_mode(vk_ctx* c, int on)
+{
+    if (!c) return VK_EINVAL;
+    c->reads_per_cta = on ? 3000 : c->reads_per_cta_env;
     return VK_OK;
 }
 

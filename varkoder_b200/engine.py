@@ -300,6 +300,11 @@ class Engine:
         """events between kernel groups (per-kernel split of timings()) on/off; off lets dependent launches overlap"""
         self._check(self._L.vk_set_fine_timing(self._ctx, 1 if on else 0))
 
+    def set_batch_mode(self, on):
+        """this engine is one of several that work on one GPU at once: small samples leave the SMs they cannot fill to
+        the others (vk_set_batch_mode)"""
+        self._check(self._L.vk_set_batch_mode(self._ctx, 1 if on else 0))
+
     def launch_count(self):
         return int(self._L.vk_launch_count(self._ctx))
 

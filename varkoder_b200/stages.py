@@ -304,6 +304,7 @@ def images_for_samples(samples, outfolder, kmer_mapping, k=7, mapping_code="varK
             eng = getattr(tls, "eng", None)
             if eng is None:
                 eng = tls.eng = Engine(device)
+                eng.set_batch_mode(gpu_workers > 1)
                 made.append(eng)
         seed = seeds[i] if seeds is not None else i
         params = Params(k=int(k), min_bp=int(min_bp), max_bp=None if max_bp is None else int(max_bp),
