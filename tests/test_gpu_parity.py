@@ -165,6 +165,37 @@ def test_read_sharding_sums_to_whole(engine):
         assert r2.levels == res.levels
         total += c2
     assert (total == whole).all()
+    # the fused call takes the sample's histogram the same way (one CUDA graph serves samples with and without it)
+    table = get_kmer_mapping(k, "cgr")
+    fused = np.zeros_like(whole)
+    for sb, base in shards:
+        ps = Params(k=k, min_bp=20000, max_bp=None, seed=77, read_index_base=base, nsites_override=p["nsites_ref"],
+                    prio_hist=hist.data_ptr())
+        fused += engine.reads_to_images(sb, ps, table, want_canon=True).canon
+    # canonical counts add over shards as the segment histograms do
+    assert (fused == engine.reads_to_images(buf, params, table, want_canon=True).canon).all()
+
+
+def test_expected_value_thresholds_still_there(engine):
+    """VK_SAMPLING_EXPECTED: round 1's fixed thresholds thr = bp * 2^64 / nsites (no histogram, no fit) against the oracle's
+    form of that rule; the two rules differ in which reads they draw, not in how reads are counted."""
+    from varkoder_b200.ladder import parse_seed
+    k = 7
+    buf = synth.variable(9000, seed=5, k=k).tobytes()
+    p = dsk.parse_fastq(buf)
+    table = get_kmer_mapping(k, "varKode")
+    got = {}
+    for sampling in (_lib.VK_SAMPLING_EXPECTED, _lib.VK_SAMPLING_CALIBRATED):
+        res = engine.reads_to_images(buf, Params(k=k, min_bp=20000, max_bp=None, seed="123456789012345678901", sampling=sampling), table, want_canon=True)
+        expect = oracle_levels(buf, k, parse_seed("123456789012345678901"), res.levels, p["nsites_ref"], calibrated=bool(sampling))
+        assert (res.canon == expect).all() and (res.pixels == oracle_images(expect, table.lut)).all()
+        got[sampling] = res
+    a, b = got[_lib.VK_SAMPLING_EXPECTED], got[_lib.VK_SAMPLING_CALIBRATED]
+    assert a.levels == b.levels and a.level_bases[0] == b.level_bases[0] and a.level_bases[1:] != b.level_bases[1:]
+    lmax = int(p["lens"].max())
+    # (level_bases leaves out the reads shorter than k, 1 % of the reads with 0..6 bases each: a second read of slack)
+    assert all(abs(x - t) <= 2 * lmax for x, t in zip(b.level_bases[1:], b.levels[1:]))        # fitted: within one read
+    assert any(abs(x - t) > 2 * lmax for x, t in zip(a.level_bases[1:], a.levels[1:]))         # expected value only
 
 
 # --------------------------------------------------------------------------------- images (make_image stand-in)
