@@ -874,7 +874,9 @@ def main():
             e.close()
         del samples, devs, dev, hosts, host_keep
         torch.cuda.empty_cache()
-        for name, fn in (("c4", lambda: c4_leg(args, world, rank, local, torch, dist, reps=3, in_flight=max(T, 8))),
+        for name, fn in (("c4", lambda: c4_leg(args, world, rank, local, torch, dist, reps=3,
+                                             # small samples: eight contexts per GPU while the host has a core for each worker thread
+                                             in_flight=max(T, min(8, max(4, len(os.sched_getaffinity(0)) // max(world, 1)))))),
                          ("c5", lambda: c5_leg(args, world, rank, local, torch, dist, steps=6)),
                          ("e2e_gz", lambda: e2e_gz_leg(eng, local, torch) if rank == 0 else None)):
             try:
