@@ -35,7 +35,7 @@ enum {
     VK_ECUDA = -2,    /* CUDA runtime error (message holds cudaGetErrorString) */
     VK_ENOMEM = -3,
     VK_ESTATE = -4,   /* call order violated (e.g. count before parse) */
-    VK_ERANGE = -5    /* input outside supported range (read longer than 2^24-1 bases, buffer >= 2^40 B) */
+    VK_ERANGE = -5    /* input outside supported range (buffer >= 2^40 B; more ladder levels than the caller allowed for) */
 };
 
 /* status of the ladder, vk_result.status */

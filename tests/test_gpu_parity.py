@@ -840,8 +840,7 @@ def test_remap_shipped_docs_pngs(engine, golden_dir):
 @pytest.mark.parametrize("k", [7, 8, 9])
 def test_very_long_reads_and_limits(engine, k):
     """reads of megabases (nanopore-like): one read spans tens of thousands of chunks, units hold 1..3 reads, break points
-    every 500 bases or none; and the documented limit: a read of 2^24 bases or more is refused, not mis-counted."""
-    from varkoder_b200.engine import VkError
+    every 500 bases or none; and reads beyond the 2^24 - 1 bases one table entry holds."""
     rng = np.random.default_rng(40 + k)
     big = "".join(rng.choice(list("ACGT"), 1_300_003))
     big = big[:500_000] + "N" + big[500_001:]
@@ -850,11 +849,16 @@ def test_very_long_reads_and_limits(engine, k):
     for bl in (500, 0, 64):
         _, res, canon, _ = gpu_counts(engine, buf, Params(k=k, min_bp=0, max_bp=None, is_query=True, breaklength=bl))
         assert (canon[0] == dsk.canonical_counts(buf, k, breaklen=bl)).all(), bl
-    huge = fastq(["A" * (1 << 24)], quals=["#"])            # malformed quality line: framing is by line count only
-    engine.upload(huge)
-    engine.parse()
-    with pytest.raises(VkError, match="longer than 2\\^24-1"):
-        engine.count(Params(k=k, min_bp=0, max_bp=None, is_query=True))
+    # reads of 2^24 bases and more (chromosomes) do not fit one entry of the read table: the scatter kernel cuts them into
+    # several -- at multiples of the break length, or overlapping by k - 1 bases when there is none -- and the counts are
+    # those of the whole read.  (Malformed quality lines: the framing is by line count only.)
+    chrom = "".join(rng.choice(list("ACGT"), (1 << 24) + 12_345))
+    chrom = chrom[:9_000_000] + "NN" + chrom[9_000_002:]
+    huge = fastq([chrom, "ACGTACGTACGTAGG", "T" * ((1 << 24) - 1), "C" * (1 << 24)], quals=["#", "#", "#", "#"])
+    for bl in (500, 0):
+        _, res, canon, _ = gpu_counts(engine, huge, Params(k=k, min_bp=0, max_bp=None, is_query=True, breaklength=bl))
+        assert (canon[0] == dsk.canonical_counts(huge, k, breaklen=bl, threads=0)).all(), bl
+        assert res.level_reads == [4] and res.level_bases == [len(chrom) + 15 + (1 << 24) - 1 + (1 << 24)]
 
 
 def test_concurrent_contexts_are_independent():

@@ -90,8 +90,38 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
             uint32_t len32 = 0;
             if (r < n_reads) {
                 const uint64_t len = en[i] - st[i];
-                if (len > kEntryLenMask) atomicAdd(&s_long, 1u);
-                else if (len >= (uint64_t)k) {
+                if (len > kEntryLenMask) {
+                    // A read of 2^24 bases or more (a chromosome) does not fit one entry: it becomes several.  With a break
+                    // length the pieces end at multiples of it (no k-mer spans a cut point anyway, image.py:586); without
+                    // one they overlap by k - 1 bases, so that every k-mer starts in exactly one piece.  Rare: the thread
+                    // takes the slots straight from the segment's counter.
+                    if (chunk_mode) atomicAdd(&s_long, 1u);
+                    else {
+                        const uint64_t h = prio64(seed, read_index_base + r);
+                        int lo = 0, hi = nl;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (s_all[mid] || h < s_thr[mid]) lo = mid + 1; else hi = mid;
+                        }
+                        const int sg = lo - 1;
+                        if (sg >= 0) {
+                            const uint64_t step = breaklen ? (kEntryLenMask / breaklen) * breaklen : kEntryLenMask - (uint64_t)(k - 1);
+                            const uint64_t ov = breaklen ? 0 : (uint64_t)(k - 1);
+                            const uint64_t n_pieces = (len + step - 1) / step;
+                            const unsigned long long slot0 = atomicAdd(&plan->seg_reads[sg], (unsigned long long)n_pieces);
+                            atomicAdd(&plan->seg_bases[sg], (unsigned long long)len);
+                            atomicAdd(&plan->seg_extra[sg], (unsigned long long)(n_pieces - 1));
+                            for (uint64_t j = 0; j < n_pieces; ++j) {
+                                const uint64_t off = j * step;
+                                const uint64_t pl = len - off < step + ov ? len - off : step + ov;
+                                if (slot0 + j < s_cap[sg]) sorted[s_begin[sg] + slot0 + j] = ((st[i] + off - text_base) << kEntryLenBits) | pl;
+                                else plan->bucket_overflow = 1u;
+                            }
+                            my_max = (uint32_t)kEntryLenMask;
+                            my_min = my_min < (uint32_t)kEntryLenMask ? my_min : (uint32_t)kEntryLenMask;
+                        }
+                    }
+                } else if (len >= (uint64_t)k) {
                     const uint64_t h = prio64(seed, read_index_base + r);
                     // number of levels the read is in: membership is monotone in the level (levels are nested: the
                     // "all reads" levels come first, thresholds never increase), so a binary search with a

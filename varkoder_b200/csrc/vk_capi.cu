@@ -569,7 +569,7 @@ void fill_result(const vk::Plan& p, vk_result* r)
     r->n_levels = p.n_levels;
     uint64_t reads = 0, bases = 0;
     for (int l = p.n_levels - 1; l >= 0; --l) {
-        reads += p.seg_reads[l];
+        reads += p.seg_reads[l] - p.seg_extra[l];          // entries - the extra entries of reads cut into several
         bases += p.seg_bases[l];
         r->level_bp[l] = p.level_bp[l];
         r->level_reads[l] = reads;

@@ -1213,13 +1213,13 @@ shard_tail_kernel(Plan* __restrict__ plan, unsigned long long* __restrict__ tail
     if (i >= kShardTail) return;
     if (!unpack) {
         unsigned long long v;
-        if (i < (uint32_t)kMaxLevels) v = plan->seg_reads[i];
+        if (i < (uint32_t)kMaxLevels) v = plan->seg_reads[i] - plan->seg_extra[i];      // reads, not entries
         else if (i < 2u * kMaxLevels) v = plan->seg_bases[i - kMaxLevels];
         else v = i == 2u * kMaxLevels ? plan->table_overflow : (i == 2u * kMaxLevels + 1 ? plan->bucket_overflow : plan->count_overflow);
         tail[i] = v;
     } else {
         const unsigned long long v = tail[i];
-        if (i < (uint32_t)kMaxLevels) plan->seg_reads[i] = v;
+        if (i < (uint32_t)kMaxLevels) { plan->seg_reads[i] = v; plan->seg_extra[i] = 0; }
         else if (i < 2u * kMaxLevels) plan->seg_bases[i - kMaxLevels] = v;
         else if (i == 2u * kMaxLevels) plan->table_overflow = v ? 1u : 0u;
         else if (i == 2u * kMaxLevels + 1) plan->bucket_overflow = v ? 1u : 0u;

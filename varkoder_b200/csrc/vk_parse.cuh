@@ -527,6 +527,7 @@ plan_kernel(const StepArgs* __restrict__ sa, uint64_t* __restrict__ starts, uint
         plan->level_thr[l] = thr;
         plan->seg_reads[l] = 0;
         plan->seg_bases[l] = 0;
+        plan->seg_extra[l] = 0;
         plan->seg_next[l] = 0;
         plan->seg_next2[l] = 0;
         plan->seg_chunks[l] = 0;
