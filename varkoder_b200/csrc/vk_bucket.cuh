@@ -19,13 +19,51 @@ constexpr int kBucketItems = 4;      // reads per thread and iteration of the sc
 constexpr int kBucketItemsChunk = 2; // chunk mode: half as many, so that the staging area stays small enough for 8 blocks per SM
 constexpr uint32_t kStageChunks = 3072;      // chunk descriptors a block stages in (dynamic) shared memory, 24 KiB: 512 reads of up to ~170 bases
 
+// A read of 2^24 bases or more (a chromosome) does not fit one entry of the read table: it becomes several.  With a break
+// length the pieces end at multiples of it (no k-mer spans a cut point anyway, image.py:586); without one they overlap by
+// k - 1 bases, so that every k-mer starts in exactly one piece.  The scatter kernel only lists such reads (they are rare
+// and the arithmetic -- 64-bit divisions by the break length -- would cost its loop a third of its occupancy); this kernel,
+// one thread per listed read, cuts them up and takes the slots straight from the segments' counters.
+constexpr uint32_t kLongListCap = 4096;
+__global__ void __launch_bounds__(256)
+long_reads_kernel(const uint64_t* __restrict__ starts, const uint64_t* __restrict__ ends, const StepArgs* __restrict__ sa,
+                  uint64_t text_base, uint64_t* __restrict__ sorted, Plan* __restrict__ plan, const uint64_t* __restrict__ long_list)
+{
+    pdl_wait();
+    const uint32_t n = plan->n_long;
+    if (n == 0 || plan->table_overflow || plan->bucket_overflow) return;
+    if (n > kLongListCap) { if (threadIdx.x == 0 && blockIdx.x == 0) plan->long_reads = n; return; }
+    const uint32_t k = (uint32_t)sa->pa.p.k, breaklen = (uint32_t)sa->pa.p.breaklength;
+    const int nl = plan->n_levels;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint64_t r = long_list[i];
+        const uint64_t start = starts[r] - text_base, len = ends[r] - starts[r];
+        const int sg = levels_of(plan, nl, prio64(sa->pa.p.seed, plan->read_index_base + r)) - 1;
+        if (sg < 0) continue;
+        const uint64_t step = breaklen ? (kEntryLenMask / breaklen) * breaklen : kEntryLenMask - (uint64_t)(k - 1);
+        const uint64_t ov = breaklen ? 0 : (uint64_t)(k - 1);
+        const uint64_t n_pieces = (len + step - 1) / step;
+        const unsigned long long slot0 = atomicAdd(&plan->seg_reads[sg], (unsigned long long)n_pieces);
+        atomicAdd(&plan->seg_bases[sg], (unsigned long long)len);
+        atomicAdd(&plan->seg_extra[sg], (unsigned long long)(n_pieces - 1));
+        const uint64_t begin = plan->seg_begin[sg], cap = plan->seg_cap[sg];
+        for (uint64_t j = 0; j < n_pieces; ++j) {
+            const uint64_t off = j * step;
+            const uint64_t pl = len - off < step + ov ? len - off : step + ov;
+            if (slot0 + j < cap) sorted[begin + slot0 + j] = ((start + off) << kEntryLenBits) | pl;
+            else plan->bucket_overflow = 1u;
+        }
+    }
+}
+
 // One pass: scatter (start, len) entries into their segment's region, count reads and bases per segment.
 // Regions were sized from the expected segment shares by plan_kernel (vk_parse.cuh); a read that does not fit
 // raises plan->bucket_overflow and the host repeats the step with regions that hold every read.
 template <int kBucketItems>
 __global__ void __launch_bounds__(kBucketThreads)
 bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __restrict__ ends, const StepArgs* __restrict__ sa,
-                      uint64_t text_base, uint64_t* __restrict__ sorted, uint64_t* __restrict__ chunks, Plan* __restrict__ plan)
+                      uint64_t text_base, uint64_t* __restrict__ sorted, uint64_t* __restrict__ chunks, Plan* __restrict__ plan,
+                      uint64_t* __restrict__ long_list)
 {
     pdl_wait();
     const int k = sa->pa.p.k;
@@ -43,7 +81,7 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
     __shared__ unsigned long long s_cbase[kMaxLevels];
     __shared__ uint64_t s_cbegin[kMaxLevels], s_ccap[kMaxLevels];
     extern __shared__ uint64_t s_stage[];      // kStageChunks descriptors (chunk mode)
-    const bool chunk_mode = chunks != nullptr;
+    const bool chunk_mode = chunks != nullptr;      // (as a compile-time constant ptxas takes 80 registers instead of 48: 22.7 -> 29.7 us)
     const uint32_t breaklen = (uint32_t)sa->pa.p.breaklength;
     // the tables do not fit (plan_kernel): the step is repeated with larger ones, nothing here may be dereferenced.
     // (bucket_overflow can also be raised by this kernel itself, below; a CTA that starts late and sees it only skips
@@ -91,35 +129,13 @@ bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __res
             if (r < n_reads) {
                 const uint64_t len = en[i] - st[i];
                 if (len > kEntryLenMask) {
-                    // A read of 2^24 bases or more (a chromosome) does not fit one entry: it becomes several.  With a break
-                    // length the pieces end at multiples of it (no k-mer spans a cut point anyway, image.py:586); without
-                    // one they overlap by k - 1 bases, so that every k-mer starts in exactly one piece.  Rare: the thread
-                    // takes the slots straight from the segment's counter.
+                    // several table entries: listed here, cut up by long_reads_kernel (keeps this loop at 48 registers)
                     if (chunk_mode) atomicAdd(&s_long, 1u);
                     else {
-                        const uint64_t h = prio64(seed, read_index_base + r);
-                        int lo = 0, hi = nl;
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if (s_all[mid] || h < s_thr[mid]) lo = mid + 1; else hi = mid;
-                        }
-                        const int sg = lo - 1;
-                        if (sg >= 0) {
-                            const uint64_t step = breaklen ? (kEntryLenMask / breaklen) * breaklen : kEntryLenMask - (uint64_t)(k - 1);
-                            const uint64_t ov = breaklen ? 0 : (uint64_t)(k - 1);
-                            const uint64_t n_pieces = (len + step - 1) / step;
-                            const unsigned long long slot0 = atomicAdd(&plan->seg_reads[sg], (unsigned long long)n_pieces);
-                            atomicAdd(&plan->seg_bases[sg], (unsigned long long)len);
-                            atomicAdd(&plan->seg_extra[sg], (unsigned long long)(n_pieces - 1));
-                            for (uint64_t j = 0; j < n_pieces; ++j) {
-                                const uint64_t off = j * step;
-                                const uint64_t pl = len - off < step + ov ? len - off : step + ov;
-                                if (slot0 + j < s_cap[sg]) sorted[s_begin[sg] + slot0 + j] = ((st[i] + off - text_base) << kEntryLenBits) | pl;
-                                else plan->bucket_overflow = 1u;
-                            }
-                            my_max = (uint32_t)kEntryLenMask;
-                            my_min = my_min < (uint32_t)kEntryLenMask ? my_min : (uint32_t)kEntryLenMask;
-                        }
+                        const uint32_t slot = atomicAdd(&plan->n_long, 1u);
+                        if (slot < kLongListCap) long_list[slot] = r;
+                        my_max = (uint32_t)kEntryLenMask;
+                        my_min = my_min < (uint32_t)kEntryLenMask ? my_min : (uint32_t)kEntryLenMask;
                     }
                 } else if (len >= (uint64_t)k) {
                     const uint64_t h = prio64(seed, read_index_base + r);

@@ -163,6 +163,7 @@ struct vk_ctx {
     DevBuf<uint8_t> remap_in, remap_out, remap_mult;
     DevBuf<int32_t> remap_src;
     DevBuf<unsigned long long> content;
+    DevBuf<uint64_t> long_list;                  // indices of the reads of 2^24 bases or more of the current sample (vk_bucket.cuh)
     DevBuf<unsigned long long> prio_hist;        // bases per priority bucket of the current sample (vk_sample.cuh)
     DevBuf<uint64_t> synth_off;     // vk_synth_fastq_variable: record offsets
     Mapping maps[4];
@@ -458,10 +459,14 @@ void enqueue_count(vk_ctx* c, int k, unsigned long long* seg_hist, const std::fu
     CU(cudaGetLastError());
     if (c->chunk_mode(k))
         launch(c, bucket_scatter_kernel<kBucketItemsChunk>, dim3(2 * bgrid), dim3(kBucketThreads), kStageChunks * sizeof(uint64_t),
-               c->starts.p, c->ends.p, (const StepArgs*)c->args_d, 0, c->sorted.p, c->chunks.p, c->plan_d);
+               c->starts.p, c->ends.p, (const StepArgs*)c->args_d, 0, c->sorted.p, c->chunks.p, c->plan_d, c->long_list.p);
     else
         launch(c, bucket_scatter_kernel<kBucketItems>, dim3(bgrid), dim3(kBucketThreads), 0, c->starts.p, c->ends.p,
-               (const StepArgs*)c->args_d, 0, c->sorted.p, (uint64_t*)nullptr, c->plan_d);
+               (const StepArgs*)c->args_d, 0, c->sorted.p, (uint64_t*)nullptr, c->plan_d, c->long_list.p);
+    CU(cudaGetLastError());
+    // reads of 2^24 bases or more, listed by the scatter kernel: several table entries each (returns at once when there are none)
+    launch(c, long_reads_kernel, dim3(4), dim3(256), 0, c->starts.p, c->ends.p, (const StepArgs*)c->args_d, 0, c->sorted.p, c->plan_d,
+           (const uint64_t*)c->long_list.p);
     CU(cudaGetLastError());
     c->mark(EV_BUCKET);
     const bool pk = c->use_packed;
@@ -834,6 +839,7 @@ int vk_ctx_create(int device, vk_ctx** out)
         for (int i = 0; i < EV_N; ++i) CU(cudaEventCreate(&c->ev[i]));
         ensure_outbox(c, 0);
         CU(cudaMalloc(&c->args_d, sizeof(vk::StepArgs)));
+        c->long_list.ensure(vk::kLongListCap);
         c->prio_hist.ensure(VK_PRIO_BUCKETS + 1024);      // + the block sums of thr_calibrate_kernel
         CU(cudaMallocHost(&c->args_h, sizeof(vk::StepArgs)));
         prepare_kernels();
@@ -876,6 +882,7 @@ int vk_ctx_destroy(vk_ctx* c)
     c->remap_src.release();
     c->content.release();
     c->prio_hist.release();
+    c->long_list.release();
     c->synth_off.release();
     for (auto& m : c->maps) m.lut.release();
     if (c->out_h) cudaFreeHost(c->out_h);
@@ -984,7 +991,7 @@ int vk_count(vk_ctx* c, const vk_params* p, uint64_t* seg_hist_dev, vk_result* o
             fetch_plan(c);
             c->parsed = false;                     // a retry (table overflow) must rescan
         });
-        if (c->plan_h->long_reads) throw ApiError{VK_ERANGE, "a read is longer than 2^24-1 bases"};
+        if (c->plan_h->long_reads) throw ApiError{VK_ERANGE, "more than 4096 reads of 2^24 bases or more (or one such read in chunk-table mode)"};
         c->parsed = true;
         c->counted = true;
         c->counted_k = p->k;
@@ -1106,7 +1113,7 @@ int vk_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, int on_dev
             c->mark(EV_DONE);
         });
         trace_dump(c);
-        if (c->plan_h->long_reads) throw ApiError{VK_ERANGE, "a read is longer than 2^24-1 bases"};
+        if (c->plan_h->long_reads) throw ApiError{VK_ERANGE, "more than 4096 reads of 2^24 bases or more (or one such read in chunk-table mode)"};
         c->parsed = c->counted = true;
         c->counted_k = k;
         fill_result(*c->plan_h, result);
@@ -1364,7 +1371,7 @@ int vk_sharded_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, in
             CU(cudaMemcpyAsync(c->out_h, c->out_d, kPlanPad + (size_t)max_levels_out * n_pix, cudaMemcpyDeviceToHost, c->stream));
             c->mark(EV_DONE);
         });
-        if (c->plan_h->long_reads) throw ApiError{VK_ERANGE, "a read is longer than 2^24-1 bases"};
+        if (c->plan_h->long_reads) throw ApiError{VK_ERANGE, "more than 4096 reads of 2^24 bases or more (or one such read in chunk-table mode)"};
         c->parsed = c->counted = true;
         c->counted_k = k;
         fill_result(*c->plan_h, result);

@@ -45,7 +45,7 @@ struct Plan {
     unsigned long long seg_next[kMaxLevels];     // dynamic unit counters of the count kernel
     uint64_t seg_begin[kMaxLevels + 1];          // offsets into the sorted entry array
     uint32_t seg_cta_begin[kMaxLevels + 1];      // CTA ranges of the count kernel
-    uint32_t long_reads;                         // reads of 2^24 bases or more that could not be cut into entries (chunk-table mode only)
+    uint32_t long_reads;                         // reads of 2^24 bases or more that could not be cut into entries (chunk-table mode; more than 4096 of them)
     uint32_t bucket_overflow;                    // a segment received more reads than its region holds (retry, exact layout)
     uint64_t seg_cap[kMaxLevels];                // entries each segment's region of the sorted array can hold
     unsigned long long seg_next2[kMaxLevels];    // second set of unit counters (k = 9: the other half of every CTA pair)
@@ -60,6 +60,7 @@ struct Plan {
     uint64_t total_reads;                        // records of the whole sample (= n_reads unless read-sharded)
     uint32_t hist_ticket;                        // CTAs of thr_calibrate_kernel that are done (the last one fits the thresholds)
     unsigned long long seg_extra[kMaxLevels];    // entries beyond one per read: a read of 2^24 bases or more is several entries (vk_bucket.cuh)
+    uint32_t n_long;                             // reads of 2^24 bases or more listed by the scatter kernel (long_reads_kernel cuts them up)
     uint32_t len_min, len_max;                   // shortest / longest read that is counted (scatter kernel): one read per lane pays only for reads of one length
 };
 

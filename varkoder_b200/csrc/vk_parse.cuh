@@ -509,6 +509,7 @@ plan_kernel(const StepArgs* __restrict__ sa, uint64_t* __restrict__ starts, uint
         plan->n_levels = nl;
         plan->long_reads = 0;
         plan->len_min = 0xFFFFFFFFu;
+        plan->n_long = 0;
         plan->hist_ticket = 0;
         plan->len_max = 0;
         s_nl = nl;
