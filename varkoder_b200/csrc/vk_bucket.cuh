@@ -60,6 +60,7 @@ long_reads_kernel(const uint64_t* __restrict__ starts, const uint64_t* __restric
 // Regions were sized from the expected segment shares by plan_kernel (vk_parse.cuh); a read that does not fit
 // raises plan->bucket_overflow and the host repeats the step with regions that hold every read.
 template <int kBucketItems>
+// (forcing 6 or 8 blocks per SM through the launch bounds spills and is slower: 720 / 728 against 746 Gbases/s)
 __global__ void __launch_bounds__(kBucketThreads)
 bucket_scatter_kernel(const uint64_t* __restrict__ starts, const uint64_t* __restrict__ ends, const StepArgs* __restrict__ sa,
                       uint64_t text_base, uint64_t* __restrict__ sorted, uint64_t* __restrict__ chunks, Plan* __restrict__ plan,
