@@ -134,6 +134,7 @@ struct vk_ctx {
     DevBuf<uint4> codes;            // 2-bit codes of every text byte, 16 B per 64 text bytes (parse_mask_kernel<true>)
     DevBuf<uint2> valid;            // validity bits, 8 B per 64 text bytes
     // one step = one CUDA graph: captured once per (k, pixel table, levels, layout) and replayed for every sample
+    bool zero_unused_rows = true;   // the count enqueue writes zeros to the segment rows beyond the ladder (false inside the fused step)
     bool use_graph = true;          // VK_GRAPH=0: launch the kernels of a step one by one
     struct StepGraph {
         int k, slot, side, max_levels, exact, packed;
@@ -391,7 +392,7 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
             const size_t smem = countu_smem_bytes();
             launch(c, countu_kernel, grid, block, smem, sa, (const uint64_t*)c->sorted.p, c->plan_d, c->slabs.p, 1u);
             c->mark(EV_COUNT);
-            launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist);
+            launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist, c->zero_unused_rows ? 1 : 0);
             return;
         }
         // k = 7 in read-aligned pairs from the chunk table (countp_kernel); a wrapped bin repeats the count with the u32 kernel
@@ -399,7 +400,7 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
             const size_t smem = (size_t)(32768 + 16384) * sizeof(uint32_t);
             launch(c, countp_kernel, grid, block, smem, sa, (const uint64_t*)c->chunks.p, c->plan_d, c->slabs.p);
             c->mark(EV_COUNT);
-            launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist);
+            launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist, c->zero_unused_rows ? 1 : 0);
             return;
         }
     }
@@ -412,7 +413,7 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
             if (fast) launch(c, (count16_kernel<K, PACKED, true>), grid, block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p);
             else launch(c, (count16_kernel<K, PACKED, false>), grid, block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p);
             c->mark(EV_COUNT);
-            launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist);
+            launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist, c->zero_unused_rows ? 1 : 0);
             return;
         }
     }
@@ -433,7 +434,7 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
         if (c->chunk_mode(K)) launch(c, countd_kernel<K>, grid, block, smem, sa, (const uint64_t*)c->chunks.p, c->plan_d, c->slabs.p);
         else launch(c, (count_kernel<K, kSmem32, PACKED>), grid, block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p, seg_hist);
         c->mark(EV_COUNT);
-        launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist);
+        launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist, c->zero_unused_rows ? 1 : 0);
     } else {
         launch(c, zero_u64_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, seg_hist, total);
         c->mark(EV_BUCKET);
@@ -504,7 +505,8 @@ void ensure_render_buffers(vk_ctx* c, const Mapping& m, int k, int levels)
 }
 
 // levels: number of levels to render (grid size); canon must hold levels * 4^k
-void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsigned long long* seg_hist)
+// live_plan: the ladder of the step that is being enqueued (levels is then an upper bound); nullptr: exactly `levels` levels
+void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsigned long long* seg_hist, const vk::Plan* live_plan = nullptr)
 {
     using namespace vk;
     const uint32_t nk = 1u << (2 * k);
@@ -514,7 +516,7 @@ void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsign
     c->last_levels = levels;
     c->last_side = m.side;
     if (seg_hist) {
-        launch(c, fold_kernel, dim3((nk + 255) / 256), dim3(256), 0, seg_hist, k, levels, c->canon.p);
+        launch(c, fold_kernel, dim3((nk + 255) / 256), dim3(256), 0, seg_hist, k, levels, c->canon.p, live_plan);
         CU(cudaGetLastError());
     }
     c->mark(EV_FOLD);
@@ -524,7 +526,7 @@ void enqueue_render(vk_ctx* c, const Mapping& m, int k, int levels, const unsign
         if (S < 64) S = 64;
         const size_t smem = (size_t)vk::kImgCluster * S * sizeof(unsigned long long);
         const unsigned threads = S / 2 > 1024 ? 1024 : S / 2;
-        launch(c, image_kernel_cluster, dim3(vk::kImgCluster, levels), dim3(threads), smem, c->canon.p, m.lut.p, nk, n_pix, S, c->pix_d());
+        launch(c, image_kernel_cluster, dim3(vk::kImgCluster, levels), dim3(threads), smem, c->canon.p, m.lut.p, nk, n_pix, S, c->pix_d(), live_plan);
         CU(cudaGetLastError());
     } else {
         dim3 g1((n_pad + 255) / 256, levels);
@@ -743,10 +745,12 @@ void enqueue_step(vk_ctx* c, const Mapping& m, int k, int max_levels_out)
     const size_t n_pix = (size_t)m.side * m.side;
     enqueue_parse(c);
     c->mark(EV_PARSE);
+    c->zero_unused_rows = false;                 // nobody reads the rows beyond the ladder in this form
     enqueue_count(c, k, c->seg_hist.p);
+    c->zero_unused_rows = true;
     // the number of levels is only known on the device: render max_levels_out, rows beyond the ladder
     // come from all-zero segments and are ignored by the caller
-    enqueue_render(c, m, k, max_levels_out, c->seg_hist.p);
+    enqueue_render(c, m, k, max_levels_out, c->seg_hist.p, c->plan_d);
     // Plan + pixels in one copy
     CU(cudaMemcpyAsync(c->out_h, c->out_d, kPlanPad + (size_t)max_levels_out * n_pix, cudaMemcpyDeviceToHost, c->stream));
 }
@@ -1037,7 +1041,7 @@ int vk_render(vk_ctx* c, int slot, int k, int n_levels, const uint64_t* seg_hist
             enqueue_render(c, *m, k, n_levels, sh);
         } else {
             c->generation += c->canon.ensure((size_t)n_levels * nk);
-            launch(c, vk::fold_kernel, dim3((nk + 255) / 256), dim3(256), 0, sh, k, n_levels, c->canon.p);
+            launch(c, vk::fold_kernel, dim3((nk + 255) / 256), dim3(256), 0, sh, k, n_levels, c->canon.p, (const vk::Plan*)nullptr);
             CU(cudaGetLastError());
         }
         if (canon_host)
@@ -1367,7 +1371,7 @@ int vk_sharded_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, in
             NC(api.AllReduce(c->seg_hist.p, c->seg_hist.p, n_hist + vk::kShardTail, ncclUint64, ncclSum, c->comm, c->stream));
             launch(c, vk::shard_tail_kernel, dim3(1), dim3(256), 0, c->plan_d, tail, 1);
             launch(c, vk::zero_u64_kernel, dim3(1), dim3(256), 0, tail, (uint64_t)vk::kShardTail);      // the row belongs to a segment again
-            enqueue_render(c, m, k, max_levels_out, c->seg_hist.p);
+            enqueue_render(c, m, k, max_levels_out, c->seg_hist.p, c->plan_d);
             CU(cudaMemcpyAsync(c->out_h, c->out_d, kPlanPad + (size_t)max_levels_out * n_pix, cudaMemcpyDeviceToHost, c->stream));
             c->mark(EV_DONE);
         });

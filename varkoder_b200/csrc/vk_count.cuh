@@ -1189,12 +1189,14 @@ reduce_slabs9h_kernel(const uint32_t* __restrict__ slabs, const Plan* __restrict
 // grid covers kMaxLevels * 4^k bins; segments beyond the ladder are written as zero.
 __global__ void __launch_bounds__(256)
 reduce_slabs_kernel(const uint32_t* __restrict__ slabs, const Plan* __restrict__ plan, uint32_t nk,
-                    unsigned long long* __restrict__ seg_hist)
+                    unsigned long long* __restrict__ seg_hist, int zero_unused)
 {
     pdl_wait();
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (uint64_t)kMaxLevels * nk) return;
     const uint32_t s = (uint32_t)(g / nk), i = (uint32_t)(g % nk);
+    // zero_unused = 0 (the fused step): the rows beyond the ladder are left alone -- the fold only reads the ladder's rows
+    if (!zero_unused && (int)s >= plan->n_levels) return;
     unsigned long long sum = 0;
     const uint32_t c0 = plan->seg_cta_begin[s], c1 = plan->seg_cta_begin[s + 1];
     for (uint32_t c = c0; c < c1; ++c) sum += slabs[(size_t)c * nk + i];

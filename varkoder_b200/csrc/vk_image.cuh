@@ -18,17 +18,34 @@ namespace vk {
 namespace cg = cooperative_groups;
 
 // canon[l][x] (lex index x) = sum over segments s >= l of fwd[s][i] + fwd[s][rc i], i = internal index of x.
+// live_plan (the fused step, where n_levels is an upper bound): only the rows of the ladder are folded -- nobody reads the others.
 __global__ void __launch_bounds__(256)
-fold_kernel(const unsigned long long* __restrict__ seg_hist, int k, int n_levels, unsigned long long* __restrict__ canon)
+fold_kernel(const unsigned long long* __restrict__ seg_hist, int k, int n_levels, unsigned long long* __restrict__ canon,
+            const Plan* __restrict__ live_plan)
 {
     pdl_wait();
     const uint32_t nk = 1u << (2 * k);
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= nk) return;
+    if (live_plan && live_plan->n_levels < n_levels) n_levels = live_plan->n_levels;
     const uint32_t i = lex_to_internal(x, k);
     const uint32_t rc = internal_revcomp(i, k);
     unsigned long long run = 0;
-    for (int s = n_levels - 1; s >= 0; --s) {
+    int s = n_levels - 1;
+    for (; s >= 3; s -= 4) {                    // four rows' loads in flight together (the loop was one round trip per row)
+        unsigned long long f[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            f[j] = seg_hist[(size_t)(s - j) * nk + i];
+            if (rc != i) f[j] += seg_hist[(size_t)(s - j) * nk + rc];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            run += f[j];
+            canon[(size_t)(s - j) * nk + x] = run;
+        }
+    }
+    for (; s >= 0; --s) {
         unsigned long long f = seg_hist[(size_t)s * nk + i];
         if (rc != i) f += seg_hist[(size_t)s * nk + rc];
         run += f;
@@ -59,9 +76,12 @@ constexpr uint32_t kImgIdxBits = 16;
 
 __global__ void __cluster_dims__(kImgCluster, 1, 1) __launch_bounds__(1024, 1)
 image_kernel_cluster(const unsigned long long* __restrict__ canon, const int32_t* __restrict__ lut, uint32_t nk,
-                     uint32_t n_pix, uint32_t S, uint8_t* __restrict__ pixels)
+                     uint32_t n_pix, uint32_t S, uint8_t* __restrict__ pixels, const Plan* __restrict__ live_plan)
 {
     pdl_wait();
+    // the fused step renders max_levels_out levels (the ladder is only known on the device): the clusters of the levels
+    // beyond it leave at once and give their SMs to the other samples in flight (a 30 Mbp sample has 7 of 16)
+    if (live_plan && blockIdx.y >= (uint32_t)live_plan->n_levels) return;
     extern __shared__ unsigned long long s_keys[];        // [kImgCluster][S]: slice r at offset r * S, in every CTA
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t rank = cluster.block_rank();
