@@ -965,7 +965,8 @@ def test_base_content_argument_and_state_errors():
 # ------------------------------------------------------------------- step variants: graph / plain, packed / text
 @pytest.mark.parametrize("packed,graph,chunks,pairs,lanes", [("1", "1", "1", "0", "0"), ("1", "0", "1", "0", "0"), ("0", "1", "1", "0", "0"),
                                                              ("0", "0", "1", "0", "0"), ("0", "1", "0", "0", "0"), ("0", "1", "1", "1", "0"),
-                                                             ("0", "0", "0", "1", "0"), ("0", "1", "0", "0", "1"), ("0", "0", "0", "0", "1")])
+                                                             ("0", "0", "0", "1", "0"), ("0", "1", "0", "0", "1"), ("0", "0", "0", "0", "1"),
+                                                             ("0", "1", "0", "0", "2"), ("0", "0", "0", "0", "3")])
 def test_step_variants_bit_exact(monkeypatch, packed, graph, chunks, pairs, lanes):
     """The fused call in its forms -- submitted as one CUDA graph or kernel by kernel, count kernels fed by the 2-bit
     pack of the framing pass or classifying the text themselves, from the chunk table or from the read table -- on samples of very different sizes through ONE

@@ -14,6 +14,7 @@
 #include "vk_common.cuh"
 #include "vk_count.cuh"
 #include "vk_countu.cuh"
+#include "vk_countt.cuh"
 #include "vk_image.cuh"
 #include "vk_parse.cuh"
 #include "vk_quality.cuh"
@@ -112,6 +113,8 @@ struct vk_ctx {
     bool use_pairs = false;         // VK_COUNT_PAIRS=1: k = 7 through 8-mer pairs in 16-bit bins (exact; halves the
                                     // shared-memory traffic but costs more instructions: 168 vs 143 us, profiles/r01_notes.md)
     bool use_lanes = false;         // VK_COUNT_LANES=1: k = 7 with one read per lane, pairs, uniform fast path (countu_kernel)
+    unsigned countt_knobs = 0;      // VK_COUNTT_KNOBS: experiments of countt_kernel (vk_countt.cuh)
+    int lanes_mode = 0;             // VK_COUNT_LANES=2 / 3: the same with cp.async staging (countt_kernel, 16 / 12 warps)
     bool use_fast = true;           // VK_COUNT_FAST=0: 16-bit bins always through returning adds + drains (exact in one go)
     bool count_safe = false;        // set for the repeat of a step whose fire-and-forget count reported a wrapped bin
     uint64_t count_fallbacks = 0;
@@ -347,6 +350,9 @@ void prepare_count_kernels()
         if constexpr (K == 7) {
             CU(cudaFuncSetAttribute(countp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((32768 + 16384) * sizeof(uint32_t))));
             CU(cudaFuncSetAttribute(countu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countu_smem_bytes()));
+            CU(cudaFuncSetAttribute((countt_kernel<16, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<16>()));
+            CU(cudaFuncSetAttribute((countt_kernel<16, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<16>()));
+            CU(cudaFuncSetAttribute((countt_kernel<12, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<12>()));
         }
     }
     if constexpr (K == 7 || K == 8) {
@@ -389,8 +395,14 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
     if constexpr (K == 7) {
         // k = 7, one read per lane, pairs (vk_countu.cuh); a wrapped bin repeats the count with the u32 kernel
         if (c->use_lanes && !PACKED && !c->chunk_mode(7) && c->use_fast && !c->count_safe) {
-            const size_t smem = countu_smem_bytes();
-            launch(c, countu_kernel, grid, block, smem, sa, (const uint64_t*)c->sorted.p, c->plan_d, c->slabs.p, 1u);
+            if (c->lanes_mode == 2)
+                launch(c, (countt_kernel<16, true>), grid, dim3(512), countt_smem_bytes<16>(), sa, (const uint64_t*)c->sorted.p, c->plan_d, c->slabs.p, 1u | (c->countt_knobs << 8));
+            else if (c->lanes_mode == 3)
+                launch(c, (countt_kernel<16, false>), grid, dim3(512), countt_smem_bytes<16>(), sa, (const uint64_t*)c->sorted.p, c->plan_d, c->slabs.p, 1u);
+            else if (c->lanes_mode == 4)
+                launch(c, (countt_kernel<12, true>), grid, dim3(384), countt_smem_bytes<12>(), sa, (const uint64_t*)c->sorted.p, c->plan_d, c->slabs.p, 1u);
+            else
+                launch(c, countu_kernel, grid, block, countu_smem_bytes(), sa, (const uint64_t*)c->sorted.p, c->plan_d, c->slabs.p, 1u);
             c->mark(EV_COUNT);
             launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist, c->zero_unused_rows ? 1 : 0);
             return;
@@ -831,7 +843,8 @@ int vk_ctx_create(int device, vk_ctx** out)
         if (const char* e = getenv("VK_PDL")) c->use_pdl = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT16")) c->use_count16 = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT_PAIRS")) c->use_pairs = atoi(e) != 0;
-        if (const char* e = getenv("VK_COUNT_LANES")) c->use_lanes = atoi(e) != 0;
+        if (const char* e = getenv("VK_COUNT_LANES")) { c->lanes_mode = atoi(e); c->use_lanes = c->lanes_mode != 0; }
+        if (const char* e = getenv("VK_COUNTT_KNOBS")) c->countt_knobs = (unsigned)strtoul(e, nullptr, 0);
         if (const char* e = getenv("VK_COUNT_FAST")) c->use_fast = atoi(e) != 0;
         if (const char* e = getenv("VK_PACKED")) c->use_packed = atoi(e) != 0;
         if (const char* e = getenv("VK_CHUNKS")) c->use_chunks = atoi(e) != 0;
