@@ -350,9 +350,10 @@ void prepare_count_kernels()
         if constexpr (K == 7) {
             CU(cudaFuncSetAttribute(countp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((32768 + 16384) * sizeof(uint32_t))));
             CU(cudaFuncSetAttribute(countu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countu_smem_bytes()));
-            CU(cudaFuncSetAttribute((countt_kernel<16, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<16>()));
-            CU(cudaFuncSetAttribute((countt_kernel<16, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<16>()));
-            CU(cudaFuncSetAttribute((countt_kernel<12, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<12>()));
+            CU(cudaFuncSetAttribute((countt_kernel<16, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<16>()));
+            CU(cudaFuncSetAttribute((countt_kernel<16, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<16>()));
+            CU(cudaFuncSetAttribute((countt_kernel<16, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<16>()));
+            CU(cudaFuncSetAttribute((countt_kernel<16, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<16>()));
         }
     }
     if constexpr (K == 7 || K == 8) {
@@ -395,12 +396,12 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
     if constexpr (K == 7) {
         // k = 7, one read per lane, pairs (vk_countu.cuh); a wrapped bin repeats the count with the u32 kernel
         if (c->use_lanes && !PACKED && !c->chunk_mode(7) && c->use_fast && !c->count_safe) {
-            if (c->lanes_mode == 2)
-                launch(c, (countt_kernel<16, true>), grid, dim3(512), countt_smem_bytes<16>(), sa, (const uint64_t*)c->sorted.p, c->plan_d, c->slabs.p, 1u | (c->countt_knobs << 8));
-            else if (c->lanes_mode == 3)
-                launch(c, (countt_kernel<16, false>), grid, dim3(512), countt_smem_bytes<16>(), sa, (const uint64_t*)c->sorted.p, c->plan_d, c->slabs.p, 1u);
-            else if (c->lanes_mode == 4)
-                launch(c, (countt_kernel<12, true>), grid, dim3(384), countt_smem_bytes<12>(), sa, (const uint64_t*)c->sorted.p, c->plan_d, c->slabs.p, 1u);
+            const uint32_t pol = 1u | (c->countt_knobs << 8);
+            const uint64_t* srt = (const uint64_t*)c->sorted.p;
+            if (c->lanes_mode == 2) launch(c, (countt_kernel<16, 0>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, pol);
+            else if (c->lanes_mode == 3) launch(c, (countt_kernel<16, 1>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, pol);
+            else if (c->lanes_mode == 4) launch(c, (countt_kernel<16, 2>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, pol);
+            else if (c->lanes_mode == 5) launch(c, (countt_kernel<16, 3>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, pol);
             else
                 launch(c, countu_kernel, grid, block, countu_smem_bytes(), sa, (const uint64_t*)c->sorted.p, c->plan_d, c->slabs.p, 1u);
             c->mark(EV_COUNT);

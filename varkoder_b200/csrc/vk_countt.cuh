@@ -37,6 +37,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 {
     asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void red_global_add(uint32_t* p, uint32_t v) { asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -72,7 +73,7 @@ __device__ __forceinline__ Cls4z classify4t(uint32_t x, uint32_t one, uint32_t z
 template <bool FMA>
 __device__ __forceinline__ uint32_t gather8t(uint32_t za, uint32_t zb, uint32_t zero, uint32_t m28) { return (zb | shr_fma<FMA, 4>(za, m28, zero)) * 0x00204081u; }
 
-template <int NW, bool FMA>
+template <int NW, int FM>
 __global__ void __launch_bounds__(NW * 32, 1)
 countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sorted, Plan* __restrict__ plan,
               uint32_t* __restrict__ slabs, uint32_t policy)
@@ -81,9 +82,10 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
     constexpr int K = 7;
     constexpr uint32_t NK = 1u << (2 * K);
     constexpr uint32_t FULL = 0xffffffffu;
+    constexpr bool FMA_CLS = (FM & 1) != 0, FMA_PAIR = (FM & 2) != 0;      // which shifts are multiplies (measured: none is fastest)
     const uint8_t* __restrict__ text = sa->text;
     const int breaklen = sa->pa.p.breaklength;
-    const uint32_t knobs = policy >> 8;          // experiments (VK_COUNTT_KNOBS): bit 0: no L2 prefetch; bits 4..7: H
+    const uint32_t knobs = policy >> 8;          // experiments (VK_COUNTT_KNOBS): bits 4..7: H
     policy &= 0xFFu;
     if (!countu_wanted(plan, breaklen, policy)) return;
     const uint32_t zero = (uint32_t)(sa->n_bytes >> 62);              // 0 (texts are shorter than 2^40), but not to ptxas
@@ -130,16 +132,17 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
     __syncthreads();
     if (R == 0u) return;                          // (countu_wanted keeps such samples away; policy 1 with huge reads)
 
-    // ---- units of R reads are claimed four units ahead of their use
+    // ---- units of R reads are claimed three units ahead of their use (the entries of a unit are needed when the unit
+    // before it is half done: that is when its first copies are issued)
     auto entry_at = [&](uint32_t base) -> uint64_t {
         return (lane < R && base < cta_hi && base + lane < cta_hi) ? __ldg(seg_sorted + base + lane) : 0ull;
     };
     auto clamp_hi = [&](uint32_t b) -> uint32_t { return b < cta_hi ? b : cta_hi; };      // (shares are below 2^32 - 2^20: claims do not wrap)
     uint32_t claim0 = 0;
-    if (lane == 0) claim0 = atomicAdd(&s_next, 4u * R);
+    if (lane == 0) claim0 = atomicAdd(&s_next, 3u * R);
     uint32_t baseA = clamp_hi(__shfl_sync(FULL, claim0, 0));
-    uint32_t baseB = clamp_hi(baseA + R), baseC = clamp_hi(baseA + 2u * R), baseD = clamp_hi(baseA + 3u * R);
-    uint64_t entA = entry_at(baseA), entB = entry_at(baseB), entC = entry_at(baseC), entD = entry_at(baseD);
+    uint32_t baseB = clamp_hi(baseA + R), baseC = clamp_hi(baseA + 2u * R);
+    uint64_t entA = entry_at(baseA), entB = entry_at(baseB), entC = entry_at(baseC);
     uint32_t pending = 0;                                              // lane 0: the claim whose answer is read a unit later
     if (lane == 0) pending = atomicAdd(&s_next, R);
 
@@ -178,17 +181,8 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
         }
         cp_async_commit();
     };
-    // the text of a unit is pulled into L2 ahead of its copies: lane l asks for the lines of its read
-    auto prefetch_l2 = [&](uint64_t ent) {
-        const uint32_t len = (uint32_t)(ent & kEntryLenMask);
-        if (len != 0u && !(knobs & 1u)) {
-            const uint64_t start = ent >> kEntryLenBits;
-            const uint8_t* const p = text + (start & ~15ull);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + ((((uint32_t)start & 15u) + len - 1u) & ~15u)));
-            if (len > 128u) for (uint32_t w = 128; w < len; w += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + w));
-        }
-    };
+    // (No L2 prefetch: asking the lines of the units ahead into L2 made the kernel 20 % slower -- 600 instead of 410 MB of
+    // DRAM reads, the copies' own lead is enough: profiles/r02c_notes.md.)
 
     // ---- the warp's queue of irregular words (window low | window high + E << 16)
     uint32_t* const qx = s_raw + 32768u + NW * kTBufWords + warp * (2u * kTQueue);
@@ -231,23 +225,20 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
 
     // codes (32 bits) and validity (16 bits) of one staged text word
     auto classify16 = [&](const uint4 q, uint32_t& P, uint32_t& V) {
-        const Cls4z c0 = classify4t<FMA>(q.x, one, zero, m29), c1 = classify4t<FMA>(q.y, one, zero, m29), c2 = classify4t<FMA>(q.z, one, zero, m29), c3 = classify4t<FMA>(q.w, one, zero, m29);
+        const Cls4z c0 = classify4t<FMA_CLS>(q.x, one, zero, m29), c1 = classify4t<FMA_CLS>(q.y, one, zero, m29), c2 = classify4t<FMA_CLS>(q.z, one, zero, m29), c3 = classify4t<FMA_CLS>(q.w, one, zero, m29);
         P = __byte_perm(__byte_perm(c0.packed_hi, c1.packed_hi, 0x0073), __byte_perm(c2.packed_hi, c3.packed_hi, 0x0073), 0x5410);
-        V = __byte_perm(gather8t<FMA>(c0.z, c1.z, zero, m28), gather8t<FMA>(c2.z, c3.z, zero, m28), 0x0073) & 0xFFFFu;
+        V = __byte_perm(gather8t<FMA_CLS>(c0.z, c1.z, zero, m28), gather8t<FMA_CLS>(c2.z, c3.z, zero, m28), 0x0073) & 0xFFFFu;
     };
 
     // Per unit: the second half of its text is asked for when the unit before it is done (the first half arrived while
     // that unit's last words were counted), waited for when the count reaches word H - 3, and the first half of the NEXT
     // unit is asked for after word H - 2, when no lane needs a word below H any more.
     issue_half(entA, rwF);
-    prefetch_l2(entB);
-    prefetch_l2(entC);
     while (baseA < cta_hi) {
         // ---- the claim made a unit ago has its answer; the entries of that unit are asked for now (used four units on)
-        const uint32_t baseE = clamp_hi(__shfl_sync(FULL, pending, 0));
-        const uint64_t entE = entry_at(baseE);
-        if (lane == 0 && baseE < cta_hi) pending = atomicAdd(&s_next, R);
-        prefetch_l2(entD);
+        const uint32_t baseD = clamp_hi(__shfl_sync(FULL, pending, 0));
+        const uint64_t entD = entry_at(baseD);
+        if (lane == 0 && baseD < cta_hi) pending = atomicAdd(&s_next, R);
         issue_half(entA, rwS);                                          // (the unit before this one is done with those quads)
         cp_async_wait<1>();                                             // first half of this unit
         __syncwarp();
@@ -281,8 +272,8 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
             auto count8 = [&](const uint32_t Xl, const uint32_t Xh) {
                 const uint32_t X2 = __funnelshift_r(Xl, Xh, 16);
                 uint32_t sh[8];
-                sh[0] = Xl; sh[1] = shr_fma<FMA, 4>(Xl, m28, zero); sh[2] = shr_fma<FMA, 8>(Xl, m24, zero); sh[3] = shr_fma<FMA, 12>(Xl, m20, zero);
-                sh[4] = X2; sh[5] = shr_fma<FMA, 4>(X2, m28, zero); sh[6] = shr_fma<FMA, 8>(X2, m24, zero); sh[7] = shr_fma<FMA, 12>(X2, m20, zero);
+                sh[0] = Xl; sh[1] = shr_fma<FMA_PAIR, 4>(Xl, m28, zero); sh[2] = shr_fma<FMA_PAIR, 8>(Xl, m24, zero); sh[3] = shr_fma<FMA_PAIR, 12>(Xl, m20, zero);
+                sh[4] = X2; sh[5] = shr_fma<FMA_PAIR, 4>(X2, m28, zero); sh[6] = shr_fma<FMA_PAIR, 8>(X2, m24, zero); sh[7] = shr_fma<FMA_PAIR, 12>(X2, m20, zero);
                 uint32_t ad[8], in[8];
 #pragma unroll
                 for (int m = 0; m < 8; ++m) {
@@ -380,8 +371,8 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
         if (!waited) cp_async_wait<0>();
         __syncwarp();                                                   // every lane has read its words: the buffer may be overwritten
         if (!filled) issue_half(entB, rwF);
-        entA = entB; entB = entC; entC = entD; entD = entE;
-        baseA = baseB; baseB = baseC; baseC = baseD; baseD = baseE;
+        entA = entB; entB = entC; entC = entD;
+        baseA = baseB; baseB = baseC; baseC = baseD;
     }
     cp_async_wait<0>();
     if (qn != 0u) drain(0u, qn);
@@ -399,8 +390,8 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
         big |= q.x | q.y | q.z | q.w;
         low += all;
         const uint32_t x1 = x | 0x2000u;
-        atomicAdd(slab + x, (h8[x] & 0xFFFFu) + (h8[x | 0x4000u] & 0xFFFFu) + (all - up));      // (RED: nothing comes back)
-        atomicAdd(slab + x1, (h8[x1] & 0xFFFFu) + (h8[x1 | 0x4000u] & 0xFFFFu) + up);
+        red_global_add(slab + x, (h8[x] & 0xFFFFu) + (h8[x | 0x4000u] & 0xFFFFu) + (all - up));
+        red_global_add(slab + x1, (h8[x1] & 0xFFFFu) + (h8[x1 | 0x4000u] & 0xFFFFu) + up);
     }
     {
         unsigned long long mine = (unsigned long long)(long long)(int32_t)made;      // (a lane drains other lanes' words: its own balance may be negative)
