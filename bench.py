@@ -893,7 +893,11 @@ def main():
         value = world * n_bases * steps / (dev_ms * 1e-3) / 1e9
         count_s = count_ms * 1e-3
         achieved = n_bases * BYTES_PER_BASE / count_s / 1e9
-        kernel_name = "count_kernel<7,smem>" if K <= 7 else ("count9h_kernel" if K == 9 else f"count16_kernel<{K}>")
+        # k = 7, reads of one length (this workload): countt_kernel counts, count_kernel<7> is launched behind it and
+        # returns at once (the choice is made on the device, vk_countt.cuh); VK_COUNT_LANES=0 keeps the flat-lane kernel
+        lanes_env = os.environ.get("VK_COUNT_LANES", "-1")
+        k7_name = "count_kernel<7,smem>" if lanes_env == "0" else ("countt_kernel<16>" if lanes_env in ("-1", "2") else f"count kernel VK_COUNT_LANES={lanes_env}")
+        kernel_name = (k7_name if K == 7 else f"count_kernel<{K},smem>") if K <= 7 else ("count9h_kernel" if K == 9 else f"count16_kernel<{K}>")
         traffic = traffic_src = None
         try:
             with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:

@@ -966,7 +966,7 @@ def test_base_content_argument_and_state_errors():
 @pytest.mark.parametrize("packed,graph,chunks,pairs,lanes", [("1", "1", "1", "0", "0"), ("1", "0", "1", "0", "0"), ("0", "1", "1", "0", "0"),
                                                              ("0", "0", "1", "0", "0"), ("0", "1", "0", "0", "0"), ("0", "1", "1", "1", "0"),
                                                              ("0", "0", "0", "1", "0"), ("0", "1", "0", "0", "1"), ("0", "0", "0", "0", "1"),
-                                                             ("0", "1", "0", "0", "2"), ("0", "0", "0", "0", "3")])
+                                                             ("0", "1", "0", "0", "2"), ("0", "0", "0", "0", "3"), ("0", "1", "0", "0", "-1"), ("0", "0", "0", "0", "-1")])
 def test_step_variants_bit_exact(monkeypatch, packed, graph, chunks, pairs, lanes):
     """The fused call in its forms -- submitted as one CUDA graph or kernel by kernel, count kernels fed by the 2-bit
     pack of the framing pass or classifying the text themselves, from the chunk table or from the read table -- on samples of very different sizes through ONE
@@ -977,7 +977,9 @@ def test_step_variants_bit_exact(monkeypatch, packed, graph, chunks, pairs, lane
     monkeypatch.setenv("VK_GRAPH", graph)
     monkeypatch.setenv("VK_CHUNKS", chunks)      # k <= 7: chunk table written by the scatter kernel / chunk stream in the count kernel
     monkeypatch.setenv("VK_COUNT_PAIRS", pairs)  # k = 7: one shared-memory increment per base pair (read-aligned pairs with the chunk table)
-    monkeypatch.setenv("VK_COUNT_LANES", lanes)  # k = 7: one read per lane, pairs, uniform fast path (countu_kernel)
+    # k = 7: 0 the flat-lane kernel, 1 one read per lane with LDG staging (countu_kernel), 2 / 3 one read per lane with cp.async
+    # staging (countt_kernel, every sample), -1 the default: countt_kernel for samples of one read length, else the flat-lane kernel
+    monkeypatch.setenv("VK_COUNT_LANES", lanes)
     eng = Engine(0)
     try:
         rng = np.random.default_rng(17)

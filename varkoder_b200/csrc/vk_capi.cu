@@ -113,11 +113,14 @@ struct vk_ctx {
     bool use_pairs = false;         // VK_COUNT_PAIRS=1: k = 7 through 8-mer pairs in 16-bit bins (exact; halves the
                                     // shared-memory traffic but costs more instructions: 168 vs 143 us, profiles/r01_notes.md)
     bool use_lanes = false;         // VK_COUNT_LANES=1: k = 7 with one read per lane, pairs, uniform fast path (countu_kernel)
+    bool k7_lanes = false;          // k = 7, automatic choice: the context's last sample was one for countt_kernel (reads of one length)
+    bool in_sharded = false;        // inside vk_sharded_reads_to_images: the ranks repeat steps together, the choice is made on the device
     unsigned countt_knobs = 0;      // VK_COUNTT_KNOBS: experiments of countt_kernel (vk_countt.cuh)
-    int lanes_mode = 0;             // VK_COUNT_LANES=2 / 3: the same with cp.async staging (countt_kernel, 16 / 12 warps)
+    int lanes_mode = -1;            // VK_COUNT_LANES=2 / 3: the same with cp.async staging (countt_kernel, 16 / 12 warps)
     bool use_fast = true;           // VK_COUNT_FAST=0: 16-bit bins always through returning adds + drains (exact in one go)
     bool count_safe = false;        // set for the repeat of a step whose fire-and-forget count reported a wrapped bin
     uint64_t count_fallbacks = 0;
+    uint64_t lanes_flips = 0;       // steps repeated because countt_kernel refused the sample
     bool use_pdl = true;            // VK_PDL=0 disables programmatic dependent launch
     bool test_tight = false;        // VK_TEST_TIGHT_BUCKETS=1: undersized regions, exercises the retry (tests only)
     uint64_t bucket_retries = 0;
@@ -396,7 +399,7 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
     if constexpr (K == 7) {
         // k = 7, one read per lane, pairs (vk_countu.cuh); a wrapped bin repeats the count with the u32 kernel
         if (c->use_lanes && !PACKED && !c->chunk_mode(7) && c->use_fast && !c->count_safe) {
-            const uint32_t pol = 1u | (c->countt_knobs << 8);
+            const uint32_t pol = 1u | ((c->countt_knobs & ~1u) << 8);
             const uint64_t* srt = (const uint64_t*)c->sorted.p;
             if (c->lanes_mode == 2) launch(c, (countt_kernel<16, 0>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, pol);
             else if (c->lanes_mode == 3) launch(c, (countt_kernel<16, 1>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, pol);
@@ -445,13 +448,38 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
         // the histogram sits at a 64 KiB-aligned shared address (vk_count.cuh): up to 64 KiB of padding in front
         const size_t smem = 0x10000 + (size_t)(NK + 32) * sizeof(uint32_t);
         if (c->chunk_mode(K)) launch(c, countd_kernel<K>, grid, block, smem, sa, (const uint64_t*)c->chunks.p, c->plan_d, c->slabs.p);
-        else launch(c, (count_kernel<K, kSmem32, PACKED>), grid, block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p, seg_hist);
+        else {
+            // k = 7, text input: the one-read-per-lane kernel (vk_countt.cuh) for samples whose reads have one length, this
+            // kernel for the others.  Which it is shows on the device only (the scatter kernel leaves the longest read in
+            // the plan), so the context goes by its LAST sample: this kernel counts and reports when the sample was one
+            // for countt_kernel (lanes_verdict bit 0: the next step launches that kernel instead); countt_kernel refuses
+            // a sample that is not (bit 1) and with_table_retry repeats the step with this kernel.  Samples of a context
+            // come from one sequencing run as a rule: one repeated step per change of kind, no idle launch otherwise.
+            // A read-sharded sample (all ranks must agree) launches both and lets the device pick (policy 2).
+            // VK_COUNT_LANES=0: always this kernel.
+            uint32_t lanes_policy = 0;
+            if constexpr (K == 7 && !PACKED) {
+                if (c->lanes_mode < 0 && c->use_fast && !c->count_safe && !c->use_pairs) {
+                    const uint64_t* srt = (const uint64_t*)c->sorted.p;
+                    if (c->in_sharded) {
+                        lanes_policy = 2u;
+                        launch(c, (countt_kernel<16, 0>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, 2u | ((c->countt_knobs & ~1u) << 8));
+                    } else if (c->k7_lanes) {
+                        launch(c, (countt_kernel<16, 0>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, 2u | ((c->countt_knobs | 1u) << 8));
+                        c->mark(EV_COUNT);
+                        launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist, c->zero_unused_rows ? 1 : 0);
+                        return;
+                    } else lanes_policy = 3u;
+                }
+            }
+            launch(c, (count_kernel<K, kSmem32, PACKED>), grid, block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p, seg_hist, lanes_policy);
+        }
         c->mark(EV_COUNT);
         launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist, c->zero_unused_rows ? 1 : 0);
     } else {
         launch(c, zero_u64_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, seg_hist, total);
         c->mark(EV_BUCKET);
-        launch(c, (count_kernel<K, kGlobal, PACKED>), grid, block, 0, sa, pk, c->sorted.p, c->plan_d, c->slabs.p, seg_hist);
+        launch(c, (count_kernel<K, kGlobal, PACKED>), grid, block, 0, sa, pk, c->sorted.p, c->plan_d, c->slabs.p, seg_hist, 0u);
         c->mark(EV_COUNT);
     }
 }
@@ -723,9 +751,19 @@ void with_table_retry(vk_ctx* c, F&& body)
         const bool t_over = c->plan_h->table_overflow != 0, b_over = c->plan_h->bucket_overflow != 0;
         const bool k_small = c->plan_h->chunk_table_small != 0 && !t_over;
         const bool c_over = c->plan_h->count_overflow != 0 && !t_over && !b_over && !k_small;
-        if (!t_over && !b_over && !c_over && !k_small) { c->exact_layout = false; c->count_safe = false; return; }
+        // k = 7: countt_kernel was launched alone and the sample was not one for it (vk_countt.cuh): nothing was counted
+        const bool l_ref = (c->plan_h->lanes_verdict & 2u) != 0 && !t_over && !b_over && !k_small && !c_over;
+        if (!t_over && !b_over && !c_over && !k_small && !l_ref) {
+            if (c->plan_h->lanes_verdict & 1u) c->k7_lanes = true;       // (the flat-lane kernel counted a sample of one read length)
+            c->exact_layout = false;
+            c->count_safe = false;
+            return;
+        }
         if (attempt == 3) { c->count_safe = false; throw ApiError{VK_ERANGE, "read table overflow after resize"}; }
-        if (c_over) {
+        if (l_ref) {
+            c->k7_lanes = false;
+            ++c->lanes_flips;
+        } else if (c_over) {
             // a 16-bit bin of the fire-and-forget count kernel wrapped (a flood of one k-mer): count again, exactly
             c->count_safe = true;
             ++c->count_fallbacks;
@@ -776,7 +814,7 @@ vk_ctx::StepGraph* step_graph(vk_ctx* c, const Mapping& m, int slot, int k, int 
     if (!c->use_graph || c->graph_failed || c->fine_timing) return nullptr;
     for (auto& g : c->graphs)
         if (g.k == k && g.slot == slot && g.side == m.side && g.max_levels == max_levels_out && g.exact == (int)c->exact_layout &&
-            g.packed == ((int)c->use_packed | (c->count_safe ? 2 : 0)) && g.generation == c->generation)
+            g.packed == ((int)c->use_packed | (c->count_safe ? 2 : 0) | (c->k7_lanes ? 4 : 0)) && g.generation == c->generation)
             return &g;
     // stale graphs (a buffer moved) are of no use any more
     for (size_t i = 0; i < c->graphs.size();) {
@@ -808,7 +846,7 @@ vk_ctx::StepGraph* step_graph(vk_ctx* c, const Mapping& m, int slot, int k, int 
         return nullptr;
     }
     ++c->graph_captures;
-    c->graphs.push_back({k, slot, m.side, max_levels_out, (int)c->exact_layout, (int)c->use_packed | (c->count_safe ? 2 : 0), c->generation, exec,
+    c->graphs.push_back({k, slot, m.side, max_levels_out, (int)c->exact_layout, (int)c->use_packed | (c->count_safe ? 2 : 0) | (c->k7_lanes ? 4 : 0), c->generation, exec,
                          c->captured_kernels});
     return &c->graphs.back();
 }
@@ -844,7 +882,7 @@ int vk_ctx_create(int device, vk_ctx** out)
         if (const char* e = getenv("VK_PDL")) c->use_pdl = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT16")) c->use_count16 = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT_PAIRS")) c->use_pairs = atoi(e) != 0;
-        if (const char* e = getenv("VK_COUNT_LANES")) { c->lanes_mode = atoi(e); c->use_lanes = c->lanes_mode != 0; }
+        if (const char* e = getenv("VK_COUNT_LANES")) { c->lanes_mode = atoi(e); c->use_lanes = c->lanes_mode > 0; }
         if (const char* e = getenv("VK_COUNTT_KNOBS")) c->countt_knobs = (unsigned)strtoul(e, nullptr, 0);
         if (const char* e = getenv("VK_COUNT_FAST")) c->use_fast = atoi(e) != 0;
         if (const char* e = getenv("VK_PACKED")) c->use_packed = atoi(e) != 0;
@@ -1347,6 +1385,7 @@ int vk_sharded_reads_to_images(vk_ctx* c, const void* text, uint64_t n_bytes, in
             c->text_own.ensure(n_bytes + 64);
         }
         const size_t n_hist = (size_t)max_levels_out * nk;                    // rows that are exchanged
+        struct InSharded { vk_ctx* c; explicit InSharded(vk_ctx* x) : c(x) { c->in_sharded = true; } ~InSharded() { c->in_sharded = false; } } in_sharded_guard(c);
         with_table_retry(c, [&] {
             c->generation += c->seg_hist.ensure((size_t)vk::kMaxLevels * nk + vk::kShardTail);
             ensure_tables_for(c, reads_bound(n_bytes));

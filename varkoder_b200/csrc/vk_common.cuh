@@ -62,6 +62,8 @@ struct Plan {
     unsigned long long seg_extra[kMaxLevels];    // entries beyond one per read: a read of 2^24 bases or more is several entries (vk_bucket.cuh)
     uint32_t n_long;                             // reads of 2^24 bases or more listed by the scatter kernel (long_reads_kernel cuts them up)
     uint32_t len_min, len_max;                   // shortest / longest read that is counted (scatter kernel): one read per lane pays only for reads of one length
+    uint32_t lanes_verdict;                      // k = 7 count kernels: bit 0: the sample is one for countt_kernel (says the flat-lane kernel, which counted it);
+                                                 // bit 1: it is not (says countt_kernel, which did not count it: the host repeats the step with the other kernel)
 };
 
 // What plan_kernel needs beside the framing: the sample's options and the capacities of the tables.

@@ -417,14 +417,35 @@ __device__ __forceinline__ void emit16(const uint64_t W4, const uint32_t E, cons
     }
 }
 
+// Is the sample one for the one-read-per-lane kernels (vk_countt.cuh, vk_countu.cuh)?  Reads of ONE length (raw Illumina
+// reads: BASELINE configs 1, 2, 3, 5), short enough for a unit of 27 reads or more (13 text words each: 176 bases), none
+// longer than the break length.  "One length" is judged by the mean: the longest counted read (scatter kernel) against
+// bases / records of the framing pass -- a unit that holds a shorter read falls back to the queue for its last words, so
+// a few stragglers (the odd last read of a file) cost nothing, while a sample whose mean is 0.4 % below its longest read
+// may have one in every eighth unit and is left to the flat-lane kernel.  Evaluated on the device by both count kernels
+// (exactly one of them counts): everything it needs is in the plan when the scatter kernel is done.
+__device__ __forceinline__ bool countu_wanted(const Plan* __restrict__ plan, int breaklen, uint32_t policy)
+{
+    if (policy != 2u) return policy == 1u;       // 0: never, 1: always (tests), 2: by the sample
+    const uint64_t hi = plan->len_max;
+    return hi != 0u && hi <= 176u && plan->nsites_true * 256u >= hi * 255u * plan->n_reads &&
+           (breaklen <= 0 || hi <= (uint64_t)breaklen);
+}
+
 template <int K, int MODE, bool PACKED>
 __global__ void __launch_bounds__(kCountThreads)
 count_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __restrict__ sorted, Plan* __restrict__ plan,
-             uint32_t* __restrict__ slabs, unsigned long long* __restrict__ seg_hist)
+             uint32_t* __restrict__ slabs, unsigned long long* __restrict__ seg_hist, uint32_t lanes_policy)
 {
     pdl_wait();
     const uint4* __restrict__ text16 = reinterpret_cast<const uint4*>(sa->text);
     const int breaklen = sa->pa.p.breaklength;
+    // lanes_policy 2: countt_kernel was launched in front of this kernel with the same rule -- exactly one of the two counts
+    // lanes_policy 3: this kernel counts, and tells the host when the sample would have been one for countt_kernel (the
+    // context then launches that kernel for its next sample, vk_capi.cu)
+    if (K == 7 && MODE == kSmem32 && lanes_policy == 2u && countu_wanted(plan, breaklen, 2u)) return;
+    if (K == 7 && MODE == kSmem32 && lanes_policy == 3u && blockIdx.x == 0 && threadIdx.x == 0 && countu_wanted(plan, breaklen, 2u))
+        atomicOr(&plan->lanes_verdict, 1u);
     const uint32_t one = (uint32_t)(sa->n_bytes >> 62) + 1u;          // 1 (texts are shorter than 2^40), but not to ptxas
     static_assert(MODE == kSmem32 || MODE == kGlobal, "count16_kernel is the kSmem16 kernel");
     constexpr uint32_t NK = 1u << (2 * K);

@@ -71,7 +71,11 @@ __device__ __forceinline__ Cls4z classify4t(uint32_t x, uint32_t one, uint32_t z
     return c;
 }
 template <bool FMA>
-__device__ __forceinline__ uint32_t gather8t(uint32_t za, uint32_t zb, uint32_t zero, uint32_t m28) { return (zb | shr_fma<FMA, 4>(za, m28, zero)) * 0x00204081u; }
+__device__ __forceinline__ uint32_t gather8t(uint32_t za, uint32_t zb, uint32_t zero, uint32_t m28)
+{
+    // (zb | za >> 4) * M as zb * M + (za >> 4) * M: the OR of disjoint bits is an add, and an add folds into the multiply (FMA pipe)
+    return mad_lo_op(zb, 0x00204081u, shr_fma<FMA, 4>(za, m28, zero) * 0x00204081u);
+}
 
 template <int NW, int FM>
 __global__ void __launch_bounds__(NW * 32, 1)
@@ -85,9 +89,12 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
     constexpr bool FMA_CLS = (FM & 1) != 0, FMA_PAIR = (FM & 2) != 0;      // which shifts are multiplies (measured: none is fastest)
     const uint8_t* __restrict__ text = sa->text;
     const int breaklen = sa->pa.p.breaklength;
-    const uint32_t knobs = policy >> 8;          // experiments (VK_COUNTT_KNOBS): bits 4..7: H
+    const uint32_t knobs = policy >> 8;          // bit 0: this kernel is the only one launched (a refusal must be reported); bits 4..7: H (experiments, VK_COUNTT_KNOBS)
     policy &= 0xFFu;
-    if (!countu_wanted(plan, breaklen, policy)) return;
+    if (!countu_wanted(plan, breaklen, policy)) {
+        if ((knobs & 1u) && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&plan->lanes_verdict, 2u);      // nobody else counts this step: say so
+        return;
+    }
     const uint32_t zero = (uint32_t)(sa->n_bytes >> 62);              // 0 (texts are shorter than 2^40), but not to ptxas
     const uint32_t one = zero + 1u;
     const uint32_t m29 = (1u << 29) + zero, m28 = (1u << 28) + zero, m24 = (1u << 24) + zero, m20 = (1u << 20) + zero;      // shifts by 3, 4, 8, 12 as multiplies
@@ -117,8 +124,6 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
     const uint32_t h8_addr = (uint32_t)__cvta_generic_to_shared(s_raw);
     const uint32_t buf_addr = h8_addr + (32768u + warp * kTBufWords + 4u) * 4u;      // quad 0 of the warp's buffer
     uint32_t* const slab = slabs + (size_t)logical_cta() * NK;
-    for (uint32_t i = tid; i < 8192u; i += nthr) reinterpret_cast<uint4*>(s_raw)[i] = make_uint4(0, 0, 0, 0);
-    for (uint32_t i = tid; i < NK / 4u; i += nthr) reinterpret_cast<uint4*>(slab)[i] = make_uint4(0, 0, 0, 0);      // singles and the final fold ADD to the slab
     if (tid < 2) s_chk[tid] = 0;
     // the CTAs of a segment take equal contiguous shares of its sorted reads; inside a CTA the warps claim units of R reads
     // from a counter in shared memory (a counter per segment in global memory: 2368 warps x 18 claims on one address,
@@ -145,6 +150,10 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
     uint64_t entA = entry_at(baseA), entB = entry_at(baseB), entC = entry_at(baseC);
     uint32_t pending = 0;                                              // lane 0: the claim whose answer is read a unit later
     if (lane == 0) pending = atomicAdd(&s_next, R);
+    // the tables are cleared while the first entries are on their way
+    for (uint32_t i = tid; i < 8192u; i += nthr) reinterpret_cast<uint4*>(s_raw)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < NK / 4u; i += nthr) reinterpret_cast<uint4*>(slab)[i] = make_uint4(0, 0, 0, 0);      // singles and the final fold ADD to the slab
+    __syncthreads();
 
     // copy round n of a half: this lane moves word w of read r to quad r * S + w -- fixed for the whole kernel.
     // packed: r (5 bits) | w * 16 (13 bits, byte offset in the text) << 5 | (r * S + w) * 16 (13 bits, byte offset in the buffer) << 18
@@ -269,8 +278,8 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
             const uint32_t inc_mask = active ? 0x20000u : 0u, inc_one = active ? 1u : 0u;
             // eight pair increments of a fast word: counted first (every lane that holds a read), looked at afterwards.
             // Pairs 0..3 lie in the low word of the window, pairs 4..7 in the word that starts at its bit 16
-            auto count8 = [&](const uint32_t Xl, const uint32_t Xh) {
-                const uint32_t X2 = __funnelshift_r(Xl, Xh, 16);
+            auto count8 = [&](const uint32_t Xl, const uint32_t C) {
+                const uint32_t X2 = C >> 2;                              // the window from its bit 16 on: (Cc << 2 | C << 14) >> 16
                 uint32_t sh[8];
                 sh[0] = Xl; sh[1] = shr_fma<FMA_PAIR, 4>(Xl, m28, zero); sh[2] = shr_fma<FMA_PAIR, 8>(Xl, m24, zero); sh[3] = shr_fma<FMA_PAIR, 12>(Xl, m20, zero);
                 sh[4] = X2; sh[5] = shr_fma<FMA_PAIR, 4>(X2, m28, zero); sh[6] = shr_fma<FMA_PAIR, 8>(X2, m24, zero); sh[7] = shr_fma<FMA_PAIR, 12>(X2, m20, zero);
@@ -336,7 +345,7 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
                 uint32_t VW = Vc | (Vv << 6);                           // bit b <-> base 16 v + b of the read, b = 0..21
                 const uint32_t Xl = (Cc << 2) | (C << 14), Xh = C >> 18;
                 const bool fast = 0u < vfast;
-                if (fast) count8(Xl, Xh);
+                if (fast) count8(Xl, C);
                 const bool push = wants_push(0u, fast, VW);
                 do_push(0u, fast, push, Xl, Xh, VW);
                 Cc = C >> 20; Vc = Vv >> 10; Pp = P; Vp = V;
@@ -356,8 +365,8 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
                 const uint32_t Xla = (Cc << 2) | (Ca << 14), Xha = Ca >> 18;
                 const uint32_t Xlb = ((Ca >> 20) << 2) | (Cb << 14), Xhb = Cb >> 18;
                 const bool fast_a = v < vfast, fast_b = v + 1u < vfast;
-                if (fast_a) count8(Xla, Xha);
-                if (fast_b) count8(Xlb, Xhb);
+                if (fast_a) count8(Xla, Ca);
+                if (fast_b) count8(Xlb, Cb);
                 const bool push_a = wants_push(v, fast_a, VWa), push_b = wants_push(v + 1u, fast_b, VWb);
                 if (__any_sync(FULL, push_a || push_b)) {
                     do_push(v, fast_a, push_a, Xla, Xha, VWa);

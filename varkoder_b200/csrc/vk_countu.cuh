@@ -49,16 +49,6 @@ constexpr uint32_t kCuQueue = kCuValid + kCountuWarps * kStagePieces / 2;
 constexpr uint32_t kCuWords = kCuQueue + kCountuWarps * 3 * kQueue;
 constexpr size_t countu_smem_bytes() { return (size_t)kCuWords * sizeof(uint32_t); }
 
-// Is the sample one for this kernel?  Reads of (about) one length, short enough for a unit of at least 16 reads, none
-// longer than the break length.  Evaluated on the device by both count kernels (exactly one of them runs): what it needs
-// -- the shortest and the longest counted read -- is known when the scatter kernel is done.
-__device__ __forceinline__ bool countu_wanted(const Plan* __restrict__ plan, int breaklen, uint32_t policy)
-{
-    if (policy != 2u) return policy == 1u;       // 0: never, 1: always (tests), 2: by the sample
-    const uint32_t lo = plan->len_min, hi = plan->len_max;
-    return hi != 0u && hi - lo <= 16u && hi <= 352u && (breaklen <= 0 || hi <= (uint32_t)breaklen);
-}
-
 // 16 validity bits of a classified text word (bit b: byte b is one of ACGTacgt)
 __device__ __forceinline__ uint32_t valid16(const Cls4z& c0, const Cls4z& c1, const Cls4z& c2, const Cls4z& c3)
 {

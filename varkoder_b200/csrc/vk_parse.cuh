@@ -483,6 +483,7 @@ plan_kernel(const StepArgs* __restrict__ sa, uint64_t* __restrict__ starts, uint
         plan->read_index_base = index_base;
         plan->total_reads = reads_all;
         plan->count_overflow = 0;
+        plan->lanes_verdict = 0;
 
         // ---- ladder, image.py:669-695 in integers
         const uint64_t nsites = nsites_all;
