@@ -591,6 +591,8 @@ def c5_leg(args, world, rank, local, torch, dist, total_bases=None, steps=8):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.cpu()[0])
+    fallbacks = eng.count_fallbacks()
+    split = eng.timings()
     if world > 1:
         eng.comm_destroy()
     eng.close()
@@ -600,6 +602,7 @@ def c5_leg(args, world, rank, local, torch, dist, total_bases=None, steps=8):
         return None
     return {"value": total_bases / (ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": ms, "steps": steps, "n_gpus": world,
             "bases": total_bases, "levels": len(rs.levels), "level_bases": rs.level_bases,
+            "count_fallbacks": fallbacks, "last_step_timings": split,
             "workload": f"configs[4]: ONE sample of {total_bases} bases (read length 150), k=7, cgr, -M 0 ({len(rs.levels)} levels), "
                         f"read-sharded over {world} GPU(s): {shard_bases} bases ({nbytes / 1e9:.1f} GB of text) resident per GPU"
                         + ("; exchange = ncclAllGather(2 x u64) + ONE ncclAllReduce(u64 x %d), issued by the library on its own "

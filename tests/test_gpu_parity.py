@@ -1009,6 +1009,27 @@ def test_step_variants_bit_exact(monkeypatch, packed, graph, chunks, pairs, lane
         eng.close()
 
 
+def test_countt_epochs_flush_the_table(monkeypatch):
+    """countt_kernel sends its 16-bit table to the slab every kTEpochUnits units of a CTA (large samples: a 15 Gbp shard
+    would wrap a word); with epochs of 16 units a 300 000-read sample crosses dozens of boundaries per CTA, warps that run
+    out of units attend the remaining ones: bit-exact against the oracle, no fallback to the exact kernel."""
+    from varkoder_b200.engine import Engine
+    monkeypatch.setenv("VK_COUNT_LANES", "2")
+    monkeypatch.setenv("VK_COUNTT_KNOBS", "0x100")
+    eng = Engine(0)
+    try:
+        table = get_kmer_mapping(7, "cgr")
+        for i, buf in enumerate((synth.fixed(300_000, 150, seed=192).tobytes(), synth.variable(40_000, seed=193).tobytes(),
+                                 synth.fixed(20_000, 151, seed=194).tobytes())):
+            res = eng.reads_to_images(buf, Params(k=7, min_bp=3_000, max_bp=None, seed=60 + i), table, want_canon=True, max_levels=14)
+            expect = oracle_levels(buf, 7, 60 + i, res.levels, res.nsites)
+            assert len(res.levels) >= 3 and (res.canon == expect).all(), i
+            assert (res.pixels == oracle_images(expect, table.lut)).all(), i
+        assert eng.count_fallbacks() == 0
+    finally:
+        eng.close()
+
+
 def test_device_variable_generator_equals_host_generator(engine):
     import torch
     n_reads = 5000

@@ -119,6 +119,11 @@ struct vk_ctx {
     int lanes_mode = -1;            // VK_COUNT_LANES=2 / 3: the same with cp.async staging (countt_kernel, 16 / 12 warps)
     bool use_fast = true;           // VK_COUNT_FAST=0: 16-bit bins always through returning adds + drains (exact in one go)
     bool count_safe = false;        // set for the repeat of a step whose fire-and-forget count reported a wrapped bin
+    // Texts of this size and more go to the exact kernels at once: the smallest text whose 16-bit bins wrapped in this
+    // context (a 15 Gbp shard puts 50 M pairs into the 2^15 words of a CTA; a 7-mer at ten times the mean wraps one), less
+    // a quarter.  Without it every step of such a sample would run the wrapped count first (36 against 19.5 ms at 15 Gbp).
+    uint64_t safe_from_bytes = ~0ull;
+    bool count_is_safe() const { return count_safe || n_bytes >= safe_from_bytes; }
     uint64_t count_fallbacks = 0;
     uint64_t lanes_flips = 0;       // steps repeated because countt_kernel refused the sample
     bool use_pdl = true;            // VK_PDL=0 disables programmatic dependent launch
@@ -353,10 +358,9 @@ void prepare_count_kernels()
         if constexpr (K == 7) {
             CU(cudaFuncSetAttribute(countp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((32768 + 16384) * sizeof(uint32_t))));
             CU(cudaFuncSetAttribute(countu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countu_smem_bytes()));
-            CU(cudaFuncSetAttribute((countt_kernel<16, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<16>()));
-            CU(cudaFuncSetAttribute((countt_kernel<16, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<16>()));
-            CU(cudaFuncSetAttribute((countt_kernel<16, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<16>()));
-            CU(cudaFuncSetAttribute((countt_kernel<16, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<16>()));
+            CU(cudaFuncSetAttribute((countt_kernel<16, 0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<16>()));
+            CU(cudaFuncSetAttribute((countt_kernel<16, 0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<16>()));
+            CU(cudaFuncSetAttribute((countt_kernel<16, 1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt_smem_bytes<16>()));
         }
     }
     if constexpr (K == 7 || K == 8) {
@@ -387,6 +391,20 @@ void prepare_kernels()
 }
 
 // ---- K1b + K2 + K3 -----------------------------------------------------------------------------------
+// countt_kernel in its two forms: a text below kEpochBytes cannot fill a 16-bit word of a CTA's table (148 CTAs share it: 27
+// MB of text, 6.5 M pairs per CTA at most if ONE segment held every read and the plan gave it every CTA; a word wraps at
+// 2^15 hits, i.e. a pair at 0.5 % of all pairs -- what the overflow check is for), so its kernel carries no epoch code (the
+// same loop with the flushes compiled in measured 108.5 against 106.1 us); larger texts flush every kTEpochUnits units.
+constexpr uint64_t kEpochBytes = 4ull << 30;
+void launch_countt(vk_ctx* c, dim3 grid, const vk::StepArgs* sa, const uint64_t* srt, uint32_t pol)
+{
+    using namespace vk;
+    if (c->n_bytes < kEpochBytes && (pol >> 16) == 0u)
+        launch(c, (countt_kernel<16, 0, false>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, pol);
+    else
+        launch(c, (countt_kernel<16, 0, true>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, pol);
+}
+
 template <int K, bool PACKED>
 void launch_count(vk_ctx* c, unsigned long long* seg_hist)
 {
@@ -398,13 +416,11 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
     const PackedSrc pk = {reinterpret_cast<const uint2*>(c->codes.p), reinterpret_cast<const uint32_t*>(c->valid.p)};
     if constexpr (K == 7) {
         // k = 7, one read per lane, pairs (vk_countu.cuh); a wrapped bin repeats the count with the u32 kernel
-        if (c->use_lanes && !PACKED && !c->chunk_mode(7) && c->use_fast && !c->count_safe) {
+        if (c->use_lanes && !PACKED && !c->chunk_mode(7) && c->use_fast && !c->count_is_safe()) {
             const uint32_t pol = 1u | ((c->countt_knobs & ~1u) << 8);
             const uint64_t* srt = (const uint64_t*)c->sorted.p;
-            if (c->lanes_mode == 2) launch(c, (countt_kernel<16, 0>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, pol);
-            else if (c->lanes_mode == 3) launch(c, (countt_kernel<16, 1>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, pol);
-            else if (c->lanes_mode == 4) launch(c, (countt_kernel<16, 2>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, pol);
-            else if (c->lanes_mode == 5) launch(c, (countt_kernel<16, 3>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, pol);
+            if (c->lanes_mode == 2) launch_countt(c, grid, sa, srt, pol);
+            else if (c->lanes_mode == 3) launch(c, (countt_kernel<16, 1, true>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, pol);
             else
                 launch(c, countu_kernel, grid, block, countu_smem_bytes(), sa, (const uint64_t*)c->sorted.p, c->plan_d, c->slabs.p, 1u);
             c->mark(EV_COUNT);
@@ -412,7 +428,7 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
             return;
         }
         // k = 7 in read-aligned pairs from the chunk table (countp_kernel); a wrapped bin repeats the count with the u32 kernel
-        if (c->use_pairs && c->chunk_mode(7) && c->use_fast && !c->count_safe) {
+        if (c->use_pairs && c->chunk_mode(7) && c->use_fast && !c->count_is_safe()) {
             const size_t smem = (size_t)(32768 + 16384) * sizeof(uint32_t);
             launch(c, countp_kernel, grid, block, smem, sa, (const uint64_t*)c->chunks.p, c->plan_d, c->slabs.p);
             c->mark(EV_COUNT);
@@ -423,7 +439,7 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
     if constexpr (K == 7 || K == 8) {
         // 16-bit bins in shared memory: k = 8 directly, k = 7 through pairs (vk_count.cuh).  The fire-and-forget form by
         // default; after it reported a wrapped bin (count_safe) the exact form -- for k = 7 that is the u32 kernel below.
-        const bool fast = c->use_fast && !c->count_safe;
+        const bool fast = c->use_fast && !c->count_is_safe();
         if (K == 8 ? c->use_count16 : (c->use_pairs && !c->chunk_mode(7) && (fast || !c->use_fast))) {
             const size_t smem = (size_t)(32768 + (K == 7 ? 16384 : 0)) * sizeof(uint32_t);
             if (fast) launch(c, (count16_kernel<K, PACKED, true>), grid, block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p);
@@ -459,13 +475,13 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
             // VK_COUNT_LANES=0: always this kernel.
             uint32_t lanes_policy = 0;
             if constexpr (K == 7 && !PACKED) {
-                if (c->lanes_mode < 0 && c->use_fast && !c->count_safe && !c->use_pairs) {
+                if (c->lanes_mode < 0 && c->use_fast && !c->count_is_safe() && !c->use_pairs) {
                     const uint64_t* srt = (const uint64_t*)c->sorted.p;
                     if (c->in_sharded) {
                         lanes_policy = 2u;
-                        launch(c, (countt_kernel<16, 0>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, 2u | ((c->countt_knobs & ~1u) << 8));
+                        launch_countt(c, grid, sa, srt, 2u | ((c->countt_knobs & ~1u) << 8));
                     } else if (c->k7_lanes) {
-                        launch(c, (countt_kernel<16, 0>), grid, dim3(512), countt_smem_bytes<16>(), sa, srt, c->plan_d, c->slabs.p, 2u | ((c->countt_knobs | 1u) << 8));
+                        launch_countt(c, grid, sa, srt, 2u | ((c->countt_knobs | 1u) << 8));
                         c->mark(EV_COUNT);
                         launch(c, reduce_slabs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, NK, seg_hist, c->zero_unused_rows ? 1 : 0);
                         return;
@@ -766,6 +782,7 @@ void with_table_retry(vk_ctx* c, F&& body)
         } else if (c_over) {
             // a 16-bit bin of the fire-and-forget count kernel wrapped (a flood of one k-mer): count again, exactly
             c->count_safe = true;
+            if (c->n_bytes - c->n_bytes / 4 < c->safe_from_bytes) c->safe_from_bytes = c->n_bytes - c->n_bytes / 4;
             ++c->count_fallbacks;
         } else if (t_over) ensure_tables_for(c, c->plan_h->n_reads + 16);          // exact size is known now
         else if (k_small) c->generation += c->chunks.ensure((size_t)c->plan_h->chunks_needed + 256);
@@ -814,7 +831,7 @@ vk_ctx::StepGraph* step_graph(vk_ctx* c, const Mapping& m, int slot, int k, int 
     if (!c->use_graph || c->graph_failed || c->fine_timing) return nullptr;
     for (auto& g : c->graphs)
         if (g.k == k && g.slot == slot && g.side == m.side && g.max_levels == max_levels_out && g.exact == (int)c->exact_layout &&
-            g.packed == ((int)c->use_packed | (c->count_safe ? 2 : 0) | (c->k7_lanes ? 4 : 0)) && g.generation == c->generation)
+            g.packed == ((int)c->use_packed | (c->count_is_safe() ? 2 : 0) | (c->k7_lanes ? 4 : 0) | (c->n_bytes >= kEpochBytes ? 8 : 0)) && g.generation == c->generation)
             return &g;
     // stale graphs (a buffer moved) are of no use any more
     for (size_t i = 0; i < c->graphs.size();) {
@@ -846,7 +863,7 @@ vk_ctx::StepGraph* step_graph(vk_ctx* c, const Mapping& m, int slot, int k, int 
         return nullptr;
     }
     ++c->graph_captures;
-    c->graphs.push_back({k, slot, m.side, max_levels_out, (int)c->exact_layout, (int)c->use_packed | (c->count_safe ? 2 : 0) | (c->k7_lanes ? 4 : 0), c->generation, exec,
+    c->graphs.push_back({k, slot, m.side, max_levels_out, (int)c->exact_layout, (int)c->use_packed | (c->count_is_safe() ? 2 : 0) | (c->k7_lanes ? 4 : 0) | (c->n_bytes >= kEpochBytes ? 8 : 0), c->generation, exec,
                          c->captured_kernels});
     return &c->graphs.back();
 }

@@ -25,6 +25,7 @@ namespace vk {
 
 constexpr uint32_t kTQuads = 352;                       // 16-byte text words a warp stages per unit
 constexpr uint32_t kTBufWords = (kTQuads + 2u) * 4u;    // + one quad of slack on either side (read, never used)
+constexpr uint32_t kTEpochUnits = 1536;                 // units of a CTA between two flushes of its table (3.5 M pairs: a word holds 2^15)
 constexpr uint32_t kTQueue = 64;                        // irregular words a warp can hold (drained 32 at a time)
 constexpr uint32_t kTRoundsF = 8, kTRoundsS = 6;        // copy rounds of the first / second half of a unit (at most 256 / 192 pieces)
 constexpr uint32_t kNoPiece = 0x80000000u | (kTQuads << 22);      // a copy round in which the lane has no word to move: 16 zero bytes to the slack quad behind the buffer
@@ -77,7 +78,7 @@ __device__ __forceinline__ uint32_t gather8t(uint32_t za, uint32_t zb, uint32_t 
     return mad_lo_op(zb, 0x00204081u, shr_fma<FMA, 4>(za, m28, zero) * 0x00204081u);
 }
 
-template <int NW, int FM>
+template <int NW, int FM, bool EPOCHS>
 __global__ void __launch_bounds__(NW * 32, 1)
 countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sorted, Plan* __restrict__ plan,
               uint32_t* __restrict__ slabs, uint32_t policy)
@@ -89,7 +90,7 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
     constexpr bool FMA_CLS = (FM & 1) != 0, FMA_PAIR = (FM & 2) != 0;      // which shifts are multiplies (measured: none is fastest)
     const uint8_t* __restrict__ text = sa->text;
     const int breaklen = sa->pa.p.breaklength;
-    const uint32_t knobs = policy >> 8;          // bit 0: this kernel is the only one launched (a refusal must be reported); bits 4..7: H (experiments, VK_COUNTT_KNOBS)
+    const uint32_t knobs = policy >> 8;          // bit 0: this kernel is the only one launched (a refusal must be reported); bits 4..7: H, bits 8..: units per epoch / 16 (experiments and tests, VK_COUNTT_KNOBS)
     policy &= 0xFFu;
     if (!countu_wanted(plan, breaklen, policy)) {
         if ((knobs & 1u) && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&plan->lanes_verdict, 2u);      // nobody else counts this step: say so
@@ -242,8 +243,37 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
     // Per unit: the second half of its text is asked for when the unit before it is done (the first half arrived while
     // that unit's last words were counted), waited for when the count reaches word H - 3, and the first half of the NEXT
     // unit is asked for after word H - 2, when no lane needs a word below H any more.
+    // The table goes to the slab (7-mer x: 8-mers that start with it, x | c << 14, + 8-mers that end with it, (x << 2 | c) &
+    // 0xFFFF; x and x | 0x2000 end the same four words (x & 0x1FFF) << 2 | c: one 16-byte load serves both -- and, summed over x,
+    // is the checksum: every increment added 1 to the low half of its word, so the low halves must sum to the increments made)
+    // at the end of the CTA and, in the form for large texts (EPOCHS), after every kTEpochUnits units: 16-bit bins hold a CTA's
+    // share of a 200 Mbp sample many times over, but a 15 Gbp shard puts 50 M pairs into the 2^15 words and a 7-mer at ten
+    // times the mean wraps one (measured: every step of BASELINE configs[4] on two GPUs fell back to the exact kernel).
+    auto flush_table = [&]() {
+        uint32_t big = 0;
+        unsigned long long low = 0;
+        for (uint32_t x = tid; x < NK / 2u; x += nthr) {
+            const uint4 q = reinterpret_cast<const uint4*>(h8)[x];
+            const uint32_t up = (q.x >> 17) + (q.y >> 17) + (q.z >> 17) + (q.w >> 17);
+            const uint32_t all = (q.x & 0xFFFFu) + (q.y & 0xFFFFu) + (q.z & 0xFFFFu) + (q.w & 0xFFFFu);
+            big |= q.x | q.y | q.z | q.w;
+            low += all;
+            const uint32_t x1 = x | 0x2000u;
+            red_global_add(slab + x, (h8[x] & 0xFFFFu) + (h8[x | 0x4000u] & 0xFFFFu) + (all - up));
+            red_global_add(slab + x1, (h8[x1] & 0xFFFFu) + (h8[x1 | 0x4000u] & 0xFFFFu) + up);
+        }
+#pragma unroll
+        for (int dlt = 16; dlt > 0; dlt >>= 1) low += __shfl_xor_sync(FULL, low, dlt);
+        if (lane == 0) atomicAdd(&s_chk[1], low);
+        // a word whose total reached 2^15 may have wrapped its high half (twice the upper bin): exact recount
+        if (big & 0x8000u) atomicOr(&plan->count_overflow, 1u);
+    };
+    const uint32_t epoch_reads = ((knobs >> 8) ? (knobs >> 8) * 16u : kTEpochUnits) * R;      // (tests: short epochs)
     issue_half(entA, rwF);
-    while (baseA < cta_hi) {
+    // epochs: every warp leaves the unit loop when the unit it holds lies beyond the epoch's end (a warp that has run out of
+    // units leaves at once), the queue is applied, the table goes to the slab and is cleared, the next epoch begins
+    for (uint32_t epoch_end = (EPOCHS && cta_hi - cta_lo > epoch_reads) ? cta_lo + epoch_reads : cta_hi;;) {
+    while (baseA < epoch_end) {
         // ---- the claim made a unit ago has its answer; the entries of that unit are asked for now (used four units on)
         const uint32_t baseD = clamp_hi(__shfl_sync(FULL, pending, 0));
         const uint64_t entD = entry_at(baseD);
@@ -383,35 +413,25 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
         entA = entB; entB = entC; entC = entD;
         baseA = baseB; baseB = baseC; baseC = baseD;
     }
+        if (!EPOCHS || epoch_end >= cta_hi) break;
+        if (qn != 0u) { drain(0u, qn); qn = 0u; }
+        __syncthreads();
+        flush_table();
+        __syncthreads();
+        for (uint32_t i = tid; i < 8192u; i += nthr) reinterpret_cast<uint4*>(s_raw)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        epoch_end = cta_hi - epoch_end < epoch_reads ? cta_hi : epoch_end + epoch_reads;
+    }
     cp_async_wait<0>();
     if (qn != 0u) drain(0u, qn);
     __threadfence();                                                    // the singles' atomics have reached the slab
     __syncthreads();
-    // 7-mer x: 8-mers that start with it (x | c << 14) + 8-mers that end with it ((x << 2 | c) & 0xFFFF).  x and
-    // x | 0x2000 end the same four words ((x & 0x1FFF) << 2 | c): one 16-byte load serves both -- and, summed over x, is
-    // the checksum: every increment added 1 to the low half of its word, so the low halves must sum to the increments made.
-    uint32_t big = 0;
-    unsigned long long low = 0;
-    for (uint32_t x = tid; x < NK / 2u; x += nthr) {
-        const uint4 q = reinterpret_cast<const uint4*>(h8)[x];
-        const uint32_t up = (q.x >> 17) + (q.y >> 17) + (q.z >> 17) + (q.w >> 17);
-        const uint32_t all = (q.x & 0xFFFFu) + (q.y & 0xFFFFu) + (q.z & 0xFFFFu) + (q.w & 0xFFFFu);
-        big |= q.x | q.y | q.z | q.w;
-        low += all;
-        const uint32_t x1 = x | 0x2000u;
-        red_global_add(slab + x, (h8[x] & 0xFFFFu) + (h8[x | 0x4000u] & 0xFFFFu) + (all - up));
-        red_global_add(slab + x1, (h8[x1] & 0xFFFFu) + (h8[x1 | 0x4000u] & 0xFFFFu) + up);
-    }
+    flush_table();
     {
         unsigned long long mine = (unsigned long long)(long long)(int32_t)made;      // (a lane drains other lanes' words: its own balance may be negative)
 #pragma unroll
-        for (int dlt = 16; dlt > 0; dlt >>= 1) {
-            low += __shfl_xor_sync(FULL, low, dlt);
-            mine += __shfl_xor_sync(FULL, mine, dlt);
-        }
-        if (lane == 0) { atomicAdd(&s_chk[0], mine); atomicAdd(&s_chk[1], low); }
-        // a word whose total reached 2^15 may have wrapped its high half (twice the upper bin): exact recount
-        if (big & 0x8000u) atomicOr(&plan->count_overflow, 1u);
+        for (int dlt = 16; dlt > 0; dlt >>= 1) mine += __shfl_xor_sync(FULL, mine, dlt);
+        if (lane == 0) atomicAdd(&s_chk[0], mine);
         __syncthreads();
         if (tid == 0 && s_chk[0] != s_chk[1]) atomicOr(&plan->count_overflow, 1u);
     }
