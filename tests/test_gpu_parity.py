@@ -491,7 +491,9 @@ def test_low_complexity_flood_16bit_bins(monkeypatch, k):
 def test_fire_and_forget_bins_fall_back_when_they_wrap(monkeypatch, k):
     """enough copies of one k-mer that a 16-bit bin wraps inside a single CTA (> 65 535 of its increments in one word):
     the fire-and-forget kernel notices at its end (the low halves no longer sum to the increments it made), the count
-    is repeated with the exact kernel, and the result is bit-exact -- staged and fused (graph) paths alike."""
+    is repeated with the exact kernel, and the result is bit-exact -- staged and fused (graph) paths alike.  The context
+    remembers the text size: the same sample again goes to the exact kernel at once (no second wasted count), a small one
+    still takes the fast kernel."""
     from varkoder_b200.engine import Engine
     monkeypatch.setenv("VK_COUNT_PAIRS", "1")
     engine = Engine(0)
@@ -512,7 +514,7 @@ def test_fire_and_forget_bins_fall_back_when_they_wrap(monkeypatch, k):
     expect = dsk.canonical_counts(buf, k, threads=0)
     assert (canon[0] == expect).all() and (r2.canon[0] == expect).all()
     assert (r3.canon[0] == dsk.canonical_counts(small, k)).all()
-    assert f1 >= 1 and f2 >= f1 + 1 and f3 == f2
+    assert f1 >= 1 and f2 == f1 and f3 == f2
 
 
 @pytest.mark.parametrize("k", [7, 8])

@@ -8,11 +8,11 @@ mkdir -p gpurun_out
 $CMD > gpurun_out/plain_${TAG}.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launches_${TAG}.log 2>&1
 echo "launch list rc=$?"
-# one step = 12 launches (begin, mask, scan, emit, plan, hist, calibrate, scatter, count, reduce, fold, image); skip the generator + warm-up steps
+# one step = 13 launches (begin, mask, scan, emit, plan, hist, calibrate, scatter, long_reads, count, reduce, fold, image); skip the generator + warm-up steps
 $CMD > gpurun_out/plain2_${TAG}.log 2>&1 && \
 ncu --set full --clock-control none --import-source on \
-    -k regex:"count_kernel|image_kernel|parse_emit|parse_mask|bucket_scatter|fold_kernel|reduce_slabs|plan_kernel|parse_scan|step_begin|prio_hist|thr_calibrate" \
-    -s 48 -c 12 -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
+    -k regex:"countt_kernel|count_kernel|image_kernel|long_reads|parse_emit|parse_mask|bucket_scatter|fold_kernel|reduce_slabs|plan_kernel|parse_scan|step_begin|prio_hist|thr_calibrate" \
+    -s 52 -c 13 -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "full rc=$?"
 tail -2 gpurun_out/ncu_full_${TAG}.log
 ls -la gpurun_out/prof_${TAG}.ncu-rep

@@ -122,7 +122,9 @@ struct vk_ctx {
     // Texts of this size and more go to the exact kernels at once: the smallest text whose 16-bit bins wrapped in this
     // context (a 15 Gbp shard puts 50 M pairs into the 2^15 words of a CTA; a 7-mer at ten times the mean wraps one), less
     // a quarter.  Without it every step of such a sample would run the wrapped count first (36 against 19.5 ms at 15 Gbp).
+    // The rule is forgotten after 32 steps it sent to the exact kernels (the samples may have changed).
     uint64_t safe_from_bytes = ~0ull;
+    uint32_t safe_by_size_steps = 0;
     bool count_is_safe() const { return count_safe || n_bytes >= safe_from_bytes; }
     uint64_t count_fallbacks = 0;
     uint64_t lanes_flips = 0;       // steps repeated because countt_kernel refused the sample
@@ -771,6 +773,10 @@ void with_table_retry(vk_ctx* c, F&& body)
         const bool l_ref = (c->plan_h->lanes_verdict & 2u) != 0 && !t_over && !b_over && !k_small && !c_over;
         if (!t_over && !b_over && !c_over && !k_small && !l_ref) {
             if (c->plan_h->lanes_verdict & 1u) c->k7_lanes = true;       // (the flat-lane kernel counted a sample of one read length)
+            if (!c->count_safe && c->n_bytes >= c->safe_from_bytes && ++c->safe_by_size_steps >= 32u) {
+                c->safe_from_bytes = ~0ull;                              // (try the 16-bit bins again)
+                c->safe_by_size_steps = 0;
+            }
             c->exact_layout = false;
             c->count_safe = false;
             return;
