@@ -4,20 +4,30 @@
 // as count_kernel / count16_kernel / countu_kernel do (vk_count.cuh: rules D1-D8, forward-strand histogram per ladder
 // segment, fold later); bins, increments, checksum and flush are countu_kernel's, the slab it writes is interchangeable.
 //
-// What is different from countu_kernel (vk_countu.cuh, 188 us per 200 Mbp):
-//  * STAGING costs no classification, no register traffic and no index arithmetic: the 16-byte text words of a unit of
-//    reads go from global to shared memory with cp.async (LDGSTS, the data never passes through registers), in the same
-//    read-major piece order (consecutive lanes copy consecutive words of one read: three reads per request).  Which word
-//    of which read a lane copies in round n is fixed for the whole kernel (the stride is the sample's), so a round is
-//    two shuffles (the read's address), an add and the copy.
+// 106.6 us per 200 Mbp = 0.605 of the measured HBM roofline (the flat-lane kernel: 139 us, countu_kernel: 188 us); what was
+// measured on the way is in profiles/r02c_notes.md, the design in DESIGN.md "K2".
+//
+// What is different from countu_kernel (vk_countu.cuh):
+//  * STAGING costs no classification, no register traffic and little arithmetic: the 16-byte text words of a unit of 32
+//    reads go from global to shared memory with cp.async (LDGSTS, the data never passes through registers), in read-major
+//    order (consecutive lanes copy consecutive words of one read: about three reads per request).  Which word of which
+//    read a lane copies in round n is fixed for the whole kernel (the stride is the sample's), so a round is two shuffles
+//    (the read's address), an add and the copy.  The buffer of a warp is refilled in two HALVES (words [0, H) and [H, S) of
+//    every read), each while the other is being counted: one buffer per warp, 16 warps per SM.  No L2 prefetch (it made
+//    every line travel twice and held the kernel at the flat-lane kernel's time).
 //  * The lane that owns a read classifies ITS words when it counts them (one LDS.128 per 16 bases): the SIMD
 //    classification of vk_count.cuh, once per text word, nothing stored back.
 //  * Words are aligned to the read's 7-MERS, not to its bases: word v holds the sixteen 7-mers that END at bases
 //    16v + 6 .. 16v + 21 (window = bases 16v .. 16v + 21).  A read of 150 bases is then nine words of eight pairs and
-//    nothing else: no first word without its six leading ends, no short last word.  Words that reach beyond the
-//    shortest read of the unit (other lengths; the odd 7-mer of a 151-base read) take the queue, as do words with an N.
+//    nothing else: no first word without its six leading ends, no short last word.
+//  * COUNT FIRST, LOOK AFTERWARDS: every lane adds the eight pairs of a word unconditionally (the increment is one LOP3);
+//    a word with an N is queued with a flag and the drain takes the pairs that should not have counted back (shared-memory
+//    arithmetic is modular).  Words that reach beyond the shortest read of the unit (other lengths; the odd 7-mer of a
+//    151-base read; reads with cut points) are not pre-counted and take the queue with their exact masks.
 //  * The queue entry is two words (window low | window high + the 16 "a 7-mer ends here" bits), filled under one
 //    ballot; drained 32 at a time by countu's rule (complete pairs to the 8-mer bins, widowed 7-mers to the slab).
+//  * Units are claimed from a counter in SHARED memory (the CTAs of a segment take equal contiguous shares).
+//  * Large texts (the EPOCHS form): the 16-bit table goes to the slab every kTEpochUnits units of a CTA.
 #pragma once
 #include "vk_countu.cuh"
 
@@ -241,8 +251,9 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
     };
 
     // Per unit: the second half of its text is asked for when the unit before it is done (the first half arrived while
-    // that unit's last words were counted), waited for when the count reaches word H - 3, and the first half of the NEXT
-    // unit is asked for after word H - 2, when no lane needs a word below H any more.
+    // that unit's last words were counted), waited for when the words in flight reach into it (v + 5 >= H: a lane reads two
+    // quads ahead of the two words of an iteration), and from then on no lane reads below H any more: the first half of
+    // the NEXT unit is asked for after that iteration.
     // The table goes to the slab (7-mer x: 8-mers that start with it, x | c << 14, + 8-mers that end with it, (x << 2 | c) &
     // 0xFFFF; x and x | 0x2000 end the same four words (x & 0x1FFF) << 2 | c: one 16-byte load serves both -- and, summed over x,
     // is the checksum: every increment added 1 to the low half of its word, so the low halves must sum to the increments made)
@@ -274,7 +285,7 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
     // units leaves at once), the queue is applied, the table goes to the slab and is cleared, the next epoch begins
     for (uint32_t epoch_end = (EPOCHS && cta_hi - cta_lo > epoch_reads) ? cta_lo + epoch_reads : cta_hi;;) {
     while (baseA < epoch_end) {
-        // ---- the claim made a unit ago has its answer; the entries of that unit are asked for now (used four units on)
+        // ---- the claim made a unit ago has its answer; the entries of that unit are asked for now (used three units on)
         const uint32_t baseD = clamp_hi(__shfl_sync(FULL, pending, 0));
         const uint64_t entD = entry_at(baseD);
         if (lane == 0 && baseD < cta_hi) pending = atomicAdd(&s_next, R);
