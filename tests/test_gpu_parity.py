@@ -736,7 +736,7 @@ def test_full_size_properties_config3(engine):
         assert (res.pixels[lvl] == oimg.image_exact(expect[lvl], table.lut)).all()
 
 
-def test_text_beyond_4_gib(engine):
+def test_text_beyond_4_gib(engine, monkeypatch):
     """One buffer of 4.65 GB (2.2 Gbp): byte offsets pass 2^32 inside the framing, the read table and the count
     kernel's chunk addresses.  The whole sample equals the sum of three read shards that each stay below 4 GiB, the
     TAIL of the buffer (where the offsets are largest) equals the CPU oracle, and the quality-flag kernel reads past
@@ -787,6 +787,18 @@ def test_text_beyond_4_gib(engine):
     tail = dev[tail_off:total].cpu().numpy().tobytes()
     r_tail = engine.reads_to_images(tail, Params(k=k, min_bp=0, max_bp=None, is_query=True), table, want_canon=True)
     assert (r_tail.canon[0] == dsk.canonical_counts(tail, k, threads=0)).all()
+    # both k = 7 count kernels on the whole buffer, each in a context of its own: the flat-lane kernel and countt_kernel in its
+    # form for texts of 4 GiB and more (table flushed in epochs; read addresses beyond 2^32 in the cp.async staging)
+    from varkoder_b200.engine import Engine
+    for lanes in ("0", "2"):
+        monkeypatch.setenv("VK_COUNT_LANES", lanes)
+        e2 = Engine(0)
+        try:
+            r2 = e2.reads_to_images(dev.data_ptr(), params, table, on_device=True, n_bytes=total, want_canon=True)
+            assert (r2.canon == res.canon).all() and (r2.pixels == res.pixels).all(), lanes
+            assert e2.count_fallbacks() == 0
+        finally:
+            e2.close()
     del dev
 
 

@@ -116,7 +116,8 @@ struct vk_ctx {
     bool k7_lanes = false;          // k = 7, automatic choice: the context's last sample was one for countt_kernel (reads of one length)
     bool in_sharded = false;        // inside vk_sharded_reads_to_images: the ranks repeat steps together, the choice is made on the device
     unsigned countt_knobs = 0;      // VK_COUNTT_KNOBS: experiments of countt_kernel (vk_countt.cuh)
-    int lanes_mode = -1;            // VK_COUNT_LANES=2 / 3: the same with cp.async staging (countt_kernel, 16 / 12 warps)
+    int lanes_mode = -1;            // VK_COUNT_LANES: -1 (default) countt_kernel or the flat-lane kernel, by the sample; 0 the flat-lane kernel;
+                                    // 1 countu_kernel; 2 countt_kernel for every sample; 3 countt_kernel with IMAD.HI shifts in the classification (experiment)
     bool use_fast = true;           // VK_COUNT_FAST=0: 16-bit bins always through returning adds + drains (exact in one go)
     bool count_safe = false;        // set for the repeat of a step whose fire-and-forget count reported a wrapped bin
     // Texts of this size and more go to the exact kernels at once: the smallest text whose 16-bit bins wrapped in this
@@ -393,10 +394,10 @@ void prepare_kernels()
 }
 
 // ---- K1b + K2 + K3 -----------------------------------------------------------------------------------
-// countt_kernel in its two forms: a text below kEpochBytes cannot fill a 16-bit word of a CTA's table (148 CTAs share it: 27
-// MB of text, 6.5 M pairs per CTA at most if ONE segment held every read and the plan gave it every CTA; a word wraps at
-// 2^15 hits, i.e. a pair at 0.5 % of all pairs -- what the overflow check is for), so its kernel carries no epoch code (the
-// same loop with the flushes compiled in measured 108.5 against 106.1 us); larger texts flush every kTEpochUnits units.
+// countt_kernel in its two forms.  The CTAs share a text in proportion to the segments' sizes: below kEpochBytes a CTA sees
+// at most 29 MB of text = 6.5 M pairs, and a 16-bit word of its table then wraps (2^15 hits) only when one pair of bins holds
+// 0.5 % of all pairs -- what the overflow check and the exact recount are for -- so the kernel for such texts carries no epoch
+// code (the same loop with the flushes compiled in measured 108.5 against 106.1 us); larger texts flush every kTEpochUnits units.
 constexpr uint64_t kEpochBytes = 4ull << 30;
 void launch_countt(vk_ctx* c, dim3 grid, const vk::StepArgs* sa, const uint64_t* srt, uint32_t pol)
 {
