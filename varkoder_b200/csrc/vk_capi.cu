@@ -898,7 +898,7 @@ int vk_ctx_create(int device, vk_ctx** out)
         c->n_sms = prop.multiProcessorCount;
         if (const char* e = getenv("VK_COUNT_THREADS")) c->count_threads = atoi(e);
         if (const char* e = getenv("VK_COUNT_CTAS")) c->count_ctas_per_sm = atoi(e);
-        if (const char* e = getenv("VK_COUNT_EXTRA")) c->count_extra = std::max(0, std::min(64, atoi(e)));
+        if (const char* e = getenv("VK_COUNT_EXTRA")) c->count_extra = std::max(-64, std::min(64, atoi(e)));      // (negative: SMs left to the other samples in flight)
         if (const char* e = getenv("VK_COUNT_EXTRA9")) c->count_extra9 = std::max(0, std::min(64, atoi(e)));
         if (const char* e = getenv("VK_COUNT_READS_PER_CTA")) c->reads_per_cta = std::max(0, atoi(e));
         c->reads_per_cta_env = c->reads_per_cta;
