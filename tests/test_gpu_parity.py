@@ -1040,6 +1040,10 @@ def test_countt_epochs_flush_the_table(monkeypatch):
             assert len(res.levels) >= 3 and (res.canon == expect).all(), i
             assert (res.pixels == oracle_images(expect, table.lut)).all(), i
         assert eng.count_fallbacks() == 0
+        # a read too long for a staging buffer (352 text words): the forced kernel hands the step to the exact flat-lane kernel
+        buf = fastq(["ACGTTGCA" * 800, "ACGT" * 30] * 3)
+        res = eng.reads_to_images(buf, Params(k=7, min_bp=0, max_bp=None, is_query=True), table, want_canon=True)
+        assert (res.canon[0] == dsk.canonical_counts(buf, 7)).all() and eng.count_fallbacks() == 1
     finally:
         eng.close()
 

@@ -146,7 +146,10 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
     const uint32_t cta_hi = seg_len - cta_lo < per_cta ? seg_len : cta_lo + per_cta;
     if (tid == 0) s_next = cta_lo;
     __syncthreads();
-    if (R == 0u) return;                          // (countu_wanted keeps such samples away; policy 1 with huge reads)
+    if (R == 0u) {                                // a read too long for a staging buffer (forced mode only: countu_wanted keeps such samples away)
+        if (tid == 0) atomicOr(&plan->count_overflow, 1u);      // -> the host repeats the step with the exact flat-lane kernel
+        return;
+    }
 
     // ---- units of R reads are claimed three units ahead of their use (the entries of a unit are needed when the unit
     // before it is half done: that is when its first copies are issued)
