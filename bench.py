@@ -900,7 +900,9 @@ def main():
         # returns at once (the choice is made on the device, vk_countt.cuh); VK_COUNT_LANES=0 keeps the flat-lane kernel
         lanes_env = os.environ.get("VK_COUNT_LANES", "-1")
         k7_name = "count_kernel<7,smem>" if lanes_env == "0" else ("countt_kernel<16>" if lanes_env in ("-1", "2") else f"count kernel VK_COUNT_LANES={lanes_env}")
-        kernel_name = (k7_name if K == 7 else f"count_kernel<{K},smem>") if K <= 7 else ("count9h_kernel" if K == 9 else f"count16_kernel<{K}>")
+        # k = 9, reads of one length: countt9_kernel (VK_COUNT_LANES9=0 keeps count9h_kernel)
+        k9_name = "count9h_kernel" if os.environ.get("VK_COUNT_LANES9", "-1") == "0" else "countt9_kernel"
+        kernel_name = (k7_name if K == 7 else f"count_kernel<{K},smem>") if K <= 7 else (k9_name if K == 9 else f"count16_kernel<{K}>")
         traffic = traffic_src = None
         try:
             with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:

@@ -1048,6 +1048,38 @@ def test_countt_epochs_flush_the_table(monkeypatch):
         eng.close()
 
 
+def test_countt9_kernel_bit_exact(monkeypatch):
+    """k = 9 with countt_kernel's front end (VK_COUNT_LANES9=1: one read per lane, cp.async staging, exact masks per word, the
+    pair-of-CTAs class tables of count9h_kernel): samples of one length, of mixed lengths, with N, cut points, a flood of one
+    9-mer (hot words are drained), a read too long for a staging buffer (the step goes to the flat-lane pair kernel), through
+    one context in both submission forms -- bit-exact against the oracle."""
+    from varkoder_b200.engine import Engine
+    monkeypatch.setenv("VK_COUNT_LANES9", "1")
+    rng = np.random.default_rng(909)
+    bufs = [synth.fixed(200_000, 150, seed=291).tobytes(), synth.variable(30_000, seed=292).tobytes(),
+            fastq(rand_reads(rng, 300, 0, 90, p_n=0.02) + ["acgtn" * 20, "ACGT" * 400, "G" * 700, ""]),
+            fastq(["A" * 150] * 60_000 + rand_reads(rng, 2000, 0, 200, p_n=0.01)), synth.fixed(20_000, 151, seed=293).tobytes(),
+            fastq(["ACGTTGCA" * 800, "ACGT" * 30] * 3), b""]
+    table = get_kmer_mapping(9, "varKode")
+    for graph in ("1", "0"):
+        monkeypatch.setenv("VK_GRAPH", graph)
+        eng = Engine(0)
+        try:
+            for i, buf in enumerate(bufs):
+                params = Params(k=9, min_bp=3_000, max_bp=None, seed=70 + i)
+                p = dsk.parse_fastq(buf)
+                if p["nsites_ref"] <= 3_000:
+                    params = Params(k=9, min_bp=0, max_bp=None, seed=70 + i, is_query=True)
+                res = eng.reads_to_images(buf, params, table, want_canon=True, max_levels=12)
+                expect = oracle_levels(buf, 9, 70 + i, res.levels, res.nsites)
+                assert (res.canon == expect).all(), (graph, i)
+                if len(res.levels):
+                    assert (res.pixels == oracle_images(expect, table.lut)).all(), (graph, i)
+            assert eng.count_fallbacks() == 1          # the 6400-base reads
+        finally:
+            eng.close()
+
+
 def test_device_variable_generator_equals_host_generator(engine):
     import torch
     n_reads = 5000

@@ -15,6 +15,7 @@
 #include "vk_count.cuh"
 #include "vk_countu.cuh"
 #include "vk_countt.cuh"
+#include "vk_countt9.cuh"
 #include "vk_image.cuh"
 #include "vk_parse.cuh"
 #include "vk_quality.cuh"
@@ -115,6 +116,13 @@ struct vk_ctx {
     bool use_lanes = false;         // VK_COUNT_LANES=1: k = 7 with one read per lane, pairs, uniform fast path (countu_kernel)
     bool k7_lanes = false;          // k = 7, automatic choice: the context's last sample was one for countt_kernel (reads of one length)
     bool in_sharded = false;        // inside vk_sharded_reads_to_images: the ranks repeat steps together, the choice is made on the device
+    int lanes9_mode = -1;           // VK_COUNT_LANES9: -1 (default) countt9_kernel or count9h_kernel, by the sample (the context's k7_lanes); 0 count9h_kernel; 1 countt9_kernel always
+    // k = 9 through countt9_kernel in this step?  (one CTA per SM: 74 pairs, no late pairs -- the plan's pair count follows)
+    bool use_countt9() const
+    {
+        if (!use_count16 || use_packed || !use_fast || count_is_safe()) return false;
+        return lanes9_mode > 0 || (lanes9_mode < 0 && k7_lanes && !in_sharded);
+    }
     unsigned countt_knobs = 0;      // VK_COUNTT_KNOBS: experiments of countt_kernel (vk_countt.cuh)
     int lanes_mode = -1;            // VK_COUNT_LANES: -1 (default) countt_kernel or the flat-lane kernel, by the sample; 0 the flat-lane kernel;
                                     // 1 countu_kernel; 2 countt_kernel for every sample; 3 countt_kernel with IMAD.HI shifts in the classification (experiment)
@@ -262,7 +270,7 @@ void enqueue_args(vk_ctx* c, const vk_params* params)
     a.pa.n_count_ctas = (uint32_t)c->count_grid();
     a.pa.reads_per_cta = (uint32_t)c->reads_per_cta;
     if (params && params->k == 9 && c->use_count16)                             // k = 9 counts in CTA pairs (count9h_kernel)
-        a.pa.n_count_ctas = (uint32_t)(c->n_sms * c->count_ctas_per_sm / 2 + c->count_extra9);
+        a.pa.n_count_ctas = (uint32_t)(c->n_sms * c->count_ctas_per_sm / 2 + (c->use_countt9() ? 0 : c->count_extra9));
     a.pa.exact_layout = c->exact_layout ? 1u : 0u;
     a.pa.test_tight = c->test_tight ? 1u : 0u;
     a.pa.shard_table = nullptr;
@@ -375,6 +383,7 @@ void prepare_count_kernels()
     }
     if constexpr (K == 9) {
         const int smem = (int)((size_t)32768 * sizeof(uint32_t) + 2048);
+        CU(cudaFuncSetAttribute(countt9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)countt9_smem_bytes()));
         CU(cudaFuncSetAttribute(count9h_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CU(cudaFuncSetAttribute(count9h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
@@ -455,9 +464,17 @@ void launch_count(vk_ctx* c, unsigned long long* seg_hist)
     if constexpr (K == 9) {
         if (c->use_count16) {
             // canonical classes in two halves, one per CTA of a pair (vk_count.cuh)
-            const unsigned pairs = (unsigned)(c->n_sms * c->count_ctas_per_sm / 2 + c->count_extra9);
+            const bool t9 = c->use_countt9();
+            const unsigned pairs = (unsigned)(c->n_sms * c->count_ctas_per_sm / 2 + (t9 ? 0 : c->count_extra9));
             const size_t smem = (size_t)32768 * sizeof(uint32_t) + 2048;      // + padding to a 2 KiB shared address
-            launch(c, (count9h_kernel<PACKED>), dim3(2 * pairs), block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p);
+            // countt9_kernel for samples of one read length, count9h_kernel for the others: the context goes by its last sample,
+            // as for k = 7 (count9h_kernel reports a sample that was one for countt9_kernel, countt9_kernel refuses one that is not)
+            if (t9)
+                launch(c, countt9_kernel, dim3(2 * pairs), dim3(512), countt9_smem_bytes(), sa, (const uint64_t*)c->sorted.p, c->plan_d, c->slabs.p,
+                       c->lanes9_mode > 0 ? 1u : 2u);
+            else
+                launch(c, (count9h_kernel<PACKED>), dim3(2 * pairs), block, smem, sa, pk, c->sorted.p, c->plan_d, c->slabs.p,
+                       (c->lanes9_mode < 0 && !c->in_sharded && c->use_fast && !c->count_is_safe()) ? 3u : 0u);
             c->mark(EV_COUNT);
             launch(c, reduce_slabs9h_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, c->slabs.p, c->plan_d, seg_hist);
             return;
@@ -907,6 +924,7 @@ int vk_ctx_create(int device, vk_ctx** out)
         if (const char* e = getenv("VK_COUNT16")) c->use_count16 = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT_PAIRS")) c->use_pairs = atoi(e) != 0;
         if (const char* e = getenv("VK_COUNT_LANES")) { c->lanes_mode = atoi(e); c->use_lanes = c->lanes_mode > 0; }
+        if (const char* e = getenv("VK_COUNT_LANES9")) c->lanes9_mode = atoi(e);
         if (const char* e = getenv("VK_COUNTT_KNOBS")) c->countt_knobs = (unsigned)strtoul(e, nullptr, 0);
         if (const char* e = getenv("VK_COUNT_FAST")) c->use_fast = atoi(e) != 0;
         if (const char* e = getenv("VK_PACKED")) c->use_packed = atoi(e) != 0;

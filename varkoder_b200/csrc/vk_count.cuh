@@ -1132,11 +1132,13 @@ __device__ __forceinline__ void drain9_steps(uint32_t Wl, uint32_t Wh, uint32_t 
 template <bool PACKED>
 __global__ void __launch_bounds__(kCountThreads)
 count9h_kernel(const StepArgs* __restrict__ sa, PackedSrc pk, const uint64_t* __restrict__ sorted, Plan* __restrict__ plan,
-               uint32_t* __restrict__ slabs)
+               uint32_t* __restrict__ slabs, uint32_t lanes_policy)
 {
     pdl_wait();
     const uint4* __restrict__ text16 = reinterpret_cast<const uint4*>(sa->text);
     const int breaklen = sa->pa.p.breaklength;
+    // lanes_policy 3: tell the host when the sample would have been one for countt9_kernel (vk_countt9.cuh)
+    if (lanes_policy == 3u && blockIdx.x == 0 && threadIdx.x == 0 && countu_wanted(plan, breaklen, 2u)) atomicOr(&plan->lanes_verdict, 1u);
     const uint32_t one = (uint32_t)(sa->n_bytes >> 62) + 1u;          // 1 (texts are shorter than 2^40), but not to ptxas
     constexpr int K = 9;
     constexpr uint32_t NB = 65536u;               // bins of one half
