@@ -192,6 +192,7 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
     auto issue_half = [&](uint64_t ent, const auto& rw) {
         constexpr uint32_t NR = sizeof(rw) / sizeof(rw[0]);
         const uint32_t len = (uint32_t)(ent & kEntryLenMask);
+        VK_ASSERT(!len || (ent >> kEntryLenBits) + len <= sa->n_bytes);            // a sorted-table entry names bytes of the text
         const uint8_t* const p0 = len ? text + ((ent >> kEntryLenBits) & ~15ull) : text_end;   // the read's first text word
         const uint32_t plo = (uint32_t)(uintptr_t)p0, phi = (uint32_t)((uintptr_t)p0 >> 32);
 #pragma unroll
@@ -200,6 +201,8 @@ countt_kernel(const StepArgs* __restrict__ sa, const uint64_t* __restrict__ sort
             const uint32_t blo = __shfl_sync(FULL, plo, (int)rw[n]), bhi = __shfl_sync(FULL, phi, (int)rw[n]);      // (the shuffle looks at the low five bits: r)
             const uint8_t* const src = reinterpret_cast<const uint8_t*>(((uint64_t)bhi << 32) | blo) + wb;
             const bool ok = src < text_end && (int32_t)rw[n] >= 0;
+            VK_ASSERT(db <= kTQuads * 16u);                              // quads 0 .. kTQuads - 1 of the warp's buffer, or the slack quad behind it
+            VK_ASSERT(!ok || (src >= text && src + 16 <= text_end));      // the source word lies inside the text allocation
             cp_async16(buf_addr + db, ok ? src : text, ok ? 16u : 0u);
         }
         cp_async_commit();
