@@ -675,9 +675,9 @@ def test_single_pigz_member_through_the_batch_entry(engine, tmp_path):
 
 
 def test_full_size_properties_config3(engine):
-    """BASELINE config 3 shape (1 Gbp, k=9, varKode, -M 0: 11 levels; the 4^9 histogram lives in L2) on device-resident
+    """BASELINE config 3 shape (1 Gbp, k=9, varKode, -M 0: 11 levels; canonical classes in the shared memory of CTA pairs) on device-resident
     synthetic reads: ladder, nesting, reverse-complement symmetry, window conservation, rank-transform invariants, exact
-    agreement with the CPU oracle on a prefix, and exact additivity over read shards."""
+    additivity over read shards, and the WHOLE sample against the CPU oracle (every level, every 9-mer, every pixel)."""
     import torch
     k, L, n_bases = 9, 150, 1_000_000_000
     table = get_kmer_mapping(k, "varKode")
