@@ -151,3 +151,20 @@ def test_remap_plan_matches_oracle(golden_dir, k):
         assert (s0 == e0).all() and (s1 == e1).all() and (mult == em).all()
     with pytest.raises(Exception, match="Input and output mapping must be one of"):
         vm.remap_plan(k, "varKode", "nope")
+
+
+def test_roofline_traffic_is_recorded_per_kernel():
+    """bench.py's ``roofline.traffic`` is looked up by the NAME of the kernel that dominates the workload (round 1 reported the
+    k = 7 kernel's DRAM bytes on the k = 9 line): every kernel a default run can name has its own entry, taken from an ncu
+    capture under profiles/, of the right order of magnitude for its workload (2.1133 text bytes per base)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "profiles", "kernel_traffic.json")) as f:
+        traffic = json.load(f)
+    bases = {"countt_kernel<16>": 200_000_000, "count_kernel<7,smem>": 200_000_000, "countt9_kernel": 1_000_000_000,
+             "count9h_kernel": 1_000_000_000}
+    for name, n in bases.items():
+        ent = traffic[name]
+        assert ent["dram_bytes_per_launch"] == ent["read"] + ent["write"]
+        assert 0.8 <= ent["dram_bytes_per_launch"] / (n * 2.1133) <= 1.1, name
+        src = ent["source"].split(" ")[0]
+        assert os.path.exists(os.path.join(root, src)), src
